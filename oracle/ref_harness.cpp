@@ -1,0 +1,470 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (checker + CPU baseline; never on the product path).
+//
+// C-ABI harness around the UNMODIFIED reference classes (imkaywu/MVSKit, compiled from
+// /root/reference by oracle/Makefile against oracle/shim/*).  Everything below calls the
+// reference's own member functions; nothing re-implements them.  Where the reference keeps a
+// value in a local variable (the pyramid level chosen inside Optim::getTex, optim.cpp:807-811)
+// the harness re-derives it with the reference's own project()/myPow2 calls and says so.
+//
+// Used by: tests/ (parity), tests/golden/make_golden.py (fixture generation),
+//          bench.py --impl reference and bench.py's cpu_baseline leg.
+#include <cmath>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <list>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <queue>
+#include <sstream>
+#include <string>
+#include <vector>
+
+// Access to Optim's per-view axes / scratch (declared protected in optim.hpp:118-139).  Member
+// layout does not depend on access specifiers, and every reference TU is built without this.
+#define protected public
+#define private public
+#include "pmmvps/pmmvps.hpp"
+#undef protected
+#undef private
+#include "nlopt.hpp"
+
+using Eigen::Vector3f;
+using Eigen::Vector4f;
+
+namespace {
+
+struct NullBuf : public std::streambuf {
+    int overflow(int c) override { return c; }
+};
+NullBuf g_nullbuf;
+std::streambuf* g_cerr_saved = nullptr;
+
+Option* g_option = nullptr;
+PmMvps* g_pm = nullptr;
+
+inline Vector4f v4(const float* p) { return Vector4f(p[0], p[1], p[2], p[3]); }
+
+void fill_patch(Patch& patch, const float* coord, const float* normal, const int* views, int nviews) {
+    patch.m_coord = v4(coord);
+    patch.m_normal = v4(normal);
+    patch.m_images.assign(views, views + nviews);
+}
+
+}  // namespace
+
+extern "C" {
+
+// 1 if an unqualified log(float) in a reference-like TU resolves to the double overload
+// (decides how optim.cpp:808 rounds; see oracle/shim/compat.h).
+int pmref_log_is_double(void) { return sizeof(decltype(log(1.0f))) == sizeof(double) ? 1 : 0; }
+
+void pmref_quiet(int on) {
+    if (on && !g_cerr_saved) g_cerr_saved = std::cerr.rdbuf(&g_nullbuf);
+    if (!on && g_cerr_saved) { std::cerr.rdbuf(g_cerr_saved); g_cerr_saved = nullptr; }
+}
+
+void pmref_shutdown(void) {
+    delete g_pm; g_pm = nullptr;
+    delete g_option; g_option = nullptr;
+}
+
+// Option::init (option.cpp:35) + PmMvps::init (pmmvps.cpp:18).  prefix must end with '/'.
+int pmref_init(const char* prefix, const char* option_name) {
+    pmref_shutdown();
+    pmref_quiet(1);
+    g_option = new Option();
+    g_option->init(prefix, option_name);
+    g_pm = new PmMvps();
+    g_pm->init(*g_option);
+    return 0;
+}
+
+// what: 0 nimages, 1 level, 2 csize, 3 wsize, 4 tau, 5 minImageNum, 6 depth, 7 maxLevel(allocated)
+int pmref_info(int what) {
+    switch (what) {
+        case 0: return g_pm->m_nimages;
+        case 1: return g_pm->m_level;
+        case 2: return g_pm->m_csize;
+        case 3: return g_pm->m_wsize;
+        case 4: return g_pm->m_tau;
+        case 5: return g_pm->m_minImageNumThreshold;
+        case 6: return g_pm->m_depth;
+        case 7: return g_pm->m_level + 3;
+    }
+    return -1;
+}
+
+// what: 0 nccThreshold, 1 nccThresholdBefore, 2 angleThreshold0, 3 angleThreshold1, 4 maxAngleThreshold,
+//       5 quadThreshold, 6 neighborThreshold, 7 neighborThreshold1, 8 neighborThreshold2
+float pmref_threshold(int what) {
+    switch (what) {
+        case 0: return g_pm->m_nccThreshold;
+        case 1: return g_pm->m_nccThresholdBefore;
+        case 2: return g_pm->m_angleThreshold0;
+        case 3: return g_pm->m_angleThreshold1;
+        case 4: return g_pm->m_maxAngleThreshold;
+        case 5: return g_pm->m_quadThreshold;
+        case 6: return g_pm->m_neighborThreshold;
+        case 7: return g_pm->m_neighborThreshold1;
+        case 8: return g_pm->m_neighborThreshold2;
+    }
+    return 0.0f;
+}
+
+void pmref_set_depth(int depth) { g_pm->m_depth = depth; }
+void pmref_set_ncc_thresholds(float ncc, float before) { g_pm->m_nccThreshold = ncc; g_pm->m_nccThresholdBefore = before; }
+
+void pmref_image_dims(int view, int level, int* w, int* h) {
+    *w = g_pm->m_photoSet.getWidth(view, level);
+    *h = g_pm->m_photoSet.getHeight(view, level);
+}
+
+void pmref_grid_dims(int view, int* gw, int* gh) {
+    *gw = g_pm->m_patchManager.m_gwidths[view];
+    *gh = g_pm->m_patchManager.m_gheights[view];
+}
+
+// u8 interleaved RGB of one pyramid level, as built by Image::buildImagePyramid (image.cpp:245-315)
+void pmref_get_image(int view, int level, unsigned char* out) {
+    const std::vector<unsigned char>& img = g_pm->m_photoSet.m_photos[view].m_images[level];
+    std::memcpy(out, img.data(), img.size());
+}
+
+// per-view constants: level-`level` projection (camera.cpp:91-100), centre (:295-308), oaxis (:68-69),
+// Optim axes + ipscale (optim.cpp:43-65)
+void pmref_get_camera(int view, int level, float* P12, float* center4, float* oaxis4, float* xaxis3,
+                      float* yaxis3, float* zaxis3, float* ipscale) {
+    const Photo& ph = g_pm->m_photoSet.m_photos[view];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) P12[r * 4 + c] = ph.m_projections[level](r, c);
+    for (int i = 0; i < 4; ++i) { center4[i] = ph.m_center(i); oaxis4[i] = ph.m_oaxis(i); }
+    for (int i = 0; i < 3; ++i) {
+        xaxis3[i] = g_pm->m_optim.m_xaxes[view](i);
+        yaxis3[i] = g_pm->m_optim.m_yaxes[view](i);
+        zaxis3[i] = g_pm->m_optim.m_zaxes[view](i);
+    }
+    *ipscale = g_pm->m_optim.m_ipscales[view];
+}
+
+void pmref_project(int n, const int* view, const float* coord4, int level, float* out3) {
+    for (int i = 0; i < n; ++i) {
+        const Vector3f ic = g_pm->m_photoSet.project(view[i], v4(coord4 + 4 * i), level);
+        out3[3 * i] = ic(0); out3[3 * i + 1] = ic(1); out3[3 * i + 2] = ic(2);
+    }
+}
+
+// Camera::unproject (camera.cpp:329-337)
+void pmref_unproject(int n, const int* view, const float* icoord3, int level, float* out4) {
+    for (int i = 0; i < n; ++i) {
+        const Vector4f c = g_pm->m_photoSet.m_photos[view[i]].unproject(
+            Vector3f(icoord3[3 * i], icoord3[3 * i + 1], icoord3[3 * i + 2]), level);
+        for (int k = 0; k < 4; ++k) out4[4 * i + k] = c(k);
+    }
+}
+
+void pmref_get_unit(int n, const int* view, const float* coord4, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = g_pm->m_optim.getUnit(view[i], v4(coord4 + 4 * i));
+}
+
+// Optim::getPAxes (optim.cpp:67-84)
+void pmref_get_paxes(int n, const int* view, const float* coord4, const float* normal4, float* px4, float* py4) {
+    for (int i = 0; i < n; ++i) {
+        Vector4f px, py;
+        g_pm->m_optim.getPAxes(view[i], v4(coord4 + 4 * i), v4(normal4 + 4 * i), px, py);
+        for (int k = 0; k < 4; ++k) { px4[4 * i + k] = px(k); py4[4 * i + k] = py(k); }
+    }
+}
+
+// Image::getColor bilinear (image.cpp:448-471)
+void pmref_get_color(int n, const int* view, const float* xy, int level, float* rgb) {
+    for (int i = 0; i < n; ++i) {
+        const Vector3f c = g_pm->m_photoSet.getColor(view[i], xy[2 * i], xy[2 * i + 1], level);
+        rgb[3 * i] = c(0); rgb[3 * i + 1] = c(1); rgb[3 * i + 2] = c(2);
+    }
+}
+
+// PatchManager::setGridsImages cell indices (patch_manager.cpp:223-239); ok[i]=0 when the view is dropped
+void pmref_cells(int n, const int* view, const float* coord4, int* ixy, int* ok) {
+    for (int i = 0; i < n; ++i) {
+        Patch p;
+        p.m_coord = v4(coord4 + 4 * i);
+        std::vector<int> images(1, view[i]);
+        g_pm->m_patchManager.setGridsImages(p, images);
+        ok[i] = p.m_images.empty() ? 0 : 1;
+        Patch q;
+        q.m_coord = p.m_coord;
+        q.m_images.assign(1, view[i]);
+        g_pm->m_patchManager.setGrids(q);     // unclipped index (patch_manager.cpp:241-249)
+        ixy[2 * i] = q.m_grids[0](0); ixy[2 * i + 1] = q.m_grids[0](1);
+    }
+}
+
+// Raw (un-normalised) texture of one hypothesis in one view: Optim::getPAxes in `refview`, then
+// Optim::getTex (optim.cpp:790-844).  flag = getTex's return; level = pyramid level it sampled,
+// re-derived here with the reference's own project()/myPow2 because getTex keeps it local.
+void pmref_get_tex(const float* coord4, const float* normal4, int refview, int view, float* tex, int* flag, int* level) {
+    Optim& op = g_pm->m_optim;
+    const Vector4f coord = v4(coord4), normal = v4(normal4);
+    Vector4f px, py;
+    op.getPAxes(refview, coord, normal, px, py);
+    std::vector<Vector3f> t;
+    *flag = op.getTex(coord, px, py, normal, view, g_pm->m_wsize, t);
+    for (size_t i = 0; i < t.size(); ++i) { tex[3 * i] = t[i](0); tex[3 * i + 1] = t[i](1); tex[3 * i + 2] = t[i](2); }
+    Vector3f center = g_pm->m_photoSet.project(view, coord, g_pm->m_level);
+    Vector3f dx = g_pm->m_photoSet.project(view, coord + px, g_pm->m_level) - center;
+    Vector3f dy = g_pm->m_photoSet.project(view, coord + py, g_pm->m_level) - center;
+    const float ratio = (dx.norm() + dy.norm()) / 2.0f;
+    int levelDiff = (int)floorf(log(ratio) / log(2.0f) + 0.5f);
+    levelDiff = std::max(-g_pm->m_level, std::min(2, levelDiff));
+    *level = g_pm->m_level + levelDiff;
+}
+
+// levelDiff rounding as compiled into this library (optim.cpp:808), for building the product's
+// threshold table test: returns (int)floorf(log(ratio)/log(2.0f)+0.5f) unclamped.
+int pmref_level_diff(float ratio) { return (int)floorf(log(ratio) / log(2.0f) + 0.5f); }
+
+// The "hypothesis NCC eval" unit: PatchManager::computeNcc (patch_manager.cpp:401-404) =
+// Optim::computeWeights (optim.cpp:942-948) + Optim::computeINCC(...,1) (optim.cpp:630-706).
+// views: n rows of `stride` ints, nviews[i] valid per row, [0] = reference view.
+void pmref_compute_ncc(int n, const float* coord4, const float* normal4, const int* views, const int* nviews,
+                       int stride, float* incc, float* ncc) {
+    Patch patch;
+    for (int i = 0; i < n; ++i) {
+        fill_patch(patch, coord4 + 4 * i, normal4 + 4 * i, views + (size_t)i * stride, nviews[i]);
+        g_pm->m_optim.computeWeights(patch);
+        const float s = g_pm->m_optim.computeINCC(patch.m_coord, patch.m_normal, patch.m_images, 1);
+        if (incc) incc[i] = s;
+        if (ncc) ncc[i] = 1.0f - g_pm->m_optim.unrobustincc(s);
+    }
+}
+
+// Same loop, timed (seconds).  Output is accumulated so the work cannot be elided.
+double pmref_time_compute_ncc(int n, const float* coord4, const float* normal4, const int* views, const int* nviews,
+                              int stride, int repeats, double* checksum) {
+    Patch patch;
+    double acc = 0.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < repeats; ++r) {
+        for (int i = 0; i < n; ++i) {
+            fill_patch(patch, coord4 + 4 * i, normal4 + 4 * i, views + (size_t)i * stride, nviews[i]);
+            g_pm->m_optim.computeWeights(patch);
+            acc += g_pm->m_optim.computeINCC(patch.m_coord, patch.m_normal, patch.m_images, 1);
+        }
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (checksum) *checksum = acc;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Optim::computeWeights (optim.cpp:942-948) -> m_weights[0..nviews)
+void pmref_weights(const float* coord4, const float* normal4, const int* views, int nviews, float* w) {
+    Patch patch;
+    fill_patch(patch, coord4, normal4, views, nviews);
+    g_pm->m_optim.computeWeights(patch);
+    for (int i = 0; i < nviews; ++i) w[i] = g_pm->m_optim.m_weights[i];
+}
+
+// Optim::setINCCs 1-vs-all (optim.cpp:708-746)
+void pmref_set_inccs(const float* coord4, const float* normal4, const int* views, int nviews, int robust, float* out) {
+    Patch patch;
+    fill_patch(patch, coord4, normal4, views, nviews);
+    std::vector<float> inccs;
+    std::vector<int> idx(views, views + nviews);
+    g_pm->m_optim.setINCCs(patch, inccs, idx, robust);
+    for (int i = 0; i < nviews; ++i) out[i] = inccs[i];
+}
+
+// Optim::setINCCs pairwise (optim.cpp:748-783); out is nviews x nviews row-major
+void pmref_set_inccs_pair(const float* coord4, const float* normal4, const int* views, int nviews, int robust, float* out) {
+    Patch patch;
+    fill_patch(patch, coord4, normal4, views, nviews);
+    std::vector<std::vector<float> > inccs;
+    std::vector<int> idx(views, views + nviews);
+    g_pm->m_optim.setINCCs(patch, inccs, idx, robust);
+    for (int i = 0; i < nviews; ++i) for (int j = 0; j < nviews; ++j) out[i * nviews + j] = inccs[i][j];
+}
+
+// ---- patch record marshalling for the multi-step functions ----------------------------------------
+// A "patch record" crosses this ABI as: coord4, normal4, scal[4] = {ncc, dscale, ascale, tmp},
+// images[maxv] + nimages, grids[2*maxv], vimages[maxv] + nvimages, vgrids[2*maxv].
+struct PatchIO {
+    float* coord4; float* normal4; float* scal4;
+    int* images; int* nimages; int* grids;
+    int* vimages; int* nvimages; int* vgrids;
+    int maxv;
+};
+
+static void patch_out(const Patch& p, const PatchIO& io, int i) {
+    for (int k = 0; k < 4; ++k) { io.coord4[4 * i + k] = p.m_coord(k); io.normal4[4 * i + k] = p.m_normal(k); }
+    io.scal4[4 * i] = p.m_ncc; io.scal4[4 * i + 1] = p.m_dscale; io.scal4[4 * i + 2] = p.m_ascale; io.scal4[4 * i + 3] = p.m_tmp;
+    const int ni = std::min((int)p.m_images.size(), io.maxv);
+    io.nimages[i] = (int)p.m_images.size();
+    for (int k = 0; k < ni; ++k) {
+        io.images[(size_t)i * io.maxv + k] = p.m_images[k];
+        if (k < (int)p.m_grids.size()) {
+            io.grids[((size_t)i * io.maxv + k) * 2] = p.m_grids[k](0);
+            io.grids[((size_t)i * io.maxv + k) * 2 + 1] = p.m_grids[k](1);
+        }
+    }
+    const int nv = std::min((int)p.m_vimages.size(), io.maxv);
+    io.nvimages[i] = (int)p.m_vimages.size();
+    for (int k = 0; k < nv; ++k) {
+        io.vimages[(size_t)i * io.maxv + k] = p.m_vimages[k];
+        if (k < (int)p.m_vgrids.size()) {
+            io.vgrids[((size_t)i * io.maxv + k) * 2] = p.m_vgrids[k](0);
+            io.vgrids[((size_t)i * io.maxv + k) * 2 + 1] = p.m_vgrids[k](1);
+        }
+    }
+}
+
+// Optim::preProcess (optim.cpp:137-163) on fresh patches {coord, normal, images}; ret[i] = its return.
+// Output record = the patch after the call (m_images order, m_dscale/m_ascale from setScales).
+void pmref_pre_process(int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride,
+                       int* ret, PatchIO* out) {
+    for (int i = 0; i < n; ++i) {
+        Patch patch;
+        fill_patch(patch, coord4 + 4 * i, normal4 + 4 * i, views + (size_t)i * stride, nviews[i]);
+        ret[i] = g_pm->m_optim.preProcess(patch);
+        patch_out(patch, *out, i);
+    }
+}
+
+// PMR1 refinement stream/seed (oracle/shim/nlopt.hpp)
+void pmref_refine_seed(unsigned long long seed) { pmr1::state().seed = seed; }
+void pmref_refine_stream(unsigned long long stream) { pmr1::state().stream = stream; }
+
+// Optim::refinePatch (optim.cpp:470-547) on patches whose images/dscale are already set (post-preProcess).
+// trace (optional): 97 * 4 doubles per patch = every evaluated {x0,x1,x2,f}.
+void pmref_refine(int n, float* coord4, float* normal4, const float* dscale, const int* views, const int* nviews, int stride,
+                  const unsigned long long* streams, float* ncc_out, double* trace) {
+    std::vector<double> tr;
+    for (int i = 0; i < n; ++i) {
+        Patch patch;
+        fill_patch(patch, coord4 + 4 * i, normal4 + 4 * i, views + (size_t)i * stride, nviews[i]);
+        patch.m_dscale = dscale[i];
+        pmr1::state().stream = streams[i];
+        tr.clear();
+        pmr1::state().trace = trace ? &tr : nullptr;
+        g_pm->m_optim.refinePatch(patch, 100);
+        pmr1::state().trace = nullptr;
+        for (int k = 0; k < 4; ++k) { coord4[4 * i + k] = patch.m_coord(k); normal4[4 * i + k] = patch.m_normal(k); }
+        ncc_out[i] = patch.m_ncc;
+        if (trace) for (size_t k = 0; k < tr.size() && k < 97 * 4; ++k) trace[(size_t)i * 97 * 4 + k] = tr[k];
+    }
+}
+
+// Optim::cost_func (optim.cpp:401-468) at given encoded points, for a patch context set up exactly as
+// refinePatch does (:481-490).  x: n x 3 doubles.
+void pmref_cost_func(const float* coord4, const float* normal4, float dscale, const int* views, int nviews,
+                     int n, const double* x, double* cost) {
+    Optim& op = g_pm->m_optim;
+    Patch patch;
+    fill_patch(patch, coord4, normal4, views, nviews);
+    op.m_center = patch.m_coord;
+    op.m_ray = patch.m_coord - g_pm->m_photoSet.m_photos[patch.m_images[0]].m_center;
+    op.m_ray /= op.m_ray.norm();
+    op.m_indexes = patch.m_images;
+    op.m_dscale = dscale;
+    op.m_ascale = M_PI / 48.0f;
+    for (int i = 0; i < n; ++i) cost[i] = Optim::cost_func(3, x + 3 * i, nullptr, nullptr);
+}
+
+// Optim::encode / decode (optim.cpp:549-599) in the same context
+void pmref_encode(const float* coord4, const float* normal4, float dscale, int refview, double* x3) {
+    Optim& op = g_pm->m_optim;
+    op.m_center = v4(coord4);
+    op.m_ray = op.m_center - g_pm->m_photoSet.m_photos[refview].m_center;
+    op.m_ray /= op.m_ray.norm();
+    op.m_indexes.assign(1, refview);
+    op.m_dscale = dscale;
+    op.m_ascale = M_PI / 48.0f;
+    op.encode(v4(coord4), v4(normal4), x3);
+}
+
+// Optim::postProcess (optim.cpp:260-298) on patches in their post-refine state.
+void pmref_post_process(int n, const float* coord4, const float* normal4, const float* scal4, const int* views, const int* nviews,
+                        int stride, int* ret, PatchIO* out) {
+    for (int i = 0; i < n; ++i) {
+        Patch patch;
+        fill_patch(patch, coord4 + 4 * i, normal4 + 4 * i, views + (size_t)i * stride, nviews[i]);
+        patch.m_ncc = scal4[4 * i]; patch.m_dscale = scal4[4 * i + 1]; patch.m_ascale = scal4[4 * i + 2];
+        ret[i] = g_pm->m_optim.postProcess(patch);
+        patch_out(patch, *out, i);
+    }
+}
+
+// ---- patch store -------------------------------------------------------------------------------------
+void pmref_clear_patches(void) { g_pm->m_patchManager.init(); }
+
+// PatchManager::addPatch (patch_manager.cpp:158-189) after setGrids (:241-249); like readPatches (:450-462)
+void pmref_add_patches(int n, const float* coord4, const float* normal4, const float* scal4, const int* views, const int* nviews, int stride) {
+    for (int i = 0; i < n; ++i) {
+        Ppatch pp(new Patch());
+        fill_patch(*pp, coord4 + 4 * i, normal4 + 4 * i, views + (size_t)i * stride, nviews[i]);
+        pp->m_ncc = scal4[4 * i]; pp->m_dscale = scal4[4 * i + 1]; pp->m_ascale = scal4[4 * i + 2];
+        pp->m_tmp = pp->score2(g_pm->m_nccThreshold);
+        g_pm->m_patchManager.setGrids(*pp);
+        g_pm->m_patchManager.addPatch(pp);
+    }
+}
+
+// DepthNormInit::createPatches (depth_normal_init.cpp:29-33) -> readPatches of <prefix>ply/00000000.patch
+void pmref_create_patches(void) { g_pm->m_dnInit.createPatches(); }
+
+// PatchManager::collectPatches(target) (patch_manager.cpp:75-104); returns count
+int pmref_collect(int target) {
+    g_pm->m_patchManager.collectPatches(target);
+    return (int)g_pm->m_patchManager.m_ppatches.size();
+}
+
+void pmref_get_patches(PatchIO* out) {
+    const std::vector<Ppatch>& pp = g_pm->m_patchManager.m_ppatches;
+    for (size_t i = 0; i < pp.size(); ++i) patch_out(*pp[i], *out, (int)i);
+}
+
+// m_dpgrids of one view as m_ppatches ids (-1 = m_MAXDEPTH); requires a prior pmref_collect
+void pmref_get_depth_map(int view, int* ids) {
+    const std::vector<Ppatch>& g = g_pm->m_patchManager.m_dpgrids[view];
+    for (size_t i = 0; i < g.size(); ++i) ids[i] = (g[i] == PatchManager::m_MAXDEPTH) ? -1 : g[i]->m_id;
+}
+
+// cell occupancy counts of m_pgrids / m_vpgrids for one view
+void pmref_get_cell_counts(int view, int which, int* counts) {
+    const std::vector<std::vector<Ppatch> >& g = which ? g_pm->m_patchManager.m_vpgrids[view] : g_pm->m_patchManager.m_pgrids[view];
+    for (size_t i = 0; i < g.size(); ++i) counts[i] = (int)g[i].size();
+}
+
+// Propagate::run (propagate.cpp:28-64): the reference's own raster Gauss-Seidel sweep, unmodified
+void pmref_propagate_run(int iter) { g_pm->m_propagate.run(iter); }
+// Filter::run (filter.cpp:25-49)
+void pmref_filter_run(void) { g_pm->m_filter.run(); }
+
+// Filter::computeGain (filter.cpp:108-146) for every collected patch (call pmref_collect first)
+void pmref_gains(float* gains) {
+    const std::vector<Ppatch>& pp = g_pm->m_patchManager.m_ppatches;
+    for (size_t i = 0; i < pp.size(); ++i) gains[i] = g_pm->m_filter.computeGain(*pp[i]);
+}
+
+// PmMvps::isNeighbor (pmmvps.cpp:117-147) between collected patches a[i], b[i]
+void pmref_is_neighbor(int n, const int* a, const int* b, float thr, int* out) {
+    const std::vector<Ppatch>& pp = g_pm->m_patchManager.m_ppatches;
+    for (int i = 0; i < n; ++i) out[i] = g_pm->isNeighbor(*pp[a[i]], *pp[b[i]], thr);
+}
+
+// PmMvps::run (pmmvps.cpp:76-114), unmodified; returns wall seconds; *alive = patches after the last Filter::run
+double pmref_run(int* alive) {
+    const auto t0 = std::chrono::steady_clock::now();
+    g_pm->run();
+    const auto t1 = std::chrono::steady_clock::now();
+    g_pm->m_patchManager.collectPatches(0);
+    if (alive) *alive = (int)g_pm->m_patchManager.m_ppatches.size();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
