@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- hypothesis-NCC throughput of the PM-MVS hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path (K1: PatchManager::computeNcc-equivalent, optim.cpp:630-706) over one
+batch of 2^20 synthetic hypotheses on the templeRing-shaped scene (BASELINE.json configs[1]: 47 views 640x480,
+tau = 6 views per eval, 7x7 RGB lattice).  N > 1 shards hypotheses across ranks (no data-path collective:
+the evals are independent; images are replicated), so scaling is weak.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the product (CUDA, through the C ABI)
+    python bench.py --impl reference ...                           # the reference's own CPU code, host cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job evals/s with inputs resident in HBM (CUDA events on the
+launching stream, L2 flushed between steps, max over ranks); `e2e` = the same metric through the host-buffer
+C-ABI call (pinned host inputs, H2D and D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_EVAL = 4692.0     # 6 views x 64 texels x 3 ch x 4 B + 84 B patch I/O
+METRIC = "hypothesis_ncc_evals_per_sec"
+UNIT = "evals/s"
+WORKLOAD = "config2 templeRing-shaped synthetic scene: 47 views 640x480, 2^20 hypotheses/step/GPU around GT, tau=6, 7x7 RGB"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------
+def scene_cache_dir():
+    d = os.path.join(tempfile.gettempdir(), "pmk_bench_cache")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def get_scene(config: int, scale: float):
+    """Render (or load the cached render of) the synthetic scene; deterministic, so every rank agrees."""
+    from mvskit_b200 import synth
+    scene = synth.make_scene(config, scale=scale)
+    path = os.path.join(scene_cache_dir(), f"scene_c{config}_s{scale:g}.npy")
+    if os.path.exists(path):
+        arr = np.load(path)
+        scene.images = [arr[v] for v in range(arr.shape[0])]
+    else:
+        scene.render()
+        tmp = path + f".{os.getpid()}.tmp.npy"
+        np.save(tmp, np.stack(scene.images))
+        os.replace(tmp, path)
+    return scene
+
+
+def get_hypotheses(scene, n: int, seed: int, config: int, scale: float):
+    path = os.path.join(scene_cache_dir(), f"hyp_c{config}_s{scale:g}_n{n}_seed{seed}.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return z["c"], z["n"], z["v"], z["nv"]
+    c, nrm, vw, nv = scene.hypotheses(n, seed=seed)
+    tmp = path + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, c=c, n=nrm, v=vw, nv=nv)
+    os.replace(tmp, path)
+    return c, nrm, vw, nv
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        for t, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(parts[1])); smax = max(smax, float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arms (the only places bench.py executes anything under oracle/)
+# ------------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    prefix, c, n, vw, nv = args
+    from oracle.pyoracle import RefLib
+    ref = RefLib(prefix)
+    return ref.time_compute_ncc(c, n, vw, nv, 1)
+
+
+def ensure_scene_dir(scene, config, scale):
+    from mvskit_b200 import synth
+    d = os.path.join(scene_cache_dir(), f"dir_c{config}_s{scale:g}")
+    if not os.path.exists(os.path.join(d, "option")):
+        tmp = d + f".{os.getpid()}.tmp"
+        synth.write_scene(scene, tmp, with_seeds=False)
+        try:
+            os.replace(tmp, d)
+        except OSError:
+            pass
+    return d + "/"
+
+
+def cpu_reference_evals_per_sec(scene, config, scale, hyp, cores: int, sample: int):
+    """Time the reference's own computeNcc loop (oracle/_ref/libpmref.so) on `cores` processes, `sample` evals each."""
+    from oracle import pyoracle
+    kind = "reference" if os.path.exists(pyoracle.REF_SO) else "port"
+    c, n, vw, nv = (a[: sample * cores] for a in hyp)
+    if kind == "reference":
+        prefix = ensure_scene_dir(scene, config, scale)
+        jobs = [(prefix, c[i::cores], n[i::cores], vw[i::cores], nv[i::cores]) for i in range(cores)]
+        if cores == 1:
+            secs = [_ref_worker(jobs[0])]
+        else:
+            import multiprocessing as mp
+            with mp.get_context("spawn").Pool(cores) as pool:
+                secs = pool.map(_ref_worker, jobs)
+        return len(c) / max(secs), kind
+    pyoracle.build(ref=False)
+    orc = pyoracle.COracle(scene.P, scene.images)
+    t0 = time.time()
+    orc.compute_ncc(c[:sample], n[:sample], vw[:sample], nv[:sample])
+    return sample / (time.time() - t0), kind
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pmk", choices=["pmk", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="hypotheses per step per GPU")
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="evals in the cpu_baseline sample (1 core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    n_gpus = max(args.gpus, world)
+    warmup = max(args.warmup, 3) if args.impl == "pmk" else args.warmup
+    config = {"workload": WORKLOAD if (args.config == 2 and args.scale == 1.0 and args.batch == 1 << 20) else
+              f"config{args.config} scale {args.scale:g}, {args.batch} hypotheses/step/GPU", "views_per_eval": 6,
+              "hypotheses_per_step_per_gpu": args.batch, "sharding": "hypotheses split across ranks, images replicated, no collective",
+              "l2": "flushed (256 MiB memset) before every timed step"}
+
+    # ---------------- reference arm: the reference's own CPU code on the host cores ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        scene = get_scene(args.config, args.scale)
+        cores = os.cpu_count() or 1
+        per_core = max(1, min(args.batch // cores, 65536))          # bounded sample per step
+        hyp = get_hypotheses(scene, args.batch, 7, args.config, args.scale)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, kind = cpu_reference_evals_per_sec(scene, args.config, args.scale, hyp, cores, per_core)
+            if i >= args.warmup:
+                vals.append(v)
+        value = float(np.mean(vals))
+        sample = f"{per_core * cores} of the {args.batch} hypotheses per step ({per_core} per process x {cores} processes)"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * per_core * cores / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- product arm ----------------
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    from mvskit_b200 import pmk
+
+    if local_rank == 0 or world == 1:
+        scene = get_scene(args.config, args.scale)
+    if dist:
+        dist.barrier()
+        if local_rank != 0:
+            scene = get_scene(args.config, args.scale)
+    hyp = get_hypotheses(scene, args.batch, 7 + rank, args.config, args.scale)
+    c, n, vw, nv = hyp
+    N = len(c)
+
+    ctx = pmk.Context(nviews=scene.nviews, device=local_rank)
+    ctx.set_scene(scene.P, scene.images)
+    launches0 = ctx.launch_count()
+
+    # device-resident inputs for `value`
+    d_c, d_n, d_v, d_nv = ctx.alloc(c.nbytes).upload(c), ctx.alloc(n.nbytes).upload(n), ctx.alloc(vw.nbytes).upload(vw), ctx.alloc(nv.nbytes).upload(nv)
+    d_incc, d_ncc = ctx.alloc(N * 4), ctx.alloc(N * 4)
+    # pinned host inputs/outputs for `e2e`
+    h_c, h_n, h_v, h_nv = (pmk.pinned_empty(a.shape, a.dtype) for a in (c, n, vw, nv))
+    h_c[:], h_n[:], h_v[:], h_nv[:] = c, n, vw, nv
+    h_incc, h_ncc = pmk.pinned_empty((N,), np.float32), pmk.pinned_empty((N,), np.float32)
+    ctx.sync()
+
+    def barrier():
+        ctx.sync()
+        if dist:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def step_dev():
+        ctx.ncc_eval_dev(N, d_c, d_n, d_v, d_nv, vw.shape[1], d_incc, d_ncc)
+
+    def step_e2e():
+        pmk._chk(pmk.lib().pmk_ncc_eval(ctx.h, N, pmk._p(h_c), pmk._p(h_n), pmk._p(h_v), pmk._p(h_nv), vw.shape[1], pmk._p(h_incc), pmk._p(h_ncc), None))
+
+    for _ in range(warmup):
+        step_dev()
+    step_e2e()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    # ---- timed: K device-resident steps ----
+    barrier()
+    t_wall0 = time.time()
+    ms_steps = []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_begin()
+        step_dev()
+        ms_steps.append(ctx.timer_end())
+    barrier()
+    t_wall1 = time.time()
+    launches_timed = ctx.launch_count() - launches0 - warmup - 1
+    # ---- timed: K end-to-end steps (host buffers, copies inside) ----
+    e2e_ms = []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.sync()
+        t0 = time.perf_counter()
+        step_e2e()                      # returns after the D2H landed
+        e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    barrier()
+    clocks = sampler.stop(t_wall0, time.time())
+
+    total_ms, total_e2e = float(sum(ms_steps)), float(sum(e2e_ms))
+    if dist:
+        import torch
+        t = torch.tensor([total_ms, total_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, total_e2e = float(t[0]), float(t[1])
+    evals = float(N) * args.steps * world
+    value = evals / (total_ms * 1e-3)
+    e2e_value = evals / (total_e2e * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        per_gpu = value / world
+        achieved = per_gpu * ALGO_BYTES_PER_EVAL / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches_timed),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c.nbytes + n.nbytes + vw.nbytes + nv.nbytes),
+                    "d2h_bytes_per_step": int(2 * N * 4), "ms_per_step": total_e2e / args.steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k1_ncc<7>", "algorithmic_bytes_per_eval": ALGO_BYTES_PER_EVAL, "peak_source": peak_src,
+                         "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, kind = cpu_reference_evals_per_sec(scene, args.config, args.scale, hyp, 1, min(args.cpu_sample, N))
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                                   "sample": f"first {min(args.cpu_sample, N)} hypotheses of the step's batch, PatchManager::computeNcc loop, 1 process"}
+        print(json.dumps(out))
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+/* include/pmk.h -- C ABI of the B200-native PatchMatch-MVS hot path ("pmk").
+ *
+ * Drop-in boundary for imkaywu/MVSKit's PM-MVS inner loop.  The reference has no FFI layer; its
+ * boundary is the C++ class surface (PmMvps / Option / PatchManager / Patch).  The host-side mirror
+ * of those classes lives in mvskit_b200/host/ and calls ONLY the functions below, each of which
+ * replaces the reference member functions cited next to it (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative pmk_status; pmk_last_error() describes the
+ *     last failure on the calling thread.  No exceptions cross this boundary.
+ *   - One pmk_ctx per GPU.  Calls on a context are serialised by the caller and are stream-ordered
+ *     on the context's CUDA stream; functions taking HOST pointers return after their results are
+ *     in the caller's buffers; `_dev` variants take DEVICE pointers and only enqueue work.
+ *   - The caller owns all host buffers; the context owns all device memory it allocates.
+ *   - No CPU fallback exists: without a CUDA device pmk_create fails (PMK_ERR_CUDA).
+ *   - Layouts: coord/normal are float[4] per item (x,y,z,w) like Eigen::Vector4f in Patch
+ *     (pmmvps/patch.hpp:33-35); view lists are rows of `stride` ints, [0] = reference image
+ *     (Patch::m_images, patch.hpp:38), entries past nviews[i] ignored.
+ */
+#ifndef PMK_H
+#define PMK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMK_ABI_VERSION 1
+#define PMK_MAX_LEVELS 6
+#define PMK_MAX_TAU 8
+
+typedef enum pmk_status {
+    PMK_OK = 0,
+    PMK_ERR_ARG = -1,      /* bad argument (the reference would exit(1) or index out of range)   */
+    PMK_ERR_CUDA = -2,     /* CUDA runtime failure, or no device                                   */
+    PMK_ERR_STATE = -3,    /* call order violated (e.g. evaluating before every view is uploaded)  */
+    PMK_ERR_CAPACITY = -4  /* a fixed-capacity device structure overflowed                         */
+} pmk_status;
+
+typedef struct pmk_ctx pmk_ctx;
+
+/* Scalars of Option (pmmvps/option.hpp:20-73, defaults option.cpp:19-33) that the path consumes;
+ * PmMvps::init derives the remaining thresholds from them exactly as pmmvps.cpp:32,54-67. */
+typedef struct pmk_config {
+    int device;                 /* CUDA device ordinal                                             */
+    int nviews;                 /* Option::m_nimages                                               */
+    int level;                  /* Option::m_level   (working pyramid level; level+3 are built)    */
+    int csize;                  /* Option::m_csize                                                 */
+    int wsize;                  /* Option::m_wsize   (5, 7, 9 or 11)                               */
+    int min_image_num;          /* Option::m_minImageNum                                           */
+    float ncc_threshold;        /* Option::m_nccThreshold                                          */
+    float max_angle_threshold;  /* Option::m_maxAngleThreshold, radians                            */
+    float quad_threshold;       /* Option::m_quadThreshold                                         */
+    int max_patches;            /* capacity of the device patch store; 0 = 8 per cell of all views */
+} pmk_config;
+
+/* Thresholds held by PmMvps (pmmvps/pmmvps.hpp:36-87); read back for parity checks. */
+typedef struct pmk_thresholds {
+    int tau, depth;
+    float ncc_threshold, ncc_threshold_before;
+    float angle_threshold0, angle_threshold1, max_angle_threshold, quad_threshold;
+    float neighbor_threshold, neighbor_threshold1, neighbor_threshold2;
+} pmk_thresholds;
+
+/* Per-view constants the device uses, as derived by the host side of the library. */
+typedef struct pmk_camera {
+    float P[12];        /* level-`level` projection, row-major 3x4 (image/camera.cpp:91-100)        */
+    float center[4];    /* Camera::getCameraCenter                       (camera.cpp:295-308)       */
+    float oaxis[4];     /* Camera::m_oaxis                               (camera.cpp:68-69)         */
+    float xaxis[3], yaxis[3], zaxis[3];   /* Optim::m_xaxes/m_yaxes/m_zaxes (optim.cpp:43-54)        */
+    float ipscale;      /* Optim::m_ipscales                             (optim.cpp:56-64)          */
+} pmk_camera;
+
+void pmk_default_config(pmk_config* cfg);                   /* Option::Option   (option.cpp:19-33)  */
+int pmk_create(const pmk_config* cfg, pmk_ctx** out);       /* PmMvps::init     (pmmvps.cpp:18-68)  */
+void pmk_destroy(pmk_ctx* ctx);
+const char* pmk_last_error(void);
+int pmk_abi_version(void);
+
+/* Photo::init + Image::alloc + buildImagePyramid for one view (image/photoSet.cpp:20-61,
+ * image/camera.cpp:27-100, image/image.cpp:92-192,245-315).  `P` is the level-0 3x4 projection
+ * ("CONTOUR" camera file), `rgb` interleaved u8 of width*height*3.  Builds the level+3 level
+ * pyramid on the device (kernel K0) as float RGBX texels holding the u8-rounded values. */
+int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int width, int height);
+
+int pmk_get_thresholds(pmk_ctx* ctx, pmk_thresholds* out);
+int pmk_set_depth(pmk_ctx* ctx, int depth);                 /* PmMvps::m_depth (pmmvps.hpp:61)      */
+int pmk_update_threshold(pmk_ctx* ctx);                     /* PmMvps::updateThreshold + ++m_depth (pmmvps.cpp:70-74,106) */
+int pmk_get_camera(pmk_ctx* ctx, int view, int level, pmk_camera* out);
+int pmk_get_level_dims(pmk_ctx* ctx, int view, int level, int* width, int* height); /* Image::getWidth/getHeight */
+int pmk_get_grid_dims(pmk_ctx* ctx, int view, int* gwidth, int* gheight);  /* PatchManager::m_gwidths/m_gheights (patch_manager.cpp:36-37) */
+int pmk_get_level_image(pmk_ctx* ctx, int view, int level, uint8_t* rgb_out);       /* Image::m_images[level] */
+
+/* K1 -- the "hypothesis NCC eval" unit: PatchManager::computeNcc (patch_manager.cpp:401-404) =
+ * Optim::computeWeights (optim.cpp:942-948) + Optim::computeINCC(coord, normal, images, 1)
+ * (optim.cpp:630-706) with getPAxes / getTex / getTexSafe / normalize / dot / robustincc inside.
+ *   incc_out[i]   : computeINCC's return (2.0f = invalid sentinel)
+ *   ncc_out[i]    : 1.0f - unrobustincc(incc)                  (may be NULL)
+ *   levels_out    : n x tau ints, pyramid level each view was sampled at, -1 where getTex
+ *                   returned -1 or the slot is unused              (may be NULL)
+ * Host-pointer variant: copies inputs H2D, runs, copies results D2H, returns when they landed. */
+int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views,
+                 const int* nviews, int stride, float* incc_out, float* ncc_out, int* levels_out);
+/* Device-pointer variant: enqueues on the context stream and returns. */
+int pmk_ncc_eval_dev(pmk_ctx* ctx, int n, const void* d_coord4, const void* d_normal4, const void* d_views,
+                     const void* d_nviews, int stride, void* d_incc_out, void* d_ncc_out, void* d_levels_out);
+
+/* Probes of the device-side building blocks, for parity tests (each item independent):
+ *   project  : Camera::project at the working level        (camera.cpp:310-326)   -> out3
+ *   unit     : Optim::getUnit                              (optim.cpp:34-41)      -> out1
+ *   paxes    : Optim::getPAxes                             (optim.cpp:67-84)      -> px4, py4
+ *   cell     : PatchManager::setGrids index + in-grid flag (patch_manager.cpp:223-249) -> ixy2, ok */
+int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const float* normal4,
+              float* project3, float* unit1, float* px4, float* py4, int* cell_ixy2, int* cell_ok);
+
+/* Stream control / timing helpers for bench.py (no reference counterpart). */
+int pmk_sync(pmk_ctx* ctx);
+int pmk_device_alloc(pmk_ctx* ctx, uint64_t bytes, void** out);
+int pmk_device_free(pmk_ctx* ctx, void* p);
+int pmk_memcpy_h2d(pmk_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int pmk_memcpy_d2h(pmk_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int pmk_host_alloc_pinned(uint64_t bytes, void** out);
+int pmk_host_free_pinned(void* p);
+/* CUDA-event timer on the context stream: begin, ..., end -> milliseconds */
+int pmk_timer_begin(pmk_ctx* ctx);
+int pmk_timer_end(pmk_ctx* ctx, float* ms);
+/* number of kernel launches issued by this context since creation */
+int pmk_launch_count(pmk_ctx* ctx, uint64_t* out);
+/* write at least `bytes` of device memory to evict L2 between timed iterations */
+int pmk_flush_l2(pmk_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMK_H */

@@ -1,0 +1,52 @@
+"""Build mvskit_b200/libpmk.so (the C-ABI shared library) for sm_100a with nvcc.
+
+In-tree build: the .so is git-ignored but travels with the repository snapshot to the GPU box.
+nvcc cross-compiles without a GPU, so this also runs in the CPU-only build container.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libpmk.so")
+SOURCES = ["pmk_api.cu"]
+HEADERS = ["pmk_device.cuh", "pmk_ncc.cuh", os.path.join("..", "..", "include", "pmk.h")]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(CSRC, "pmk_exports.map"), __file__]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return OUT
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v" if verbose else "-warn-spills",
+           "-shared", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + \
+          ["-Xlinker", "--version-script=" + os.path.join(CSRC, "pmk_exports.map")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libpmk.so")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

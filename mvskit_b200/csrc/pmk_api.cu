@@ -1,0 +1,556 @@
+// mvskit_b200/csrc/pmk_api.cu -- C ABI (include/pmk.h): context, per-view constants, kernel launches.
+//
+// Host-side float math in this file (camera constants, level table) follows the same operation order as
+// the reference; the file is compiled with -Xcompiler -ffp-contract=off so x86 never fuses it.
+#include <cmath>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pmk_ncc.cuh"
+
+using namespace pmk;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess) return fail(PMK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- host copies of the reference's small linear algebra (left-to-right, one rounding per op) ----------
+inline float hdot3(const float* a, const float* b) { float acc = a[0] * b[0]; acc = acc + a[1] * b[1]; acc = acc + a[2] * b[2]; return acc; }
+inline float hdot4(const float* a, const float* b) { float acc = a[0] * b[0]; acc = acc + a[1] * b[1]; acc = acc + a[2] * b[2]; acc = acc + a[3] * b[3]; return acc; }
+inline float hnorm3(const float* a) { return std::sqrt(hdot3(a, a)); }
+inline void hcross3(const float* a, const float* b, float* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// adjugate / determinant, cofactor expansion along the first row
+inline void hinv3(const float* m, float* r) {
+    const float c00 = m[4] * m[8] - m[5] * m[7];
+    const float c01 = m[5] * m[6] - m[3] * m[8];
+    const float c02 = m[3] * m[7] - m[4] * m[6];
+    const float det = (m[0] * c00 + m[1] * c01) + m[2] * c02;
+    r[0] = c00 / det;
+    r[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+    r[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+    r[3] = c01 / det;
+    r[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+    r[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+    r[6] = c02 / det;
+    r[7] = (m[1] * m[6] - m[0] * m[7]) / det;
+    r[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+}
+
+// (int)floorf(log(ratio) / log(2.0f) + 0.5f) with the unqualified log resolving to double (optim.cpp:808)
+inline int level_diff_host(float ratio) {
+    const double v = std::log((double)ratio) / std::log((double)2.0f) + (double)0.5f;
+    const float fv = (float)v;
+    if (!(fv > -1.0e9f)) return INT_MIN;
+    return (int)std::floor(fv);
+}
+
+// smallest float r with level_diff_host(r) >= k
+float level_threshold(int k) {
+    float r = std::exp2f((float)k - 0.5f);
+    for (int guard = 0; guard < 64 && level_diff_host(r) >= k; ++guard) r = std::nextafterf(r, 0.0f);
+    for (int guard = 0; guard < 128 && level_diff_host(r) < k; ++guard) r = std::nextafterf(r, INFINITY);
+    return r;
+}
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct pmk_ctx {
+    pmk_config cfg;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    Params params;
+    std::vector<ViewConst> h_views;          // working-level constants (device mirror in d_views)
+    std::vector<std::vector<float> > P_all;  // per view: nlevels * 12
+    std::vector<char> view_set;
+    std::vector<void*> owned;                // every device allocation of the context
+    ViewConst* d_views = nullptr;
+    bool views_dirty = true;
+    Scratch s_coord, s_normal, s_views, s_nviews, s_incc, s_ncc, s_levels, s_misc[8];
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    uint64_t launches = 0;
+    bool k1_attr_done = false;
+    // PmMvps thresholds (pmmvps.cpp:54-67)
+    float angle_threshold0, angle_threshold1, neighbor_threshold, neighbor_threshold1, neighbor_threshold2;
+    float ncc_threshold, ncc_threshold_before;
+    int depth = 0;
+};
+
+namespace {
+
+int ensure(pmk_ctx* ctx, Scratch& s, size_t bytes) {
+    if (bytes <= s.cap) return PMK_OK;
+    if (s.p) CUDA_TRY(cudaFree(s.p));
+    s.p = nullptr; s.cap = 0;
+    const size_t cap = bytes + bytes / 4 + 256;
+    CUDA_TRY(cudaMalloc(&s.p, cap));
+    s.cap = cap;
+    (void)ctx;
+    return PMK_OK;
+}
+
+int upload_views(pmk_ctx* ctx) {
+    if (!ctx->views_dirty) return PMK_OK;
+    for (int v = 0; v < ctx->cfg.nviews; ++v)
+        if (!ctx->view_set[v]) return fail(PMK_ERR_STATE, "pmk: view " + std::to_string(v) + " has not been uploaded (pmk_set_view)");
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_views, ctx->h_views.data(), sizeof(ViewConst) * ctx->cfg.nviews, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->views_dirty = false;
+    return PMK_OK;
+}
+
+void refresh_params(pmk_ctx* ctx) {
+    Params& p = ctx->params;
+    p.views = ctx->d_views;
+    p.nviews = ctx->cfg.nviews;
+    p.level = ctx->cfg.level;
+    p.nlevels = ctx->cfg.level + 3;
+    p.csize = ctx->cfg.csize;
+    p.wsize = ctx->cfg.wsize;
+    p.min_image_num = ctx->cfg.min_image_num;
+    p.tau = std::min(ctx->cfg.min_image_num * 2, ctx->cfg.nviews);        // pmmvps.cpp:32
+    p.depth = ctx->depth;
+    p.cos_angle1 = cosf(ctx->angle_threshold1);
+    p.cos_angle0 = cosf(ctx->angle_threshold0);
+    p.ncc_threshold = ctx->ncc_threshold;
+    p.ncc_threshold_before = ctx->ncc_threshold_before;
+    p.level_scale = (float)(1 << ctx->cfg.level);
+    for (int k = 0; k < PMK_MAX_LEVELS; ++k) p.level_thr[k] = INFINITY;
+    int slot = 0;
+    for (int k = -ctx->cfg.level + 1; k <= 2 && slot < PMK_MAX_LEVELS; ++k) p.level_thr[slot++] = level_threshold(k);
+}
+
+template <int WS>
+int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
+              void* incc, void* ncc, void* levels) {
+    const int fstride = ctx->params.tau * K1_FRAME_WORDS + 4;
+    const size_t smem = (size_t)K1_WARPS * 32 * fstride * sizeof(float);
+    if (!ctx->k1_attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->k1_attr_done = true;
+    }
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_ncc<WS>, K1_WARPS * 32, smem));
+    if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k1_ncc does not fit on an SM");
+    const int nbatch = (n + 31) / 32;
+    const int want = (nbatch + K1_WARPS - 1) / K1_WARPS;
+    const int grid = std::max(1, std::min(want, ctx->sm_count * per_sm));
+    k1_ncc<WS><<<grid, K1_WARPS * 32, smem, ctx->stream>>>(ctx->params, n, (const float4*)coord, (const float4*)normal, (const int*)views,
+                                                          (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PMK_OK;
+}
+
+int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
+                void* incc, void* ncc, void* levels) {
+    switch (ctx->cfg.wsize) {
+        case 5: return launch_k1<5>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 7: return launch_k1<7>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 9: return launch_k1<9>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 11: return launch_k1<11>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+    }
+    return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11");
+}
+
+}  // namespace
+
+extern "C" {
+
+int pmk_abi_version(void) { return PMK_ABI_VERSION; }
+const char* pmk_last_error(void) { return g_err.c_str(); }
+
+void pmk_default_config(pmk_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->device = 0;
+    c->nviews = 0;
+    c->level = 1; c->csize = 2; c->wsize = 7; c->min_image_num = 3;       // option.cpp:19-33
+    c->ncc_threshold = 0.7f;
+    c->max_angle_threshold = 10.0f * M_PI / 180.0f;
+    c->quad_threshold = 2.5f;
+    c->max_patches = 0;
+}
+
+int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
+    if (!cfg || !out) return fail(PMK_ERR_ARG, "pmk_create: null argument");
+    *out = nullptr;
+    if (cfg->nviews < 1 || cfg->nviews > 4096) return fail(PMK_ERR_ARG, "pmk_create: nviews out of range");
+    if (cfg->level < 0 || cfg->level + 3 > PMK_MAX_LEVELS) return fail(PMK_ERR_ARG, "pmk_create: level out of range");
+    if (cfg->csize < 1) return fail(PMK_ERR_ARG, "pmk_create: csize < 1");
+    if (cfg->wsize != 5 && cfg->wsize != 7 && cfg->wsize != 9 && cfg->wsize != 11) return fail(PMK_ERR_ARG, "pmk_create: wsize must be 5, 7, 9 or 11");
+    if (cfg->min_image_num < 1 || std::min(cfg->min_image_num * 2, cfg->nviews) > PMK_MAX_TAU)
+        return fail(PMK_ERR_ARG, "pmk_create: tau = min(2*minImageNum, nviews) exceeds PMK_MAX_TAU");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(PMK_ERR_CUDA, "pmk_create: no CUDA device (this library has no CPU path)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(PMK_ERR_ARG, "pmk_create: bad device ordinal");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    pmk_ctx* ctx = new pmk_ctx();
+    ctx->cfg = *cfg;
+    CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    ctx->h_views.resize(cfg->nviews);
+    std::memset(ctx->h_views.data(), 0, sizeof(ViewConst) * cfg->nviews);
+    ctx->P_all.resize(cfg->nviews);
+    ctx->view_set.assign(cfg->nviews, 0);
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_views, sizeof(ViewConst) * cfg->nviews));
+    // thresholds, pmmvps.cpp:54-67
+    ctx->angle_threshold0 = 60.0f * M_PI / 180.0f;
+    ctx->angle_threshold1 = 60.0f * M_PI / 180.0f;
+    ctx->neighbor_threshold = 0.5f;
+    ctx->neighbor_threshold1 = 1.0f;
+    ctx->neighbor_threshold2 = 1.0f;
+    ctx->ncc_threshold = cfg->ncc_threshold;
+    ctx->ncc_threshold_before = cfg->ncc_threshold - 0.3f;
+    ctx->depth = 0;
+    refresh_params(ctx);
+    *out = ctx;
+    return PMK_OK;
+}
+
+void pmk_destroy(pmk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->owned) cudaFree(p);
+    Scratch* all[] = {&ctx->s_coord, &ctx->s_normal, &ctx->s_views, &ctx->s_nviews, &ctx->s_incc, &ctx->s_ncc, &ctx->s_levels};
+    for (Scratch* s : all) if (s->p) cudaFree(s->p);
+    for (Scratch& s : ctx->s_misc) if (s.p) cudaFree(s.p);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    cudaFree(ctx->d_views);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int width, int height) {
+    if (!ctx || !P || !rgb) return fail(PMK_ERR_ARG, "pmk_set_view: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_set_view: view out of range");
+    const int nlevels = ctx->cfg.level + 3, level = ctx->cfg.level;
+    if (width < (16 << nlevels) / 2 || height < (16 << nlevels) / 2) return fail(PMK_ERR_ARG, "pmk_set_view: image too small for the pyramid");
+    if (ctx->view_set[view]) return fail(PMK_ERR_STATE, "pmk_set_view: view already uploaded");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    ViewConst& vc = ctx->h_views[view];
+    // ---- camera: updateProjection / updateCamera (camera.cpp:65-100), getCameraCenter (:295-308) ----
+    std::vector<float>& Pl = ctx->P_all[view];
+    Pl.assign((size_t)nlevels * 12, 0.0f);
+    std::memcpy(Pl.data(), P, 12 * sizeof(float));
+    for (int l = 1; l < nlevels; ++l) {
+        float* q = Pl.data() + l * 12;
+        std::memcpy(q, q - 12, 12 * sizeof(float));
+        for (int c = 0; c < 8; ++c) q[c] = q[c] / 2.0f;
+    }
+    const float* P0 = Pl.data();
+    std::memcpy(vc.P, Pl.data() + level * 12, 12 * sizeof(float));
+    const float on = hnorm3(P0 + 8);
+    for (int c = 0; c < 4; ++c) vc.oaxis[c] = P0[8 + c] / on;
+    {
+        const float M[9] = {P0[0], P0[1], P0[2], P0[4], P0[5], P0[6], P0[8], P0[9], P0[10]};
+        float Mi[9];
+        hinv3(M, Mi);
+        const float q[3] = {P0[3], P0[7], P0[11]};
+        for (int r = 0; r < 3; ++r) {
+            float acc = (-Mi[3 * r]) * q[0];
+            acc = acc + (-Mi[3 * r + 1]) * q[1];
+            acc = acc + (-Mi[3 * r + 2]) * q[2];
+            vc.center[r] = acc;
+        }
+        vc.center[3] = 1.0f;
+    }
+    {
+        const float* Pw = vc.P;   // Camera::unproject inverts the working-level 3x3 (camera.cpp:331-335)
+        const float M[9] = {Pw[0], Pw[1], Pw[2], Pw[4], Pw[5], Pw[6], Pw[8], Pw[9], Pw[10]};
+        float Mi[9];
+        hinv3(M, Mi);
+        for (int r = 0; r < 3; ++r) { vc.Minv[4 * r] = Mi[3 * r]; vc.Minv[4 * r + 1] = Mi[3 * r + 1]; vc.Minv[4 * r + 2] = Mi[3 * r + 2]; vc.Minv[4 * r + 3] = 0.0f; }
+    }
+    // ---- Optim::setAxesScales (optim.cpp:43-65) ----
+    {
+        float za[3] = {vc.oaxis[0], vc.oaxis[1], vc.oaxis[2]}, x0[3] = {P0[0], P0[1], P0[2]}, ya[3], xa[3];
+        hcross3(za, x0, ya);
+        const float yn = hnorm3(ya);
+        ya[0] = ya[0] / yn; ya[1] = ya[1] / yn; ya[2] = ya[2] / yn;
+        hcross3(ya, za, xa);
+        for (int i = 0; i < 3; ++i) { vc.xaxis[i] = xa[i]; vc.yaxis[i] = ya[i]; vc.zaxis[i] = za[i]; }
+        vc.xaxis[3] = vc.yaxis[3] = vc.zaxis[3] = 0.0f;
+        const float xa4[4] = {xa[0], xa[1], xa[2], 0.0f}, ya4[4] = {ya[0], ya[1], ya[2], 0.0f};
+        vc.ipscale = hdot4(P0, xa4) + hdot4(P0 + 4, ya4);
+    }
+    // ---- image: dims (image.cpp:135-138), grid (patch_manager.cpp:36-37), pyramid (K0) ----
+    vc.w[0] = width; vc.h[0] = height;
+    for (int l = 1; l < nlevels; ++l) { vc.w[l] = vc.w[l - 1] / 2; vc.h[l] = vc.h[l - 1] / 2; }
+    for (int l = nlevels; l < PMK_MAX_LEVELS; ++l) { vc.w[l] = 0; vc.h[l] = 0; vc.img[l] = nullptr; }
+    vc.gw = (vc.w[level] + ctx->cfg.csize - 1) / ctx->cfg.csize;
+    vc.gh = (vc.h[level] + ctx->cfg.csize - 1) / ctx->cfg.csize;
+    const size_t npix0 = (size_t)width * height;
+    { const int rc = ensure(ctx, ctx->s_misc[0], npix0 * 3); if (rc) return rc; }
+    CUDA_TRY(cudaMemcpyAsync(ctx->s_misc[0].p, rgb, npix0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+    for (int l = 0; l < nlevels; ++l) {
+        void* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, (size_t)vc.w[l] * vc.h[l] * sizeof(float4)));
+        ctx->owned.push_back(d);
+        vc.img[l] = (const float4*)d;
+    }
+    k0_u8_to_rgbx<<<(unsigned)((npix0 + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->s_misc[0].p, (float4*)vc.img[0], (int)npix0);
+    ctx->launches++;
+    for (int l = 1; l < nlevels; ++l) {
+        dim3 blk(32, 8), grd((vc.w[l] + 31) / 32, (vc.h[l] + 7) / 8);
+        k0_downsample<<<grd, blk, 0, ctx->stream>>>(vc.img[l - 1], vc.w[l - 1], vc.h[l - 1], (float4*)vc.img[l], vc.w[l], vc.h[l]);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));       // rgb is a caller buffer; the staging copy must land
+    ctx->view_set[view] = 1;
+    ctx->views_dirty = true;
+    return PMK_OK;
+}
+
+int pmk_get_thresholds(pmk_ctx* ctx, pmk_thresholds* t) {
+    if (!ctx || !t) return fail(PMK_ERR_ARG, "pmk_get_thresholds: null argument");
+    t->tau = ctx->params.tau; t->depth = ctx->depth;
+    t->ncc_threshold = ctx->ncc_threshold; t->ncc_threshold_before = ctx->ncc_threshold_before;
+    t->angle_threshold0 = ctx->angle_threshold0; t->angle_threshold1 = ctx->angle_threshold1;
+    t->max_angle_threshold = ctx->cfg.max_angle_threshold; t->quad_threshold = ctx->cfg.quad_threshold;
+    t->neighbor_threshold = ctx->neighbor_threshold; t->neighbor_threshold1 = ctx->neighbor_threshold1; t->neighbor_threshold2 = ctx->neighbor_threshold2;
+    return PMK_OK;
+}
+
+int pmk_set_depth(pmk_ctx* ctx, int depth) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_set_depth: null ctx");
+    ctx->depth = depth;
+    refresh_params(ctx);
+    return PMK_OK;
+}
+
+int pmk_update_threshold(pmk_ctx* ctx) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_update_threshold: null ctx");
+    ctx->ncc_threshold -= 0.05f;              // pmmvps.cpp:70-74
+    ctx->ncc_threshold_before -= 0.05f;
+    ctx->depth += 1;                          // pmmvps.cpp:106
+    refresh_params(ctx);
+    return PMK_OK;
+}
+
+int pmk_get_camera(pmk_ctx* ctx, int view, int level, pmk_camera* out) {
+    if (!ctx || !out) return fail(PMK_ERR_ARG, "pmk_get_camera: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews || !ctx->view_set[view]) return fail(PMK_ERR_ARG, "pmk_get_camera: view not set");
+    if (level < 0 || level >= ctx->cfg.level + 3) return fail(PMK_ERR_ARG, "pmk_get_camera: level out of range");
+    const ViewConst& vc = ctx->h_views[view];
+    std::memcpy(out->P, ctx->P_all[view].data() + level * 12, 12 * sizeof(float));
+    std::memcpy(out->center, vc.center, sizeof(out->center));
+    std::memcpy(out->oaxis, vc.oaxis, sizeof(out->oaxis));
+    for (int i = 0; i < 3; ++i) { out->xaxis[i] = vc.xaxis[i]; out->yaxis[i] = vc.yaxis[i]; out->zaxis[i] = vc.zaxis[i]; }
+    out->ipscale = vc.ipscale;
+    return PMK_OK;
+}
+
+int pmk_get_level_dims(pmk_ctx* ctx, int view, int level, int* width, int* height) {
+    if (!ctx || !width || !height) return fail(PMK_ERR_ARG, "pmk_get_level_dims: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews || !ctx->view_set[view]) return fail(PMK_ERR_ARG, "pmk_get_level_dims: view not set");
+    if (level < 0 || level >= ctx->cfg.level + 3) return fail(PMK_ERR_ARG, "pmk_get_level_dims: level out of range");
+    *width = ctx->h_views[view].w[level]; *height = ctx->h_views[view].h[level];
+    return PMK_OK;
+}
+
+int pmk_get_grid_dims(pmk_ctx* ctx, int view, int* gw, int* gh) {
+    if (!ctx || !gw || !gh) return fail(PMK_ERR_ARG, "pmk_get_grid_dims: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews || !ctx->view_set[view]) return fail(PMK_ERR_ARG, "pmk_get_grid_dims: view not set");
+    *gw = ctx->h_views[view].gw; *gh = ctx->h_views[view].gh;
+    return PMK_OK;
+}
+
+int pmk_get_level_image(pmk_ctx* ctx, int view, int level, uint8_t* rgb_out) {
+    int w = 0, h = 0;
+    int rc = pmk_get_level_dims(ctx, view, level, &w, &h);
+    if (rc) return rc;
+    if (!rgb_out) return fail(PMK_ERR_ARG, "pmk_get_level_image: null output");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    const size_t npix = (size_t)w * h;
+    if ((rc = ensure(ctx, ctx->s_misc[0], npix * 3))) return rc;
+    k0_rgbx_to_u8<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(ctx->h_views[view].img[level], (uint8_t*)ctx->s_misc[0].p, (int)npix);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, ctx->s_misc[0].p, npix * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_ncc_eval_dev(pmk_ctx* ctx, int n, const void* d_coord4, const void* d_normal4, const void* d_views, const void* d_nviews, int stride,
+                     void* d_incc, void* d_ncc, void* d_levels) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_ncc_eval: null ctx");
+    if (n < 0 || stride < 1) return fail(PMK_ERR_ARG, "pmk_ncc_eval: bad n/stride");
+    if (n == 0) return PMK_OK;
+    if (!d_coord4 || !d_normal4 || !d_views || !d_nviews || !d_incc) return fail(PMK_ERR_ARG, "pmk_ncc_eval: null buffer");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    return dispatch_k1(ctx, n, d_coord4, d_normal4, d_views, d_nviews, stride, d_incc, d_ncc, d_levels);
+}
+
+int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride,
+                 float* incc_out, float* ncc_out, int* levels_out) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_ncc_eval: null ctx");
+    if (n < 0 || stride < 1) return fail(PMK_ERR_ARG, "pmk_ncc_eval: bad n/stride");
+    if (n == 0) return PMK_OK;
+    if (!coord4 || !normal4 || !views || !nviews || !incc_out) return fail(PMK_ERR_ARG, "pmk_ncc_eval: null buffer");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    const size_t N = (size_t)n;
+    const int tau = ctx->params.tau;
+    int rc;
+    if ((rc = ensure(ctx, ctx->s_coord, N * 16)) || (rc = ensure(ctx, ctx->s_normal, N * 16)) || (rc = ensure(ctx, ctx->s_views, N * stride * 4)) ||
+        (rc = ensure(ctx, ctx->s_nviews, N * 4)) || (rc = ensure(ctx, ctx->s_incc, N * 4)) || (rc = ensure(ctx, ctx->s_ncc, N * 4)) ||
+        (rc = ensure(ctx, ctx->s_levels, N * tau * 4)))
+        return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(ctx->s_coord.p, coord4, N * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->s_normal.p, normal4, N * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->s_views.p, views, N * stride * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->s_nviews.p, nviews, N * 4, cudaMemcpyHostToDevice, st));
+    rc = pmk_ncc_eval_dev(ctx, n, ctx->s_coord.p, ctx->s_normal.p, ctx->s_views.p, ctx->s_nviews.p, stride, ctx->s_incc.p,
+                          ncc_out ? ctx->s_ncc.p : nullptr, levels_out ? ctx->s_levels.p : nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(incc_out, ctx->s_incc.p, N * 4, cudaMemcpyDeviceToHost, st));
+    if (ncc_out) CUDA_TRY(cudaMemcpyAsync(ncc_out, ctx->s_ncc.p, N * 4, cudaMemcpyDeviceToHost, st));
+    if (levels_out) CUDA_TRY(cudaMemcpyAsync(levels_out, ctx->s_levels.p, N * tau * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PMK_OK;
+}
+
+int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const float* normal4, float* project3, float* unit1,
+              float* px4, float* py4, int* cell_ixy2, int* cell_ok) {
+    if (!ctx || !view || !coord4) return fail(PMK_ERR_ARG, "pmk_probe: null argument");
+    if (n <= 0) return PMK_OK;
+    for (int i = 0; i < n; ++i) if (view[i] < 0 || view[i] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe: view out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    const size_t N = (size_t)n;
+    Scratch* s = ctx->s_misc;
+    if ((rc = ensure(ctx, s[0], N * 4)) || (rc = ensure(ctx, s[1], N * 16)) || (rc = ensure(ctx, s[2], N * 16)) || (rc = ensure(ctx, s[3], N * 12)) ||
+        (rc = ensure(ctx, s[4], N * 4)) || (rc = ensure(ctx, s[5], N * 16)) || (rc = ensure(ctx, s[6], N * 16)) || (rc = ensure(ctx, s[7], N * 12)))
+        return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(s[0].p, view, N * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s[1].p, coord4, N * 16, cudaMemcpyHostToDevice, st));
+    if (normal4) CUDA_TRY(cudaMemcpyAsync(s[2].p, normal4, N * 16, cudaMemcpyHostToDevice, st));
+    int* cells = (int*)s[7].p;
+    k_probe<<<(n + 127) / 128, 128, 0, st>>>(ctx->params, n, (const int*)s[0].p, (const float4*)s[1].p, normal4 ? (const float4*)s[2].p : nullptr,
+                                             project3 ? (float*)s[3].p : nullptr, unit1 ? (float*)s[4].p : nullptr,
+                                             (px4 && py4) ? (float4*)s[5].p : nullptr, (px4 && py4) ? (float4*)s[6].p : nullptr,
+                                             cell_ixy2 ? cells : nullptr, cell_ok ? cells + 2 * N : nullptr);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (project3) CUDA_TRY(cudaMemcpyAsync(project3, s[3].p, N * 12, cudaMemcpyDeviceToHost, st));
+    if (unit1) CUDA_TRY(cudaMemcpyAsync(unit1, s[4].p, N * 4, cudaMemcpyDeviceToHost, st));
+    if (px4 && py4) {
+        CUDA_TRY(cudaMemcpyAsync(px4, s[5].p, N * 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(py4, s[6].p, N * 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (cell_ixy2) CUDA_TRY(cudaMemcpyAsync(cell_ixy2, cells, N * 8, cudaMemcpyDeviceToHost, st));
+    if (cell_ixy2 && cell_ok) CUDA_TRY(cudaMemcpyAsync(cell_ok, cells + 2 * N, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PMK_OK;
+}
+
+int pmk_sync(pmk_ctx* ctx) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_sync: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_device_alloc(pmk_ctx* ctx, uint64_t bytes, void** out) {
+    if (!ctx || !out) return fail(PMK_ERR_ARG, "pmk_device_alloc: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+    return PMK_OK;
+}
+
+int pmk_device_free(pmk_ctx* ctx, void* p) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_device_free: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaFree(p));
+    return PMK_OK;
+}
+
+int pmk_memcpy_h2d(pmk_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_memcpy_h2d: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_memcpy_d2h(pmk_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_memcpy_d2h: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_host_alloc_pinned(uint64_t bytes, void** out) {
+    if (!out) return fail(PMK_ERR_ARG, "pmk_host_alloc_pinned: null argument");
+    CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return PMK_OK;
+}
+
+int pmk_host_free_pinned(void* p) {
+    CUDA_TRY(cudaFreeHost(p));
+    return PMK_OK;
+}
+
+int pmk_timer_begin(pmk_ctx* ctx) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_timer_begin: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_timer_end(pmk_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(PMK_ERR_ARG, "pmk_timer_end: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return PMK_OK;
+}
+
+int pmk_launch_count(pmk_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return fail(PMK_ERR_ARG, "pmk_launch_count: null argument");
+    *out = ctx->launches;
+    return PMK_OK;
+}
+
+int pmk_flush_l2(pmk_ctx* ctx) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_flush_l2: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t)256 << 20;       // > 126 MB L2
+        CUDA_TRY(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    return PMK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+"""ctypes binding of the C ABI in include/pmk.h (mvskit_b200/libpmk.so).
+
+This is plumbing for tests and bench.py; the product is the shared library.  There is no CPU
+fallback: importing works anywhere (so the symbol table can be checked on a CPU box), but creating
+a :class:`Context` raises unless a CUDA device is present, and a missing library raises at load.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpmk.so")
+
+PMK_MAX_LEVELS = 6
+PMK_MAX_TAU = 8
+
+
+class PmkError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("nviews", C.c_int), ("level", C.c_int), ("csize", C.c_int), ("wsize", C.c_int),
+                ("min_image_num", C.c_int), ("ncc_threshold", C.c_float), ("max_angle_threshold", C.c_float),
+                ("quad_threshold", C.c_float), ("max_patches", C.c_int)]
+
+
+class Thresholds(C.Structure):
+    _fields_ = [("tau", C.c_int), ("depth", C.c_int)] + [(k, C.c_float) for k in (
+        "ncc_threshold", "ncc_threshold_before", "angle_threshold0", "angle_threshold1", "max_angle_threshold",
+        "quad_threshold", "neighbor_threshold", "neighbor_threshold1", "neighbor_threshold2")]
+
+
+class Camera(C.Structure):
+    _fields_ = [("P", C.c_float * 12), ("center", C.c_float * 4), ("oaxis", C.c_float * 4), ("xaxis", C.c_float * 3),
+                ("yaxis", C.c_float * 3), ("zaxis", C.c_float * 3), ("ipscale", C.c_float)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpmk.so.  Raises (never falls back) when the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PmkError(f"{LIB_PATH} is missing: build it with `python -m mvskit_b200.build` (no CPU fallback exists)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pmk_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _chk(rc: int):
+    if rc != 0:
+        raise PmkError(f"pmk error {rc}: {lib().pmk_last_error().decode()}")
+
+
+class DeviceBuffer:
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        self.ptr = C.c_void_p()
+        _chk(lib().pmk_device_alloc(ctx.h, C.c_uint64(self.nbytes), C.byref(self.ptr)))
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _chk(lib().pmk_memcpy_h2d(self.ctx.h, self.ptr, _p(arr), C.c_uint64(arr.nbytes)))
+        return self
+
+    def download(self, arr: np.ndarray):
+        assert arr.flags["C_CONTIGUOUS"] and arr.nbytes <= self.nbytes
+        _chk(lib().pmk_memcpy_d2h(self.ctx.h, _p(arr), self.ptr, C.c_uint64(arr.nbytes)))
+        return arr
+
+    def free(self):
+        if self.ptr:
+            lib().pmk_device_free(self.ctx.h, self.ptr)
+            self.ptr = C.c_void_p()
+
+
+class Context:
+    """One per GPU.  Mirrors PmMvps::init's effect on the device (pmmvps/pmmvps.cpp:18-68)."""
+
+    def __init__(self, nviews: int, device: int = 0, level: int = 1, csize: int = 2, wsize: int = 7, min_image_num: int = 3,
+                 ncc_threshold: float = 0.7, max_patches: int = 0):
+        L = lib()
+        cfg = Config()
+        L.pmk_default_config(C.byref(cfg))
+        cfg.device, cfg.nviews, cfg.level, cfg.csize, cfg.wsize = device, nviews, level, csize, wsize
+        cfg.min_image_num, cfg.ncc_threshold, cfg.max_patches = min_image_num, ncc_threshold, max_patches
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _chk(L.pmk_create(C.byref(cfg), C.byref(self.h)))
+        self.nviews, self.level, self.nlevels = nviews, level, level + 3
+        self.tau = min(2 * min_image_num, nviews)
+
+    def close(self):
+        if self.h:
+            lib().pmk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scene ---------------------------------------------------------------------------------------
+    def set_view(self, view: int, P: np.ndarray, rgb: np.ndarray):
+        P = np.ascontiguousarray(P, np.float32).reshape(12)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        assert rgb.ndim == 3 and rgb.shape[2] == 3
+        _chk(lib().pmk_set_view(self.h, view, _p(P), _p(rgb), rgb.shape[1], rgb.shape[0]))
+
+    def set_scene(self, P: np.ndarray, images: Sequence[np.ndarray]):
+        for v in range(self.nviews):
+            self.set_view(v, P[v], images[v])
+
+    def thresholds(self) -> Thresholds:
+        t = Thresholds()
+        _chk(lib().pmk_get_thresholds(self.h, C.byref(t)))
+        return t
+
+    def set_depth(self, d: int):
+        _chk(lib().pmk_set_depth(self.h, d))
+
+    def update_threshold(self):
+        _chk(lib().pmk_update_threshold(self.h))
+
+    def camera(self, view: int, level: int = 0) -> dict:
+        c = Camera()
+        _chk(lib().pmk_get_camera(self.h, view, level, C.byref(c)))
+        return dict(P=np.array(c.P, np.float32).reshape(3, 4), center=np.array(c.center, np.float32), oaxis=np.array(c.oaxis, np.float32),
+                    xaxis=np.array(c.xaxis, np.float32), yaxis=np.array(c.yaxis, np.float32), zaxis=np.array(c.zaxis, np.float32),
+                    ipscale=np.float32(c.ipscale))
+
+    def level_dims(self, view: int, level: int):
+        w, h = C.c_int(), C.c_int()
+        _chk(lib().pmk_get_level_dims(self.h, view, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def grid_dims(self, view: int):
+        w, h = C.c_int(), C.c_int()
+        _chk(lib().pmk_get_grid_dims(self.h, view, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level_image(self, view: int, level: int) -> np.ndarray:
+        w, h = self.level_dims(view, level)
+        out = np.zeros((h, w, 3), np.uint8)
+        _chk(lib().pmk_get_level_image(self.h, view, level, _p(out)))
+        return out
+
+    # -- K1 ------------------------------------------------------------------------------------------
+    def ncc_eval(self, coord, normal, views, nviews, want_levels: bool = False):
+        """PatchManager::computeNcc for a batch; host arrays in, host arrays out."""
+        coord = np.ascontiguousarray(coord, np.float32)
+        normal = np.ascontiguousarray(normal, np.float32)
+        views = np.ascontiguousarray(views, np.int32)
+        nviews = np.ascontiguousarray(nviews, np.int32)
+        n = coord.shape[0]
+        incc, ncc = np.empty(n, np.float32), np.empty(n, np.float32)
+        levels = np.empty((n, self.tau), np.int32) if want_levels else None
+        stride = views.shape[1] if views.ndim == 2 else 1
+        _chk(lib().pmk_ncc_eval(self.h, n, _p(coord), _p(normal), _p(views), _p(nviews), stride, _p(incc), _p(ncc), _p(levels)))
+        return (incc, ncc, levels) if want_levels else (incc, ncc)
+
+    def ncc_eval_dev(self, n: int, coord: DeviceBuffer, normal: DeviceBuffer, views: DeviceBuffer, nviews: DeviceBuffer, stride: int,
+                     incc: DeviceBuffer, ncc: Optional[DeviceBuffer] = None, levels: Optional[DeviceBuffer] = None):
+        _chk(lib().pmk_ncc_eval_dev(self.h, n, coord.ptr, normal.ptr, views.ptr, nviews.ptr, stride, incc.ptr,
+                                    ncc.ptr if ncc else None, levels.ptr if levels else None))
+
+    def probe(self, view, coord, normal=None):
+        view = np.ascontiguousarray(view, np.int32)
+        coord = np.ascontiguousarray(coord, np.float32)
+        n = len(view)
+        normal = np.ascontiguousarray(normal, np.float32) if normal is not None else None
+        proj, unit = np.empty((n, 3), np.float32), np.empty(n, np.float32)
+        px = np.empty((n, 4), np.float32) if normal is not None else None
+        py = np.empty((n, 4), np.float32) if normal is not None else None
+        ixy, ok = np.empty((n, 2), np.int32), np.empty(n, np.int32)
+        _chk(lib().pmk_probe(self.h, n, _p(view), _p(coord), _p(normal), _p(proj), _p(unit), _p(px), _p(py), _p(ixy), _p(ok)))
+        return dict(project=proj, unit=unit, px=px, py=py, cell=ixy, cell_ok=ok)
+
+    # -- plumbing ------------------------------------------------------------------------------------
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def sync(self):
+        _chk(lib().pmk_sync(self.h))
+
+    def timer_begin(self):
+        _chk(lib().pmk_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        _chk(lib().pmk_timer_end(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        _chk(lib().pmk_launch_count(self.h, C.byref(v)))
+        return int(v.value)
+
+    def flush_l2(self):
+        _chk(lib().pmk_flush_l2(self.h))
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over cudaMallocHost memory (kept alive for the life of the process)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    _chk(lib().pmk_host_alloc_pinned(C.c_uint64(max(n, 1)), C.byref(ptr)))
+    buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def exported_symbols():
+    """Names declared in include/pmk.h, for the CPU-side symbol test."""
+    import re
+    hdr = os.path.join(HERE, "..", "include", "pmk.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(pmk_[a-z0-9_]+)\s*\(", txt)))
