@@ -76,12 +76,12 @@ def get_scene(config: int, scale: float):
     return scene
 
 
-def get_hypotheses(scene, n: int, seed: int, config: int, scale: float):
-    path = os.path.join(scene_cache_dir(), f"hyp_c{config}_s{scale:g}_n{n}_seed{seed}.npz")
+def get_hypotheses(scene, n: int, seed: int, config: int, scale: float, order: str = "grid"):
+    path = os.path.join(scene_cache_dir(), f"hyp_c{config}_s{scale:g}_n{n}_seed{seed}_{order}.npz")
     if os.path.exists(path):
         z = np.load(path)
         return z["c"], z["n"], z["v"], z["nv"]
-    c, nrm, vw, nv = scene.hypotheses(n, seed=seed)
+    c, nrm, vw, nv = scene.hypotheses(n, seed=seed, order=order)
     tmp = path + f".{os.getpid()}.tmp.npz"
     np.savez(tmp, c=c, n=nrm, v=vw, nv=nv)
     os.replace(tmp, path)
@@ -131,11 +131,43 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU arms (the only places bench.py executes anything under oracle/)
 # ------------------------------------------------------------------------------------------------------
-def _ref_worker(args):
-    prefix, c, n, vw, nv = args
+_REF = None
+
+
+def _ref_init(prefix):
+    global _REF
     from oracle.pyoracle import RefLib
-    ref = RefLib(prefix)
-    return ref.time_compute_ncc(c, n, vw, nv, 1)
+    _REF = RefLib(prefix)
+
+
+def _ref_worker(args):
+    c, n, vw, nv = args
+    return _REF.time_compute_ncc(c, n, vw, nv, 1)
+
+
+class RefPool:
+    """`cores` processes, each holding one instance of the compiled reference (it is not re-entrant:
+    static Optim::m_inst, optim.cpp:18-22), timed on disjoint slices of the batch."""
+
+    def __init__(self, prefix: str, cores: int):
+        self.cores = cores
+        if cores == 1:
+            _ref_init(prefix)
+            self.pool = None
+        else:
+            import multiprocessing as mp
+            self.pool = mp.get_context("spawn").Pool(cores, initializer=_ref_init, initargs=(prefix,))
+
+    def evals_per_sec(self, hyp, sample_per_core: int) -> float:
+        c, n, vw, nv = (a[: sample_per_core * self.cores] for a in hyp)
+        jobs = [(c[i::self.cores], n[i::self.cores], vw[i::self.cores], nv[i::self.cores]) for i in range(self.cores)]
+        secs = [_ref_worker(jobs[0])] if self.pool is None else self.pool.map(_ref_worker, jobs)
+        return len(c) / max(secs)
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
 
 
 def ensure_scene_dir(scene, config, scale):
@@ -151,33 +183,27 @@ def ensure_scene_dir(scene, config, scale):
     return d + "/"
 
 
-def cpu_reference_evals_per_sec(scene, config, scale, hyp, cores: int, sample: int):
+def cpu_reference_evals_per_sec(scene, config, scale, hyp, cores: int, sample: int, steps: int = 1, warmup: int = 0):
     """Time the reference's own computeNcc loop (oracle/_ref/libpmref.so) on `cores` processes, `sample` evals each."""
     from oracle import pyoracle
-    kind = "reference" if os.path.exists(pyoracle.REF_SO) else "port"
-    c, n, vw, nv = (a[: sample * cores] for a in hyp)
-    if kind == "reference":
-        prefix = ensure_scene_dir(scene, config, scale)
-        jobs = [(prefix, c[i::cores], n[i::cores], vw[i::cores], nv[i::cores]) for i in range(cores)]
-        if cores == 1:
-            secs = [_ref_worker(jobs[0])]
-        else:
-            import multiprocessing as mp
-            with mp.get_context("spawn").Pool(cores) as pool:
-                secs = pool.map(_ref_worker, jobs)
-        return len(c) / max(secs), kind
+    if os.path.exists(pyoracle.REF_SO):
+        pool = RefPool(ensure_scene_dir(scene, config, scale), cores)
+        vals = [pool.evals_per_sec(hyp, sample) for _ in range(warmup + steps)][warmup:]
+        pool.close()
+        return float(np.mean(vals)), "reference"
     pyoracle.build(ref=False)
     orc = pyoracle.COracle(scene.P, scene.images)
+    c, n, vw, nv = (a[:sample] for a in hyp)
     t0 = time.time()
-    orc.compute_ncc(c[:sample], n[:sample], vw[:sample], nv[:sample])
-    return sample / (time.time() - t0), kind
+    orc.compute_ncc(c, n, vw, nv)
+    return sample / (time.time() - t0), "port"
 
 
 # ------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pmk", choices=["pmk", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="hypotheses per step per GPU")
@@ -185,6 +211,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="evals in the cpu_baseline sample (1 core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--order", default="grid", choices=["grid", "random"], help="hypothesis order: Z-order of the reference pixel (patch-grid walk) or random")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -193,7 +220,7 @@ def main():
     config = {"workload": WORKLOAD if (args.config == 2 and args.scale == 1.0 and args.batch == 1 << 20) else
               f"config{args.config} scale {args.scale:g}, {args.batch} hypotheses/step/GPU", "views_per_eval": 6,
               "hypotheses_per_step_per_gpu": args.batch, "sharding": "hypotheses split across ranks, images replicated, no collective",
-              "l2": "flushed (256 MiB memset) before every timed step"}
+              "hypothesis_order": args.order, "l2": "flushed (256 MiB memset) before every timed step"}
 
     # ---------------- reference arm: the reference's own CPU code on the host cores ----------------
     if args.impl == "reference":
@@ -201,14 +228,9 @@ def main():
             return
         scene = get_scene(args.config, args.scale)
         cores = os.cpu_count() or 1
-        per_core = max(1, min(args.batch // cores, 65536))          # bounded sample per step
-        hyp = get_hypotheses(scene, args.batch, 7, args.config, args.scale)
-        vals = []
-        for i in range(args.warmup + args.steps):
-            v, kind = cpu_reference_evals_per_sec(scene, args.config, args.scale, hyp, cores, per_core)
-            if i >= args.warmup:
-                vals.append(v)
-        value = float(np.mean(vals))
+        per_core = max(1, min(args.batch // cores, 32768))          # bounded sample per step (~0.3 s)
+        hyp = get_hypotheses(scene, args.batch, 7, args.config, args.scale, args.order)
+        value, kind = cpu_reference_evals_per_sec(scene, args.config, args.scale, hyp, cores, per_core, args.steps, args.warmup)
         sample = f"{per_core * cores} of the {args.batch} hypotheses per step ({per_core} per process x {cores} processes)"
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
@@ -234,7 +256,7 @@ def main():
         dist.barrier()
         if local_rank != 0:
             scene = get_scene(args.config, args.scale)
-    hyp = get_hypotheses(scene, args.batch, 7 + rank, args.config, args.scale)
+    hyp = get_hypotheses(scene, args.batch, 7 + rank, args.config, args.scale, args.order)
     c, n, vw, nv = hyp
     N = len(c)
 

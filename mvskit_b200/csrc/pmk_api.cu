@@ -85,6 +85,7 @@ struct pmk_ctx {
     std::vector<char> view_set;
     std::vector<void*> owned;                // every device allocation of the context
     ViewConst* d_views = nullptr;
+    unsigned int* d_counters = nullptr;      // work-queue heads
     bool views_dirty = true;
     Scratch s_coord, s_normal, s_views, s_nviews, s_incc, s_ncc, s_levels, s_misc[8];
     void* flush_buf = nullptr;
@@ -147,6 +148,7 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
     const size_t smem = (size_t)K1_WARPS * 32 * fstride * sizeof(float);
     if (!ctx->k1_attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         ctx->k1_attr_done = true;
     }
     int per_sm = 0;
@@ -155,8 +157,9 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
     const int nbatch = (n + 31) / 32;
     const int want = (nbatch + K1_WARPS - 1) / K1_WARPS;
     const int grid = std::max(1, std::min(want, ctx->sm_count * per_sm));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), ctx->stream));
     k1_ncc<WS><<<grid, K1_WARPS * 32, smem, ctx->stream>>>(ctx->params, n, (const float4*)coord, (const float4*)normal, (const int*)views,
-                                                          (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels);
+                                                          (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels, ctx->d_counters);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return PMK_OK;
@@ -216,6 +219,7 @@ int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
     ctx->P_all.resize(cfg->nviews);
     ctx->view_set.assign(cfg->nviews, 0);
     CUDA_TRY(cudaMalloc((void**)&ctx->d_views, sizeof(ViewConst) * cfg->nviews));
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_counters, 64 * sizeof(unsigned int)));
     // thresholds, pmmvps.cpp:54-67
     ctx->angle_threshold0 = 60.0f * M_PI / 180.0f;
     ctx->angle_threshold1 = 60.0f * M_PI / 180.0f;
@@ -240,6 +244,7 @@ void pmk_destroy(pmk_ctx* ctx) {
     for (Scratch& s : ctx->s_misc) if (s.p) cudaFree(s.p);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     cudaFree(ctx->d_views);
+    cudaFree(ctx->d_counters);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

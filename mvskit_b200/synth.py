@@ -305,9 +305,12 @@ class Scene:
             out[:, j + 1] = np.where(good[:, j], order[:, j], -1)
         return out
 
-    def hypotheses(self, n: int, seed: int = 7, depth_jitter: float = 0.02, normal_jitter_deg: float = 20.0, tau: int = 6):
+    def hypotheses(self, n: int, seed: int = 7, depth_jitter: float = 0.02, normal_jitter_deg: float = 20.0, tau: int = 6,
+                   order: str = "random"):
         """n hypotheses around ground truth, each with up to tau views ([0] = reference).
 
+        order="random": random pixels of each reference view in draw order; order="grid": the same draws sorted
+        in Z-order of their reference pixel, i.e. the spatially coherent order in which a patch grid is walked.
         Returns coord (n,4) f32, normal (n,4) f32, views (n,tau) i32 (-1 padded, compacted), nviews (n,) i32.
         """
         rng = np.random.RandomState(seed)
@@ -319,6 +322,13 @@ class Scene:
                 break
             px = rng.uniform(24, self.width - 25, m)
             py = rng.uniform(24, self.height - 25, m)
+            if order == "grid":
+                code = np.zeros(m, np.int64)
+                ix, iy = px.astype(np.int64), py.astype(np.int64)
+                for b in range(13):
+                    code |= ((ix >> b) & 1) << (2 * b) | ((iy >> b) & 1) << (2 * b + 1)
+                o = np.argsort(code, kind="stable")
+                px, py = px[o], py[o]
             X, hit = self.cast(v, px, py)
             nrm = self.surface.normal(X)
             vw = self.neighbours(X, nrm, v, tau)
