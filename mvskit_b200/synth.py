@@ -283,7 +283,7 @@ class Scene:
         return self
 
     # -- hypotheses for the NCC micro-benchmark / parity tests -----------------------------------------
-    def neighbours(self, X: np.ndarray, n: np.ndarray, ref: int, k: int) -> np.ndarray:
+    def neighbours(self, X: np.ndarray, n: np.ndarray, ref: int, k: int, cos_min: float = math.cos(math.radians(58.0))) -> np.ndarray:
         """For each point: [ref] + the k-1 other views with the smallest angle to the ref ray that see it."""
         N = X.shape[0]
         ray_ref = self.eyes[ref] - X
@@ -294,7 +294,7 @@ class Scene:
                 continue
             r = self.eyes[v] - X
             r /= np.linalg.norm(r, axis=-1, keepdims=True)
-            ok = self.visible(v, X) & (np.sum(r * n, -1) > math.cos(math.radians(58.0)))
+            ok = self.visible(v, X) & (np.sum(r * n, -1) > cos_min)
             score[:, v] = np.where(ok, 1.0 - np.sum(r * ray_ref, -1), np.inf)
         m = min(k - 1, self.nviews - 1)
         order = np.argsort(score, axis=1, kind="stable")[:, :m]
@@ -316,12 +316,36 @@ class Scene:
         rng = np.random.RandomState(seed)
         per = (n + self.nviews - 1) // self.nviews
         coords, normals, views = [], [], []
+        cos_ref, cos_nb = math.cos(math.radians(35.0)), math.cos(math.radians(42.0))
         for v in range(self.nviews):
             m = min(per, n - v * per)
             if m <= 0:
                 break
-            px = rng.uniform(24, self.width - 25, m)
-            py = rng.uniform(24, self.height - 25, m)
+            # rejection-sample pixels whose ground-truth point is well observed: facing the reference view
+            # and seen by tau-1 other views (so the jittered hypothesis normally keeps all tau views)
+            got_px, got_py, have, rounds = [], [], 0, 0
+            while have < m and rounds < 12:
+                k = max(1024, 3 * (m - have))
+                px = rng.uniform(24, self.width - 25, k)
+                py = rng.uniform(24, self.height - 25, k)
+                X, hit = self.cast(v, px, py)
+                nrm = self.surface.normal(X)
+                ray = self.eyes[v] - X
+                ray /= np.linalg.norm(ray, axis=-1, keepdims=True)
+                good = hit & (np.sum(ray * nrm, -1) > cos_ref)
+                if rounds < 11:
+                    idx = np.nonzero(good)[0]
+                    if idx.size:
+                        vw = self.neighbours(X[idx], nrm[idx], v, tau, cos_min=cos_nb)
+                        good[idx] &= (vw >= 0).sum(1) >= min(tau, self.nviews)
+                else:
+                    good = hit                       # give up filtering: keep the batch size exact
+                got_px.append(px[good]); got_py.append(py[good])
+                have += int(good.sum()); rounds += 1
+            px, py = np.concatenate(got_px)[:m], np.concatenate(got_py)[:m]
+            if px.size < m:                          # pathological scene: pad with unfiltered draws
+                px = np.concatenate([px, rng.uniform(24, self.width - 25, m - px.size)])
+                py = np.concatenate([py, rng.uniform(24, self.height - 25, m - py.size)])
             if order == "grid":
                 code = np.zeros(m, np.int64)
                 ix, iy = px.astype(np.int64), py.astype(np.int64)
@@ -331,7 +355,7 @@ class Scene:
                 px, py = px[o], py[o]
             X, hit = self.cast(v, px, py)
             nrm = self.surface.normal(X)
-            vw = self.neighbours(X, nrm, v, tau)
+            vw = self.neighbours(X, nrm, v, tau, cos_min=cos_nb)
             d = X - self.eyes[v]
             X = self.eyes[v] + d * (1.0 + rng.uniform(-depth_jitter, depth_jitter, (m, 1)))
             ang = math.radians(normal_jitter_deg)
