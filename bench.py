@@ -334,9 +334,12 @@ def main():
     if rank == 0:
         peak, peak_src = load_peaks()
         per_gpu = value / world
-        # algorithmic bytes: SURVEY 8(d) counts tau = 6 sampled views per eval (4692 B); views that fail the angle
-        # gate / getTexSafe are not gathered, so scale the texel term by the measured valid-view count
+        # algorithmic bytes per eval = SURVEY.md 8(d)'s figure: 84 B of patch I/O + 768 B (64 texels x 3 ch x 4 B) per
+        # sampled view (4692 B at tau = 6); views failing the angle gate / getTexSafe are not gathered, so the texel
+        # term is scaled by the measured valid-view count.  The pyramid is STORED as 4 x fp16 texels (exact for the
+        # u8-rounded values), so the bytes this layout must move are 84 + 384 per view: reported as *_layout.
         algo_bytes = 84.0 + 768.0 * valid_views
+        layout_bytes = 84.0 + 384.0 * valid_views
         achieved = per_gpu * algo_bytes / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -345,7 +348,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c.nbytes + n.nbytes + vw.nbytes + nv.nbytes),
                     "d2h_bytes_per_step": int(2 * N * 4), "ms_per_step": total_e2e / args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k1_ncc<7>", "algorithmic_bytes_per_eval": algo_bytes, "valid_views_per_eval": valid_views, "peak_source": peak_src,
+                         "kernel": "k1_ncc<7,4>", "algorithmic_bytes_per_eval": algo_bytes, "valid_views_per_eval": valid_views,
+                         "layout_bytes_per_eval": layout_bytes, "achieved_layout": per_gpu * layout_bytes / 1e9, "frac_layout": per_gpu * layout_bytes / 1e9 / peak,
+                         "note": "not HBM-bound: the pyramid stays L2/L1 resident; binding units per ncu (profiles/): L1TEX data pipe ~71%, issue slots ~74%", "peak_source": peak_src,
                          "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0)},
         }
         if world == 1 and not args.no_cpu_baseline:

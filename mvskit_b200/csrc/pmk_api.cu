@@ -6,6 +6,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -141,24 +142,24 @@ void refresh_params(pmk_ctx* ctx) {
     for (int k = -ctx->cfg.level + 1; k <= 2 && slot < PMK_MAX_LEVELS; ++k) p.level_thr[slot++] = level_threshold(k);
 }
 
-template <int WS>
+template <int WS, int MINB>
 int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
               void* incc, void* ncc, void* levels) {
     const int fstride = ctx->params.tau * K1_FRAME_WORDS + 4;
     const size_t smem = (size_t)K1_WARPS * 32 * fstride * sizeof(float);
     if (!ctx->k1_attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         ctx->k1_attr_done = true;
     }
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_ncc<WS>, K1_WARPS * 32, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_ncc<WS, MINB>, K1_WARPS * 32, smem));
     if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k1_ncc does not fit on an SM");
     const int nbatch = (n + 31) / 32;
     const int want = (nbatch + K1_WARPS - 1) / K1_WARPS;
     const int grid = std::max(1, std::min(want, ctx->sm_count * per_sm));
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), ctx->stream));
-    k1_ncc<WS><<<grid, K1_WARPS * 32, smem, ctx->stream>>>(ctx->params, n, (const float4*)coord, (const float4*)normal, (const int*)views,
+    k1_ncc<WS, MINB><<<grid, K1_WARPS * 32, smem, ctx->stream>>>(ctx->params, n, (const float4*)coord, (const float4*)normal, (const int*)views,
                                                           (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels, ctx->d_counters);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -167,11 +168,13 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
 
 int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
                 void* incc, void* ncc, void* levels) {
+    static const int minb = getenv("PMK_K1_MINB") ? atoi(getenv("PMK_K1_MINB")) : 4;   // tuning knob: CTAs/SM the kernel is compiled for
     switch (ctx->cfg.wsize) {
-        case 5: return launch_k1<5>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
-        case 7: return launch_k1<7>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
-        case 9: return launch_k1<9>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
-        case 11: return launch_k1<11>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 5: return launch_k1<5, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 7: return minb == 3 ? launch_k1<7, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels)
+                                 : launch_k1<7, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 9: return launch_k1<9, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 11: return launch_k1<11, 2>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
     }
     return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11");
 }
@@ -314,15 +317,15 @@ int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int
     CUDA_TRY(cudaMemcpyAsync(ctx->s_misc[0].p, rgb, npix0 * 3, cudaMemcpyHostToDevice, ctx->stream));
     for (int l = 0; l < nlevels; ++l) {
         void* d = nullptr;
-        CUDA_TRY(cudaMalloc(&d, (size_t)vc.w[l] * vc.h[l] * sizeof(float4)));
+        CUDA_TRY(cudaMalloc(&d, (size_t)vc.w[l] * vc.h[l] * sizeof(Texel)));
         ctx->owned.push_back(d);
-        vc.img[l] = (const float4*)d;
+        vc.img[l] = (const Texel*)d;
     }
-    k0_u8_to_rgbx<<<(unsigned)((npix0 + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->s_misc[0].p, (float4*)vc.img[0], (int)npix0);
+    k0_u8_to_rgbx<<<(unsigned)((npix0 + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->s_misc[0].p, (Texel*)vc.img[0], (int)npix0);
     ctx->launches++;
     for (int l = 1; l < nlevels; ++l) {
         dim3 blk(32, 8), grd((vc.w[l] + 31) / 32, (vc.h[l] + 7) / 8);
-        k0_downsample<<<grd, blk, 0, ctx->stream>>>(vc.img[l - 1], vc.w[l - 1], vc.h[l - 1], (float4*)vc.img[l], vc.w[l], vc.h[l]);
+        k0_downsample<<<grd, blk, 0, ctx->stream>>>(vc.img[l - 1], vc.w[l - 1], vc.h[l - 1], (Texel*)vc.img[l], vc.w[l], vc.h[l]);
         ctx->launches++;
     }
     CUDA_TRY(cudaGetLastError());

@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/pmk.h"
@@ -43,6 +44,20 @@ __device__ __forceinline__ V4 div4(V4 a, float s) { return V4{xdiv(a.x, s), xdiv
 __device__ __forceinline__ V3 div3(V3 a, float s) { return V3{xdiv(a.x, s), xdiv(a.y, s), xdiv(a.z, s)}; }
 __device__ __forceinline__ V4 mul4(V4 a, float s) { return V4{xmul(a.x, s), xmul(a.y, s), xmul(a.z, s), xmul(a.w, s)}; }
 
+// ---- image texel: R, G, B, X as four IEEE half floats (8 bytes).  The pyramid only ever holds the integers
+// 0..255 (every level is re-rounded to u8, image.cpp:308-310), which binary16 represents exactly, so widening
+// a texel to fp32 reproduces the reference's (float)uchar bit for bit at half the L1/L2/HBM traffic of fp32.
+typedef uint2 Texel;
+__device__ __forceinline__ Texel make_texel(float r, float g, float b) {
+    const __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, 0.0f);
+    return make_uint2(*reinterpret_cast<const unsigned int*>(&lo), *reinterpret_cast<const unsigned int*>(&hi));
+}
+__device__ __forceinline__ void texel_rgb(Texel t, float& r, float& g, float& b) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    r = lo.x; g = lo.y;
+    b = __low2float(*reinterpret_cast<const __half2*>(&t.y));
+}
+
 // ---- per-view constants (one per image, in global memory; 16-byte aligned rows) -------------------
 struct __align__(16) ViewConst {
     float P[12];                          // working-level projection rows (camera.cpp:91-100)
@@ -57,7 +72,7 @@ struct __align__(16) ViewConst {
     int pad0;
     int w[PMK_MAX_LEVELS];                // image.cpp:135-138
     int h[PMK_MAX_LEVELS];
-    const float4* img[PMK_MAX_LEVELS];    // RGBX float texels holding the u8-rounded pyramid (image.cpp:245-315)
+    const Texel* img[PMK_MAX_LEVELS];     // RGBX half-float texels holding the u8-rounded pyramid (image.cpp:245-315)
 };
 
 // scalars shared by all kernels (passed by value)
@@ -84,7 +99,7 @@ __device__ __forceinline__ V3 project(const float* __restrict__ P, V4 X) {
     V3 r;
     r.x = max_std(lo, min_std(hi, xdiv(i0, i2)));
     r.y = max_std(lo, min_std(hi, xdiv(i1, i2)));
-    r.z = xdiv(i2, i2);
+    r.z = (i2 < __int_as_float(0x7f800000)) ? 1.0f : __int_as_float(0x7fc00000);   // z / z for z > 0: 1, or NaN at +inf
     return r;
 }
 
@@ -98,16 +113,20 @@ __device__ __forceinline__ V3 project(const Proj& P, V4 X) {
     V3 r;
     r.x = max_std(lo, min_std(hi, xdiv(i0, i2)));
     r.y = max_std(lo, min_std(hi, xdiv(i1, i2)));
-    r.z = xdiv(i2, i2);
+    r.z = (i2 < __int_as_float(0x7f800000)) ? 1.0f : __int_as_float(0x7fc00000);   // z / z for z > 0: 1, or NaN at +inf
     return r;
 }
 
-// ---- Optim::getUnit (optim.cpp:34-41): 2.0 * fz * (1 << level) / ipscale in double, narrowed -----------
+// ---- Optim::getUnit (optim.cpp:34-41): (float)(2.0 * fz * (1 << level) / ipscale), evaluated in double --------
+// 2.0 * fz * 2^level is a power-of-two scaling (exact in float as well), and a correctly rounded double
+// quotient of two floats narrows to the correctly rounded float quotient (double rounding is innocuous for
+// division when the wide format has >= 2p + 2 = 50 bits; double has 53), so one fp32 divide is bit-identical.
+__device__ __forceinline__ float unit_from_dist(float fz, float ipscale, float level_scale) {
+    if (ipscale == 0.0f) return 1.0f;
+    return xdiv(xmul(fz, 2.0f * level_scale), ipscale);
+}
 __device__ __forceinline__ float get_unit(const ViewConst& vc, V4 X, float level_scale) {
-    const float fz = norm4(sub4(X, ld4(vc.center)));
-    if (vc.ipscale == 0.0f) return 1.0f;
-    // 2.0 * fz and * 2^level are exact in double; one correctly rounded divide, then one narrowing
-    return __double2float_rn(__ddiv_rn(2.0 * (double)fz * (double)level_scale, (double)vc.ipscale));
+    return unit_from_dist(norm4(sub4(X, ld4(vc.center))), vc.ipscale, level_scale);
 }
 
 // ---- Optim::getPAxes (optim.cpp:67-84) ------------------------------------------------------------------
@@ -133,6 +152,7 @@ __device__ __forceinline__ void get_paxes(const ViewConst& vc, V4 X, V4 N, float
 struct Frame {
     float tlx, tly, dxx, dxy, dyx, dyy;
     int level;
+    float unit;      // Optim::computeUnits entry for this view (optim.cpp:109-132)
 };
 
 __device__ __forceinline__ Frame make_frame(const Params& p, const ViewConst& vc, V4 X, V4 N, V4 px, V4 py) {
@@ -140,8 +160,12 @@ __device__ __forceinline__ Frame make_frame(const Params& p, const ViewConst& vc
     f.level = -1;
     f.tlx = f.tly = f.dxx = f.dxy = f.dyx = f.dyy = 0.0f;
     V4 ray = sub4(ld4(vc.center), X);
-    ray = div4(ray, norm4(ray));
-    const float weight = max_std(0.0f, dot4(ray, N));
+    const float dist = norm4(ray);          // == ||X - center|| bit for bit (squares of negated terms)
+    ray = div4(ray, dist);
+    const float rn = dot4(ray, N);
+    // computeUnits: getUnit / (ray . n), INT_MAX / 2 when back-facing
+    f.unit = (0.0f < rn) ? xdiv(unit_from_dist(dist, vc.ipscale, p.level_scale), rn) : 1073741824.0f;
+    const float weight = max_std(0.0f, rn);
     if (weight < p.cos_angle1) return f;
     const Proj P = load_proj(vc.P);
     V3 c = project(P, X);
@@ -187,18 +211,20 @@ __device__ __forceinline__ float view_unit(const Params& p, const ViewConst& vc,
 // ---- PatchManager::setGrids cell index (patch_manager.cpp:229-231,245-247) --------------------------------
 __device__ __forceinline__ int cell_of(float u, int csize) { return ((int)floorf(xadd(u, 0.5f))) / csize; }
 
-// ---- Image::getColor bilinear (image.cpp:448-471) on RGBX float texels --------------------------------------
+// ---- Image::getColor bilinear (image.cpp:448-471) on RGBX half-float texels --------------------------------------
 // Truncating index, reference tap weights; the blend itself is tolerance-bound and uses FMAs.
-__device__ __forceinline__ void bilinear(const float4* __restrict__ img, int W, float x, float y, float& r, float& g, float& b) {
+__device__ __forceinline__ void bilinear(const Texel* __restrict__ img, int W, float x, float y, float& r, float& g, float& b) {
     const int lx = (int)x, ly = (int)y;
     const float dx1 = xsub(x, (float)lx), dx0 = xsub(1.0f, dx1);
     const float dy1 = xsub(y, (float)ly), dy0 = xsub(1.0f, dy1);
     const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
-    const float4* p0 = img + (size_t)ly * W + lx;
-    const float4 a = __ldg(p0), c = __ldg(p0 + 1), d = __ldg(p0 + W), e = __ldg(p0 + W + 1);
-    r = fmaf(e.x, f11, fmaf(c.x, f10, fmaf(d.x, f01, a.x * f00)));
-    g = fmaf(e.y, f11, fmaf(c.y, f10, fmaf(d.y, f01, a.y * f00)));
-    b = fmaf(e.z, f11, fmaf(c.z, f10, fmaf(d.z, f01, a.z * f00)));
+    const Texel* p0 = img + (size_t)ly * W + lx;
+    const Texel ta = __ldg(p0), tc = __ldg(p0 + 1), td = __ldg(p0 + W), te = __ldg(p0 + W + 1);
+    float ar, ag, ab, cr, cg, cb, dr, dg, db, er, eg, eb;
+    texel_rgb(ta, ar, ag, ab); texel_rgb(tc, cr, cg, cb); texel_rgb(td, dr, dg, db); texel_rgb(te, er, eg, eb);
+    r = fmaf(er, f11, fmaf(cr, f10, fmaf(dr, f01, ar * f00)));
+    g = fmaf(eg, f11, fmaf(cg, f10, fmaf(dg, f01, ag * f00)));
+    b = fmaf(eb, f11, fmaf(cb, f10, fmaf(db, f01, ab * f00)));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -9,16 +9,16 @@ namespace pmk {
 // K0: image pyramid.  Image::buildImagePyramid (image/image.cpp:245-315), filter == 0.
 // The 4x4 [1 3 3 1]x[1 3 3 1]/64 taps times u8 values are exact in fp32 and so are their partial sums
 // (multiples of 1/64 below 256), so any summation order reproduces the reference bit for bit; the
-// result is re-rounded to an integer (floorf(c + 0.5f)) and stored as float RGBX.
+// result is re-rounded to an integer (floorf(c + 0.5f)) and stored as a half-float RGBX texel (exact for 0..255).
 // =====================================================================================================
-__global__ void k0_u8_to_rgbx(const uint8_t* __restrict__ src, float4* __restrict__ dst, int npix) {
+__global__ void k0_u8_to_rgbx(const uint8_t* __restrict__ src, Texel* __restrict__ dst, int npix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     const uint8_t* p = src + (size_t)i * 3;
-    dst[i] = make_float4((float)p[0], (float)p[1], (float)p[2], 0.0f);
+    dst[i] = make_texel((float)p[0], (float)p[1], (float)p[2]);
 }
 
-__global__ void k0_downsample(const float4* __restrict__ src, int Wp, int Hp, float4* __restrict__ dst, int W, int H) {
+__global__ void k0_downsample(const Texel* __restrict__ src, int Wp, int Hp, Texel* __restrict__ dst, int W, int H) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -32,19 +32,21 @@ __global__ void k0_downsample(const float4* __restrict__ src, int Wp, int Hp, fl
         for (int j = -1; j < 3; ++j) {
             const int xt = 2 * x + j;
             if (xt < 0 || Wp - 1 < xt) continue;
-            const float4 t = __ldg(src + (size_t)yt * Wp + xt);
+            float tr, tg, tb;
+            texel_rgb(__ldg(src + (size_t)yt * Wp + xt), tr, tg, tb);
             const float wgt = k4[i + 1] * k4[j + 1];
-            r += wgt * t.x; g += wgt * t.y; b += wgt * t.z;
+            r += wgt * tr; g += wgt * tg; b += wgt * tb;
         }
     }
-    dst[(size_t)y * W + x] = make_float4(floorf(r + 0.5f), floorf(g + 0.5f), floorf(b + 0.5f), 0.0f);
+    dst[(size_t)y * W + x] = make_texel(floorf(r + 0.5f), floorf(g + 0.5f), floorf(b + 0.5f));
 }
 
-__global__ void k0_rgbx_to_u8(const float4* __restrict__ src, uint8_t* __restrict__ dst, int npix) {
+__global__ void k0_rgbx_to_u8(const Texel* __restrict__ src, uint8_t* __restrict__ dst, int npix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    const float4 t = src[i];
-    dst[(size_t)i * 3] = (uint8_t)t.x; dst[(size_t)i * 3 + 1] = (uint8_t)t.y; dst[(size_t)i * 3 + 2] = (uint8_t)t.z;
+    float r, g, b;
+    texel_rgb(src[i], r, g, b);
+    dst[(size_t)i * 3] = (uint8_t)r; dst[(size_t)i * 3 + 1] = (uint8_t)g; dst[(size_t)i * 3 + 2] = (uint8_t)b;
 }
 
 // =====================================================================================================
@@ -55,54 +57,32 @@ __global__ void k0_rgbx_to_u8(const float4* __restrict__ src, uint8_t* __restric
 //   phase B  lane = hypothesis,     loop over its <= tau views: sampling frame (angle gate, 3 projections,
 //            pyramid level, getTexSafe) and computeUnits weight; frames go to warp-private shared memory
 //                                                                                      (optim.cpp:790-833,895-915,109-132)
-//   phase C  warp = hypothesis,     lane = sample of the wsize x wsize lattice: bilinear gather, normalise,
-//            dot against the reference view with warp-shuffle reductions               (optim.cpp:835-842,917-940,601-609)
+//   phase C  32/GW hypotheses at a time, GW = 8 lanes each (16 for wsize > 8): lane = lattice column, loop over
+//            rows: bilinear gather, normalise, dot against the reference view; sums are 3-step shuffle
+//            reductions inside each lane group, shared by all groups         (optim.cpp:835-842,917-940,601-609)
 //   phase D  lane = hypothesis      robust weighted mean                               (optim.cpp:686-703)
 // Phases A, B and D keep all 32 lanes busy with distinct hypotheses; only phase C is per-hypothesis.
 // =====================================================================================================
 constexpr int K1_WARPS = 8;            // warps per CTA
 constexpr int K1_FRAME_WORDS = 8;      // tlx tly dxx dxy dyx dyy (level | view << 4) weight
 
-// Butterfly reduction of four values at once: 6 shuffles leave the totals of (a, b, c, d) in lanes
-// 0, 8, 16 and 24; three more broadcast the first three to every lane.
-__device__ __forceinline__ void warp_sum3_all(int lane, float& a, float& b, float& c) {
-    const bool h16 = lane & 16, h8 = lane & 8;
-    float k0 = h16 ? c : a, k1 = h16 ? 0.0f : b;
-    const float s0 = h16 ? a : c, s1 = h16 ? b : 0.0f;
-    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-    float k = h8 ? k1 : k0;
-    const float s = h8 ? k0 : k1;
-    k += __shfl_xor_sync(0xffffffffu, s, 8);
-    k += __shfl_xor_sync(0xffffffffu, k, 4);
-    k += __shfl_xor_sync(0xffffffffu, k, 2);
-    k += __shfl_xor_sync(0xffffffffu, k, 1);
-    a = __shfl_sync(0xffffffffu, k, 0);
-    b = __shfl_sync(0xffffffffu, k, 8);
-    c = __shfl_sync(0xffffffffu, k, 16);
+// sum over the aligned group of GW lanes this lane belongs to (every lane of the group gets the total)
+template <int GW>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
-// Two values: 5 shuffles; the total of `a` lands in lanes 0-15, the total of `b` in lanes 16-31.
-__device__ __forceinline__ float warp_sum2_split(int lane, float a, float b) {
-    const bool h16 = lane & 16;
-    float k = h16 ? b : a;
-    const float s = h16 ? a : b;
-    k += __shfl_xor_sync(0xffffffffu, s, 16);
-    k += __shfl_xor_sync(0xffffffffu, k, 8);
-    k += __shfl_xor_sync(0xffffffffu, k, 4);
-    k += __shfl_xor_sync(0xffffffffu, k, 2);
-    k += __shfl_xor_sync(0xffffffffu, k, 1);
-    return k;
-}
-
-template <int WS>
-__global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_ncc(const Params p, int n, const float4* __restrict__ coord,
-                                                           const float4* __restrict__ normal, const int* __restrict__ views,
-                                                           const int* __restrict__ nviews, int stride,
-                                                           float* __restrict__ incc_out, float* __restrict__ ncc_out,
-                                                           int* __restrict__ levels_out, unsigned int* __restrict__ next_batch) {
+template <int WS, int MINB>
+__global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, int n, const float4* __restrict__ coord,
+                                                              const float4* __restrict__ normal, const int* __restrict__ views,
+                                                              const int* __restrict__ nviews, int stride,
+                                                              float* __restrict__ incc_out, float* __restrict__ ncc_out,
+                                                              int* __restrict__ levels_out, unsigned int* __restrict__ next_batch) {
     constexpr int NSAMP = WS * WS;
-    constexpr int NS = (NSAMP + 31) / 32;                 // sample slots per lane
+    constexpr int GW = WS <= 8 ? 8 : 16;                  // lanes that share one hypothesis in phase C
+    constexpr int G = 32 / GW;                            // hypotheses sampled concurrently by a warp
     constexpr float INV_NSAMP = 1.0f / (float)NSAMP;
     constexpr float INV_3NSAMP = 1.0f / (float)(3 * NSAMP);
     extern __shared__ __align__(16) float smem[];
@@ -113,16 +93,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_ncc(const Params p, int n
     const int fstride = p.tau * K1_FRAME_WORDS + 4;
     float* frames = smem + (size_t)warp_in_cta * 32 * fstride;
     const int nbatch = (n + 31) / 32;
-
-    // lattice coordinates of this lane's sample slots; slots past the lattice re-sample the last point
-    // (same address for those lanes: a broadcast) and are masked out of every sum
-    float lx[NS], ly[NS], lm[NS];
-#pragma unroll
-    for (int q = 0; q < NS; ++q) {
-        const int s = lane + 32 * q;
-        const int sc = s < NSAMP ? s : NSAMP - 1;
-        lx[q] = (float)(sc % WS); ly[q] = (float)(sc / WS); lm[q] = s < NSAMP ? 1.0f : 0.0f;
-    }
+    const int grp = lane / GW, col = lane % GW;           // phase C: hypothesis slot and lattice column of this lane
+    const float cmask = col < WS ? 1.0f : 0.0f;           // lanes past the lattice width contribute nothing
+    const float fcol = (float)(col < WS ? col : WS - 1);
 
     // batches are handed out through a global counter: hypotheses differ a lot in cost (0..tau valid views)
     for (;;) {
@@ -156,7 +129,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_ncc(const Params p, int n
             float unit0 = 1.0f;
 #pragma unroll 1
             for (int k = 0; k < p.tau; ++k) {
-                Frame f; f.level = -1; f.tlx = f.tly = f.dxx = f.dxy = f.dyx = f.dyy = 0.0f;
+                Frame f; f.level = -1; f.tlx = f.tly = f.dxx = f.dxy = f.dyx = f.dyy = 0.0f; f.unit = 1.0f;
                 float w = 0.0f;
                 int vk = 0;
                 if (ref_ok && k < sz) {
@@ -165,13 +138,17 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_ncc(const Params p, int n
                         vk = v;
                         const ViewConst& vc = p.views[v];
                         f = make_frame(p, vc, X, N, px, py);
-                        const float u = view_unit(p, vc, X, N);
-                        if (k == 0) { unit0 = u; w = 1.0f; }
-                        else w = min_std(1.0f, xdiv(unit0, u));                 // optim.cpp:944-946
+                        if (k == 0) { unit0 = f.unit; w = 1.0f; }
+                        else w = min_std(1.0f, xdiv(unit0, f.unit));            // optim.cpp:944-946
                     }
                 }
                 if (live && levels_out) levels_out[(size_t)h * p.tau + k] = f.level;
                 if (f.level >= 0) valid_mask |= 1 << k;
+                else {
+                    // frames nobody may sample still get a harmless target (texel (2,2) of view 0 at the working
+                    // level, zero pitch) so that phase C can run branch-free over every lane group
+                    f.tlx = f.tly = 2.0f; f.dxx = f.dxy = f.dyx = f.dyy = 0.0f; f.level = p.level; vk = 0;
+                }
                 float* fr = myrow + k * K1_FRAME_WORDS;
                 *reinterpret_cast<float4*>(fr) = make_float4(f.tlx, f.tly, f.dxx, f.dxy);
                 *reinterpret_cast<float4*>(fr + 4) = make_float4(f.dyx, f.dyy, __int_as_float((f.level & 15) | (vk << 4)), w);
@@ -179,64 +156,85 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 3) k1_ncc(const Params p, int n
         }
         __syncwarp();
 
-        // ---------------- phase C: warp = hypothesis, lane = sample ----------------
-        // a hypothesis needs the gather only if its reference view and at least one other are valid
+        // ---------------- phase C: G hypotheses per pass, GW lanes each; lane = lattice column, loop = row ----------------
+        // Branch-free over the warp: lanes past the lattice width re-sample the last column and invalid frames
+        // point at a harmless texel (phase B); both are kept out of the sums arithmetically (cmask) or simply never
+        // stored, so there is no divergence inside the gather.
+        // A hypothesis needs the gather only if its reference view and at least one other are valid.
         const bool need = usable && (valid_mask & 1) && (valid_mask & ~1);
-        unsigned todo = __ballot_sync(0xffffffffu, need);
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int vm = __shfl_sync(0xffffffffu, valid_mask, j);
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+#pragma unroll 1
+        for (int i = 0; i < 32 / G; ++i) {
+            if (!((need_mask >> (i * G)) & ((1u << G) - 1u))) continue;      // warp-uniform: nobody in this pass
+            const int j = i * G + grp;                                         // this lane's hypothesis
+            const int vmj = __shfl_sync(0xffffffffu, valid_mask, j);
+            const int vm = ((need_mask >> j) & 1u) ? vmj : 0;
+            const unsigned any_vm = __reduce_or_sync(0xffffffffu, (unsigned)vm);
             float* row = frames + (size_t)j * fstride;
-            float t0[NS][3];                                   // centred (not yet scaled) reference texture
+            float t0[WS][3];                                   // centred reference texture: this lane's column
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;                // reference-view channel means (times cmask)
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;                // residual sums of the centred reference texture
             float inv_msd0 = 1.0f;
 #pragma unroll 1
             for (int k = 0; k < p.tau; ++k) {
-                if (!((vm >> k) & 1)) continue;                // warp-uniform
+                if (!((any_vm >> k) & 1u)) continue;           // warp-uniform
                 const float* fr = row + k * K1_FRAME_WORDS;
                 const float4 fa = *reinterpret_cast<const float4*>(fr);
                 const float4 fb = *reinterpret_cast<const float4*>(fr + 4);
                 const int packed = __float_as_int(fb.z);
-                const int lvl = packed & 15;
                 const ViewConst& vc = p.views[packed >> 4];
-                const float4* img = vc.img[lvl];
-                const int W = vc.w[lvl];
-                float t[NS][3];
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    // Vector3f samp = tl + dx * x + dy * y   (optim.cpp:837); tolerance domain -> FMAs
-                    const float sx = fmaf(fb.x, ly[q], fmaf(fa.z, lx[q], fa.x));
-                    const float sy = fmaf(fb.y, ly[q], fmaf(fa.w, lx[q], fa.y));
-                    bilinear(img, W, sx, sy, t[q][0], t[q][1], t[q][2]);
-                    s0 = fmaf(t[q][0], lm[q], s0); s1 = fmaf(t[q][1], lm[q], s1); s2 = fmaf(t[q][2], lm[q], s2);
-                }
-                // Optim::normalize (optim.cpp:917-940): per-channel mean, joint variance
-                warp_sum3_all(lane, s0, s1, s2);
-                const float a0 = s0 * INV_NSAMP, a1 = s1 * INV_NSAMP, a2 = s2 * INV_NSAMP;
-                float ssd = 0.f, dp = 0.f;
-#pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    t[q][0] = (t[q][0] - a0) * lm[q]; t[q][1] = (t[q][1] - a1) * lm[q]; t[q][2] = (t[q][2] - a2) * lm[q];
-                    ssd = fmaf(t[q][0], t[q][0], fmaf(t[q][1], t[q][1], fmaf(t[q][2], t[q][2], ssd)));
-                }
+                const Texel* img = vc.img[packed & 15];
+                const int W = vc.w[packed & 15];
+                // Vector3f samp = tl + dx * x + dy * y   (optim.cpp:837); tolerance domain -> FMAs
+                const float bx = fmaf(fa.z, fcol, fa.x), by = fmaf(fa.w, fcol, fa.y);
                 if (k == 0) {
-                    ssd = warp_sum(ssd);
+                    // Optim::normalize (optim.cpp:917-940) of the reference texture: per-channel mean, joint variance
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int y = 0; y < WS; ++y) {
+                        bilinear(img, W, fmaf(fb.x, (float)y, bx), fmaf(fb.y, (float)y, by), t0[y][0], t0[y][1], t0[y][2]);
+                        s0 = fmaf(t0[y][0], cmask, s0); s1 = fmaf(t0[y][1], cmask, s1); s2 = fmaf(t0[y][2], cmask, s2);
+                    }
+                    a0 = group_sum<GW>(s0) * INV_NSAMP; a1 = group_sum<GW>(s1) * INV_NSAMP; a2 = group_sum<GW>(s2) * INV_NSAMP;
+                    const float m0 = -a0 * cmask, m1 = -a1 * cmask, m2 = -a2 * cmask;
+                    float ssd = 0.f;
+                    c0 = c1 = c2 = 0.f;
+#pragma unroll
+                    for (int y = 0; y < WS; ++y) {
+                        t0[y][0] = fmaf(t0[y][0], cmask, m0); t0[y][1] = fmaf(t0[y][1], cmask, m1); t0[y][2] = fmaf(t0[y][2], cmask, m2);
+                        c0 += t0[y][0]; c1 += t0[y][1]; c2 += t0[y][2];
+                        ssd = fmaf(t0[y][0], t0[y][0], fmaf(t0[y][1], t0[y][1], fmaf(t0[y][2], t0[y][2], ssd)));
+                    }
+                    ssd = group_sum<GW>(ssd);
+                    c0 = group_sum<GW>(c0); c1 = group_sum<GW>(c1); c2 = group_sum<GW>(c2);
                     const float var = ssd * INV_3NSAMP;
                     inv_msd0 = var > 0.0f ? rsqrtf(var) : 1.0f;            // msd == 0 -> 1 (optim.cpp:934-936)
-#pragma unroll
-                    for (int q = 0; q < NS; ++q) { t0[q][0] = t[q][0]; t0[q][1] = t[q][1]; t0[q][2] = t[q][2]; }
                 } else {
-                    // Optim::dot (optim.cpp:601-609): sum(tex0 . tex_k) / (3 * sz)
+                    // one pass over view k, centred on the REFERENCE view's channel means (photo-consistent views
+                    // differ little from them, so the moment subtraction below does not cancel):
+                    //   u = tex_k - a_ref;  mean_k = a_ref + sum(u)/n;  ssd_k = sum(u^2) - n * |sum(u)/n|^2
+                    //   sum(t0 * (tex_k - mean_k)) = sum(t0 * u) - (sum(u)/n) . sum(t0)
+                    const float m0 = -a0 * cmask, m1 = -a1 * cmask, m2 = -a2 * cmask;
+                    float u0 = 0.f, u1 = 0.f, u2 = 0.f, uu = 0.f, tu = 0.f;
 #pragma unroll
-                    for (int q = 0; q < NS; ++q)
-                        dp = fmaf(t0[q][0], t[q][0], fmaf(t0[q][1], t[q][1], fmaf(t0[q][2], t[q][2], dp)));
-                    const float r = warp_sum2_split(lane, ssd, dp);        // lanes 0-15: ssd, lanes 16-31: dp
-                    const float dpt = __shfl_sync(0xffffffffu, r, 16);
-                    if (lane == 0) {
-                        const float var = r * INV_3NSAMP;
+                    for (int y = 0; y < WS; ++y) {
+                        float r, g, b;
+                        bilinear(img, W, fmaf(fb.x, (float)y, bx), fmaf(fb.y, (float)y, by), r, g, b);
+                        r = fmaf(r, cmask, m0); g = fmaf(g, cmask, m1); b = fmaf(b, cmask, m2);
+                        u0 += r; u1 += g; u2 += b;
+                        uu = fmaf(r, r, fmaf(g, g, fmaf(b, b, uu)));
+                        tu = fmaf(t0[y][0], r, fmaf(t0[y][1], g, fmaf(t0[y][2], b, tu)));
+                    }
+                    u0 = group_sum<GW>(u0) * INV_NSAMP; u1 = group_sum<GW>(u1) * INV_NSAMP; u2 = group_sum<GW>(u2) * INV_NSAMP;
+                    uu = group_sum<GW>(uu);
+                    tu = group_sum<GW>(tu);
+                    if (col == 0 && ((vm >> k) & 1)) {
+                        const float ssd = fmaxf(uu - (float)NSAMP * fmaf(u0, u0, fmaf(u1, u1, u2 * u2)), 0.0f);
+                        const float var = ssd * INV_3NSAMP;
                         const float inv_msd = var > 0.0f ? rsqrtf(var) : 1.0f;
-                        row[k * K1_FRAME_WORDS] = dpt * inv_msd0 * inv_msd * INV_3NSAMP;   // overwrites tlx (consumed)
+                        const float dp = tu - fmaf(u0, c0, fmaf(u1, c1, u2 * c2));
+                        // Optim::dot (optim.cpp:601-609): sum(tex0 . tex_k) / (3 * sz); overwrites tlx (consumed)
+                        row[k * K1_FRAME_WORDS] = dp * inv_msd0 * inv_msd * INV_3NSAMP;
                     }
                 }
             }
