@@ -306,11 +306,14 @@ class Scene:
         return out
 
     def hypotheses(self, n: int, seed: int = 7, depth_jitter: float = 0.02, normal_jitter_deg: float = 20.0, tau: int = 6,
-                   order: str = "random"):
+                   order: str = "random", well_observed: bool = True):
         """n hypotheses around ground truth, each with up to tau views ([0] = reference).
 
         order="random": random pixels of each reference view in draw order; order="grid": the same draws sorted
         in Z-order of their reference pixel, i.e. the spatially coherent order in which a patch grid is walked.
+        well_observed=True keeps only pixels whose ground-truth point faces the reference view and is seen by
+        tau-1 other views (every eval then samples all tau views); False keeps every draw, so the set also holds
+        hypotheses with missing, back-facing or out-of-image views (edge cases for the parity tests).
         Returns coord (n,4) f32, normal (n,4) f32, views (n,tau) i32 (-1 padded, compacted), nviews (n,) i32.
         """
         rng = np.random.RandomState(seed)
@@ -333,7 +336,9 @@ class Scene:
                 ray = self.eyes[v] - X
                 ray /= np.linalg.norm(ray, axis=-1, keepdims=True)
                 good = hit & (np.sum(ray * nrm, -1) > cos_ref)
-                if rounds < 11:
+                if not well_observed:
+                    good = np.ones_like(hit)
+                elif rounds < 11:
                     idx = np.nonzero(good)[0]
                     if idx.size:
                         vw = self.neighbours(X[idx], nrm[idx], v, tau, cos_min=cos_nb)

@@ -85,7 +85,10 @@ def reflib(scene_dir):
 
 @pytest.fixture(scope="session")
 def hyps(small_scene):
-    return small_scene.hypotheses(4096, seed=7)
+    """Half well-observed hypotheses (all tau views valid), half unfiltered draws (missing / back-facing views)."""
+    a = small_scene.hypotheses(2048, seed=7, well_observed=True)
+    b = small_scene.hypotheses(2048, seed=8, well_observed=False, normal_jitter_deg=35.0)
+    return tuple(np.concatenate([x, y]) for x, y in zip(a, b))
 
 
 def bits(a):

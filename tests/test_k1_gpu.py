@@ -95,7 +95,7 @@ def test_ncc_parity_plane(ctx, coracle, hyps):
 
 
 def test_ncc_parity_sphere_with_occlusion(ctx_sphere, coracle_sphere, sphere_scene):
-    hyp = sphere_scene.hypotheses(4096, seed=11, depth_jitter=0.03, normal_jitter_deg=30.0)
+    hyp = sphere_scene.hypotheses(4096, seed=11, depth_jitter=0.03, normal_jitter_deg=30.0, well_observed=False)
     _check_ncc(ctx_sphere, coracle_sphere, hyp)
 
 
@@ -137,7 +137,7 @@ def test_ncc_edge_cases(ctx, coracle, small_scene, hyps):
 def test_ncc_batch_invariance_large(ctx, small_scene):
     """Size-independent properties at a size the oracle is not run on: results do not depend on the order
     or the batching of hypotheses (each eval is independent), and repeated launches are deterministic."""
-    c, n, vw, nv = small_scene.hypotheses(1 << 18, seed=99)
+    c, n, vw, nv = small_scene.hypotheses(1 << 18, seed=99, well_observed=False)
     a = ctx.ncc_eval(c, n, vw, nv)[0]
     b = ctx.ncc_eval(c, n, vw, nv)[0]
     assert_bits_equal(a, b, "determinism")
@@ -148,7 +148,7 @@ def test_ncc_batch_invariance_large(ctx, small_scene):
     s = np.concatenate([ctx.ncc_eval(c[:h], n[:h], vw[:h], nv[:h])[0], ctx.ncc_eval(c[h:], n[h:], vw[h:], nv[h:])[0]])
     assert_bits_equal(s, a, "split invariance")
     ok = a != 2.0
-    assert ok.mean() > 0.8 and (a[ok] >= 0).all() and (a[ok] < 0.7).all()     # robust incc range: x/(1+3x) < 1/3 .. 2/7
+    assert ok.mean() > 0.5 and (a[ok] >= 0).all() and (a[ok] < 0.7).all()     # robust incc range: x/(1+3x) < 1/3 .. 2/7
 
 
 def test_state_errors(small_scene):
