@@ -81,7 +81,7 @@ int pmk_abi_version(void);
 /* Photo::init + Image::alloc + buildImagePyramid for one view (image/photoSet.cpp:20-61,
  * image/camera.cpp:27-100, image/image.cpp:92-192,245-315).  `P` is the level-0 3x4 projection
  * ("CONTOUR" camera file), `rgb` interleaved u8 of width*height*3.  Builds the level+3 level
- * pyramid on the device (kernel K0) as float RGBX texels holding the u8-rounded values. */
+ * pyramid on the device (kernel K0) as 4 x fp16 RGBX texels holding the u8-rounded values (exact). */
 int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int width, int height);
 
 int pmk_get_thresholds(pmk_ctx* ctx, pmk_thresholds* out);
@@ -105,6 +105,41 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
 /* Device-pointer variant: enqueues on the context stream and returns. */
 int pmk_ncc_eval_dev(pmk_ctx* ctx, int n, const void* d_coord4, const void* d_normal4, const void* d_views,
                      const void* d_nviews, int stride, void* d_incc_out, void* d_ncc_out, void* d_levels_out);
+
+/* K2 -- Optim::setINCCs (optim.cpp:708-783) for n patches {coord, normal, images}: robust = isRobust.
+ *   pairwise == 0: 1-vs-all, out[n][stride]          (out[i][0] = 0, 2.0f where a texture is missing)
+ *   pairwise == 1: all pairs, out[n][stride][stride] (symmetric, zero diagonal)
+ * Unlike computeINCC this looks at EVERY listed image, not just the first tau (stride <= 128). */
+int pmk_set_inccs(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews,
+                  int stride, int robust, int pairwise, float* out);
+
+/* Optim::preProcess (optim.cpp:137-163) on fresh candidates {coord, normal, images}: addImages, constraintImages at
+ * m_nccThresholdBefore, sortImages, PatchManager::setScales (patch_manager.cpp:378-399), PhotoSet::checkAngles
+ * (photoSet.cpp:77-103).  ret[i] = the reference's return value (0 / -1); images_out[i][maxv] (-1 padded) and
+ * nimages_out[i] = m_images afterwards (cleared, like the reference, when checkAngles fails). */
+int pmk_pre_process(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews,
+                    int stride, int maxv, int* ret, int* images_out, int* nimages_out, float* dscale_out, float* ascale_out);
+
+/* Optim::cost_func (optim.cpp:401-468): objective of the refinement, at nitems encoded points x3[i] (depth along the
+ * reference ray / dscale, two normal angles / (pi/48)); item i belongs to patch patch_of_item[i], whose context
+ * (m_center, m_ray, m_indexes, m_dscale) is set up as refinePatch does (optim.cpp:481-490). */
+int pmk_cost_func(pmk_ctx* ctx, int npatches, const float* coord4, const float* normal4, const float* dscale, const int* views,
+                  const int* nviews, int stride, int nitems, const int* patch_of_item, const double* x3, double* cost_out);
+
+/* K3 -- Optim::refinePatch (optim.cpp:470-547).  The reference drives NLopt BOBYQA (third party, absent, unpinned);
+ * this path runs the seeded counter-based schedule PMR1 over the same 3 variables, bounds and objective:
+ * 1 + 12 levels x 8 candidates = 97 cost_func evaluations, Philox4x32-10 keyed by `seed`, counter (streams[i], level,
+ * candidate).  coord4 / normal4 are updated in place; ncc_out = 1 - unrobustincc(computeINCC) with the pre-refinement
+ * weights (optim.cpp:539).  trace_out (optional): n x 97 x {x0, x1, x2, cost} doubles, every evaluated point. */
+int pmk_refine(pmk_ctx* ctx, int n, float* coord4, float* normal4, const float* dscale, const int* views, const int* nviews,
+               int stride, const uint64_t* streams, uint64_t seed, float* ncc_out, double* trace_out);
+
+/* Optim::postProcess (optim.cpp:260-290) up to and including m_tmp = score2: addImages, constraintImages at
+ * m_nccThreshold, filterImagesByAngle, setRefImage (pairwise INCC), constraintImages, PatchManager::setGrids.
+ * The tail that reads the patch store (setVImagesVGrids, check; optim.cpp:291-296) runs in pmk_propagate. */
+int pmk_post_process(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* ncc, const int* views,
+                     const int* nviews, int stride, int maxv, int* ret, int* images_out, int* nimages_out, int* grids_out,
+                     float* tmp_out);
 
 /* Probes of the device-side building blocks, for parity tests (each item independent):
  *   project  : Camera::project at the working level        (camera.cpp:310-326)   -> out3

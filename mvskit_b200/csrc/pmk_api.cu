@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "pmk_ncc.cuh"
+#include "pmk_cand.cuh"
 
 using namespace pmk;
 
@@ -93,6 +93,10 @@ struct pmk_ctx {
     size_t flush_bytes = 0;
     uint64_t launches = 0;
     bool k1_attr_done = false;
+    std::vector<Scratch> pool;               // staging buffers of the host-pointer entry points
+    float* tex_scratch = nullptr;
+    float* mat_scratch = nullptr;
+    int cand_grid = 0;
     // PmMvps thresholds (pmmvps.cpp:54-67)
     float angle_threshold0, angle_threshold1, neighbor_threshold, neighbor_threshold1, neighbor_threshold2;
     float ncc_threshold, ncc_threshold_before;
@@ -179,6 +183,77 @@ int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, cons
     return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11");
 }
 
+
+// ---- candidate-kernel plumbing ------------------------------------------------------------------------------------
+// order-preserving map between floats and unsigned ints, for bisection over float values
+inline uint32_t f2o(float f) { uint32_t u; std::memcpy(&u, &f, 4); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+inline float o2f(uint32_t o) { uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; float f; std::memcpy(&f, &u, 4); return f; }
+// const float angle = acos(dot) with the unqualified (double) acos, narrowed (photoSet.cpp:92)
+inline float acos_ref(float d) { return (float)std::acos((double)d); }
+
+AngleGate make_gate(float min_angle, float max_angle) {
+    AngleGate g;
+    {   // smallest d in [-1, 1] with acos_ref(d) < max_angle (predicate is monotone: false ... true)
+        uint32_t lo = f2o(-1.0f), hi = f2o(1.0f);
+        if (acos_ref(-1.0f) < max_angle) g.dot_ge = -1.0f;
+        else if (!(acos_ref(1.0f) < max_angle)) g.dot_ge = 2.0f;
+        else { while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (acos_ref(o2f(mid)) < max_angle) hi = mid; else lo = mid; } g.dot_ge = o2f(hi); }
+    }
+    {   // largest d in [-1, 1] with min_angle < acos_ref(d) (true ... false)
+        uint32_t lo = f2o(-1.0f), hi = f2o(1.0f);
+        if (min_angle < acos_ref(1.0f)) g.dot_le = 1.0f;
+        else if (!(min_angle < acos_ref(-1.0f))) g.dot_le = -2.0f;
+        else { while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (min_angle < acos_ref(o2f(mid))) lo = mid; else hi = mid; } g.dot_le = o2f(lo); }
+    }
+    return g;
+}
+
+int cand_params(pmk_ctx* ctx, CandParams& cp, uint64_t seed) {
+    if (ctx->cfg.nviews > CAND_MAXV) return fail(PMK_ERR_ARG, "pmk: the candidate kernels support at most 128 views");
+    const int ws = ctx->cfg.wsize, texw = ws * ws * 3 + 4;
+    if (!ctx->cand_grid) {
+        ctx->cand_grid = ctx->sm_count * 4;
+        const size_t warps = (size_t)ctx->cand_grid * CAND_WARPS;
+        CUDA_TRY(cudaMalloc((void**)&ctx->tex_scratch, warps * ctx->cfg.nviews * texw * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&ctx->mat_scratch, warps * ctx->cfg.nviews * ctx->cfg.nviews * sizeof(float)));
+        ctx->owned.push_back(ctx->tex_scratch);
+        ctx->owned.push_back(ctx->mat_scratch);
+    }
+    cp.p = ctx->params;
+    cp.gate = make_gate(ctx->cfg.max_angle_threshold, ctx->angle_threshold1);           // optim.cpp:153-156
+    cp.sort_threshold = (float)(1.0f - std::cos(10.0f * M_PI / 180.0f));                // optim.cpp:222
+    cp.ascale = (float)(M_PI / 48.0f);                                                   // optim.cpp:487
+    cp.tex_scratch = ctx->tex_scratch;
+    cp.mat_scratch = ctx->mat_scratch;
+    cp.seed = seed;
+    return PMK_OK;
+}
+
+// stage a host array into pool slot `slot`; returns the device pointer through *out
+int stage_in(pmk_ctx* ctx, int slot, const void* host, size_t bytes, void** out) {
+    if ((int)ctx->pool.size() <= slot) ctx->pool.resize(slot + 1);
+    int rc = ensure(ctx, ctx->pool[slot], bytes ? bytes : 16);
+    if (rc) return rc;
+    if (host && bytes) CUDA_TRY(cudaMemcpyAsync(ctx->pool[slot].p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = ctx->pool[slot].p;
+    return PMK_OK;
+}
+
+template <typename K>
+int cand_grid_for(pmk_ctx* ctx, int nwarps_needed) {
+    (void)sizeof(K);
+    return std::max(1, std::min(ctx->cand_grid, (nwarps_needed + CAND_WARPS - 1) / CAND_WARPS));
+}
+
+#define WS_DISPATCH(ws, CALL)                                 \
+    switch (ws) {                                             \
+        case 5: { constexpr int WS = 5; CALL; } break;        \
+        case 7: { constexpr int WS = 7; CALL; } break;        \
+        case 9: { constexpr int WS = 9; CALL; } break;        \
+        case 11: { constexpr int WS = 11; CALL; } break;      \
+        default: return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11"); \
+    }
+
 }  // namespace
 
 extern "C" {
@@ -245,6 +320,7 @@ void pmk_destroy(pmk_ctx* ctx) {
     Scratch* all[] = {&ctx->s_coord, &ctx->s_normal, &ctx->s_views, &ctx->s_nviews, &ctx->s_incc, &ctx->s_ncc, &ctx->s_levels};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     for (Scratch& s : ctx->s_misc) if (s.p) cudaFree(s.p);
+    for (Scratch& s : ctx->pool) if (s.p) cudaFree(s.p);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     cudaFree(ctx->d_views);
     cudaFree(ctx->d_counters);
@@ -478,6 +554,159 @@ int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const f
     }
     if (cell_ixy2) CUDA_TRY(cudaMemcpyAsync(cell_ixy2, cells, N * 8, cudaMemcpyDeviceToHost, st));
     if (cell_ixy2 && cell_ok) CUDA_TRY(cudaMemcpyAsync(cell_ok, cells + 2 * N, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PMK_OK;
+}
+
+// ---- candidate entry points (host pointers in, host pointers out) ----------------------------------------------------
+int pmk_set_inccs(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride,
+                  int robust, int pairwise, float* out) {
+    if (!ctx || !coord4 || !normal4 || !views || !nviews || !out) return fail(PMK_ERR_ARG, "pmk_set_inccs: null argument");
+    if (n <= 0) return PMK_OK;
+    if (stride < 1 || stride > CAND_MAXV) return fail(PMK_ERR_ARG, "pmk_set_inccs: stride out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    CandParams cp;
+    if ((rc = cand_params(ctx, cp, 0))) return rc;
+    const size_t N = (size_t)n, osz = N * stride * (pairwise ? stride : 1) * sizeof(float);
+    void *dc, *dn, *dv, *dnv, *dout;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, views, N * stride * 4, &dv)) ||
+        (rc = stage_in(ctx, 3, nviews, N * 4, &dnv)) || (rc = stage_in(ctx, 4, nullptr, osz, &dout)))
+        return rc;
+    CUDA_TRY(cudaMemsetAsync(dout, 0, osz, ctx->stream));
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    const size_t smem = CAND_WARPS * sizeof(WarpScratch);
+    WS_DISPATCH(ctx->cfg.wsize, (k2_set_inccs<WS><<<grid, CAND_WARPS * 32, smem, ctx->stream>>>(cp, n, (const float4*)dc, (const float4*)dn, (const int*)dv,
+                                                                                            (const int*)dnv, stride, robust, pairwise, (float*)dout)));
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout, osz, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_pre_process(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride, int maxv,
+                    int* ret, int* images_out, int* nimages_out, float* dscale_out, float* ascale_out) {
+    if (!ctx || !coord4 || !normal4 || !views || !nviews || !ret || !images_out || !nimages_out || !dscale_out || !ascale_out)
+        return fail(PMK_ERR_ARG, "pmk_pre_process: null argument");
+    if (n <= 0) return PMK_OK;
+    if (stride < 1 || maxv < 1) return fail(PMK_ERR_ARG, "pmk_pre_process: bad stride/maxv");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    CandParams cp;
+    if ((rc = cand_params(ctx, cp, 0))) return rc;
+    const size_t N = (size_t)n;
+    void *dc, *dn, *dv, *dnv, *dret, *dimg, *dni, *dds, *das;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, views, N * stride * 4, &dv)) ||
+        (rc = stage_in(ctx, 3, nviews, N * 4, &dnv)) || (rc = stage_in(ctx, 4, nullptr, N * 4, &dret)) || (rc = stage_in(ctx, 5, nullptr, N * maxv * 4, &dimg)) ||
+        (rc = stage_in(ctx, 6, nullptr, N * 4, &dni)) || (rc = stage_in(ctx, 7, nullptr, N * 4, &dds)) || (rc = stage_in(ctx, 8, nullptr, N * 4, &das)))
+        return rc;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    const size_t smem = CAND_WARPS * sizeof(WarpScratch);
+    WS_DISPATCH(ctx->cfg.wsize, (k_pre_process<WS><<<grid, CAND_WARPS * 32, smem, ctx->stream>>>(cp, n, (const float4*)dc, (const float4*)dn, (const int*)dv,
+                                 (const int*)dnv, stride, maxv, (int*)dret, (int*)dimg, (int*)dni, (float*)dds, (float*)das)));
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(ret, dret, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(images_out, dimg, N * maxv * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nimages_out, dni, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(dscale_out, dds, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ascale_out, das, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PMK_OK;
+}
+
+int pmk_cost_func(pmk_ctx* ctx, int npatches, const float* coord4, const float* normal4, const float* dscale, const int* views, const int* nviews,
+                  int stride, int nitems, const int* patch_of_item, const double* x3, double* cost_out) {
+    if (!ctx || !coord4 || !normal4 || !dscale || !views || !nviews || !patch_of_item || !x3 || !cost_out) return fail(PMK_ERR_ARG, "pmk_cost_func: null argument");
+    if (npatches <= 0 || nitems <= 0) return PMK_OK;
+    for (int i = 0; i < nitems; ++i) if (patch_of_item[i] < 0 || patch_of_item[i] >= npatches) return fail(PMK_ERR_ARG, "pmk_cost_func: patch index out of range");
+    for (int i = 0; i < npatches; ++i) if (nviews[i] < 1 || views[(size_t)i * stride] < 0 || views[(size_t)i * stride] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_cost_func: bad reference view");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    CandParams cp;
+    if ((rc = cand_params(ctx, cp, 0))) return rc;
+    const size_t N = (size_t)npatches, M = (size_t)nitems;
+    void *dc, *dn, *dd, *dv, *dnv, *dp, *dx, *dcost;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, views, N * stride * 4, &dv)) ||
+        (rc = stage_in(ctx, 3, nviews, N * 4, &dnv)) || (rc = stage_in(ctx, 4, dscale, N * 4, &dd)) || (rc = stage_in(ctx, 5, patch_of_item, M * 4, &dp)) ||
+        (rc = stage_in(ctx, 6, x3, M * 24, &dx)) || (rc = stage_in(ctx, 7, nullptr, M * 8, &dcost)))
+        return rc;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (nitems + CAND_WARPS * 4 - 1) / (CAND_WARPS * 4)));
+    WS_DISPATCH(ctx->cfg.wsize, (k_cost_func<WS><<<grid, CAND_WARPS * 32, 0, ctx->stream>>>(cp, nitems, (const int*)dp, (const float4*)dc, (const float4*)dn,
+                                 (const float*)dd, (const int*)dv, (const int*)dnv, stride, (const double*)dx, (double*)dcost)));
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(cost_out, dcost, M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_refine(pmk_ctx* ctx, int n, float* coord4, float* normal4, const float* dscale, const int* views, const int* nviews, int stride,
+               const uint64_t* streams, uint64_t seed, float* ncc_out, double* trace_out) {
+    if (!ctx || !coord4 || !normal4 || !dscale || !views || !nviews || !streams || !ncc_out) return fail(PMK_ERR_ARG, "pmk_refine: null argument");
+    if (n <= 0) return PMK_OK;
+    for (int i = 0; i < n; ++i) if (nviews[i] < 1 || views[(size_t)i * stride] < 0 || views[(size_t)i * stride] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_refine: bad reference view");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    CandParams cp;
+    if ((rc = cand_params(ctx, cp, seed))) return rc;
+    const size_t N = (size_t)n;
+    void *dc, *dn, *dd, *dv, *dnv, *dst, *dncc, *dtr = nullptr;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, views, N * stride * 4, &dv)) ||
+        (rc = stage_in(ctx, 3, nviews, N * 4, &dnv)) || (rc = stage_in(ctx, 4, dscale, N * 4, &dd)) || (rc = stage_in(ctx, 5, streams, N * 8, &dst)) ||
+        (rc = stage_in(ctx, 6, nullptr, N * 4, &dncc)))
+        return rc;
+    if (trace_out && (rc = stage_in(ctx, 7, nullptr, N * PMR1_EVALS * 32, &dtr))) return rc;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    const size_t smem = CAND_WARPS * sizeof(WarpScratch);
+    WS_DISPATCH(ctx->cfg.wsize, (k3_refine<WS><<<grid, CAND_WARPS * 32, smem, ctx->stream>>>(cp, n, (float4*)dc, (float4*)dn, (const float*)dd, (const int*)dv,
+                                 (const int*)dnv, stride, (const uint64_t*)dst, (float*)dncc, (double*)dtr)));
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(coord4, dc, N * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(normal4, dn, N * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ncc_out, dncc, N * 4, cudaMemcpyDeviceToHost, st));
+    if (trace_out) CUDA_TRY(cudaMemcpyAsync(trace_out, dtr, N * PMR1_EVALS * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PMK_OK;
+}
+
+int pmk_post_process(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* ncc, const int* views, const int* nviews, int stride,
+                     int maxv, int* ret, int* images_out, int* nimages_out, int* grids_out, float* tmp_out) {
+    if (!ctx || !coord4 || !normal4 || !ncc || !views || !nviews || !ret || !images_out || !nimages_out || !grids_out || !tmp_out)
+        return fail(PMK_ERR_ARG, "pmk_post_process: null argument");
+    if (n <= 0) return PMK_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    CandParams cp;
+    if ((rc = cand_params(ctx, cp, 0))) return rc;
+    const size_t N = (size_t)n;
+    void *dc, *dn, *dq, *dv, *dnv, *dret, *dimg, *dni, *dgr, *dtmp;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, views, N * stride * 4, &dv)) ||
+        (rc = stage_in(ctx, 3, nviews, N * 4, &dnv)) || (rc = stage_in(ctx, 4, ncc, N * 4, &dq)) || (rc = stage_in(ctx, 5, nullptr, N * 4, &dret)) ||
+        (rc = stage_in(ctx, 6, nullptr, N * maxv * 4, &dimg)) || (rc = stage_in(ctx, 7, nullptr, N * 4, &dni)) || (rc = stage_in(ctx, 8, nullptr, N * maxv * 8, &dgr)) ||
+        (rc = stage_in(ctx, 9, nullptr, N * 4, &dtmp)))
+        return rc;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    const size_t smem = CAND_WARPS * sizeof(WarpScratch);
+    WS_DISPATCH(ctx->cfg.wsize, (k_post_process<WS><<<grid, CAND_WARPS * 32, smem, ctx->stream>>>(cp, n, (const float4*)dc, (const float4*)dn, (const float*)dq,
+                                 (const int*)dv, (const int*)dnv, stride, maxv, (int*)dret, (int*)dimg, (int*)dni, (int*)dgr, (float*)dtmp)));
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(ret, dret, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(images_out, dimg, N * maxv * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nimages_out, dni, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(grids_out, dgr, N * maxv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(tmp_out, dtmp, N * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PMK_OK;
 }

@@ -67,12 +67,16 @@ constexpr int K1_WARPS = 8;            // warps per CTA
 constexpr int K1_FRAME_WORDS = 8;      // tlx tly dxx dxy dyx dyy (level | view << 4) weight
 
 // sum over the aligned group of GW lanes this lane belongs to (every lane of the group gets the total)
+// `mask` names the lanes that execute the call together: the whole warp, or just this lane's group when the
+// groups may sit in different control flow (candidate kernels)
 template <int GW>
-__device__ __forceinline__ float group_sum(float v) {
+__device__ __forceinline__ float group_sum(float v, unsigned mask = 0xffffffffu) {
 #pragma unroll
-    for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
+template <int GW>
+__device__ __forceinline__ unsigned group_mask(int lane) { return GW >= 32 ? 0xffffffffu : (((1u << GW) - 1u) << ((lane / GW) * GW)); }
 
 template <int WS, int MINB>
 __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, int n, const float4* __restrict__ coord,

@@ -177,6 +177,63 @@ class Context:
         _chk(lib().pmk_ncc_eval_dev(self.h, n, coord.ptr, normal.ptr, views.ptr, nviews.ptr, stride, incc.ptr,
                                     ncc.ptr if ncc else None, levels.ptr if levels else None))
 
+    # -- candidate kernels ------------------------------------------------------------------------------
+    @staticmethod
+    def _cv(coord, normal, views, nviews):
+        return (np.ascontiguousarray(coord, np.float32), np.ascontiguousarray(normal, np.float32),
+                np.ascontiguousarray(views, np.int32), np.ascontiguousarray(nviews, np.int32))
+
+    def set_inccs(self, coord, normal, views, nviews, robust: int, pairwise: bool = False):
+        """Optim::setINCCs (optim.cpp:708-783)."""
+        coord, normal, views, nviews = self._cv(coord, normal, views, nviews)
+        n, stride = views.shape
+        out = np.zeros((n, stride, stride) if pairwise else (n, stride), np.float32)
+        _chk(lib().pmk_set_inccs(self.h, n, _p(coord), _p(normal), _p(views), _p(nviews), stride, int(robust), int(pairwise), _p(out)))
+        return out
+
+    def pre_process(self, coord, normal, views, nviews, maxv: Optional[int] = None):
+        """Optim::preProcess (optim.cpp:137-163) -> ret, images (n, maxv), nimages, dscale, ascale."""
+        coord, normal, views, nviews = self._cv(coord, normal, views, nviews)
+        n, stride = views.shape
+        maxv = maxv or self.nviews
+        ret, images, nimg = np.zeros(n, np.int32), np.zeros((n, maxv), np.int32), np.zeros(n, np.int32)
+        ds, asc = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        _chk(lib().pmk_pre_process(self.h, n, _p(coord), _p(normal), _p(views), _p(nviews), stride, maxv, _p(ret), _p(images), _p(nimg), _p(ds), _p(asc)))
+        return ret, images, nimg, ds, asc
+
+    def cost_func(self, coord, normal, dscale, views, nviews, patch_of_item, x3):
+        """Optim::cost_func (optim.cpp:401-468) at encoded points."""
+        coord, normal, views, nviews = self._cv(coord, normal, views, nviews)
+        dscale = np.ascontiguousarray(dscale, np.float32)
+        pid = np.ascontiguousarray(patch_of_item, np.int32)
+        x3 = np.ascontiguousarray(x3, np.float64)
+        out = np.zeros(len(pid), np.float64)
+        _chk(lib().pmk_cost_func(self.h, len(coord), _p(coord), _p(normal), _p(dscale), _p(views), _p(nviews), views.shape[1], len(pid), _p(pid), _p(x3), _p(out)))
+        return out
+
+    def refine(self, coord, normal, dscale, views, nviews, streams, seed: int, trace: bool = False):
+        """Optim::refinePatch (optim.cpp:470-547) with the PMR1 schedule."""
+        coord, normal, views, nviews = self._cv(coord, normal, views, nviews)
+        coord, normal = coord.copy(), normal.copy()
+        dscale = np.ascontiguousarray(dscale, np.float32)
+        streams = np.ascontiguousarray(streams, np.uint64)
+        n = len(coord)
+        ncc = np.zeros(n, np.float32)
+        tr = np.zeros((n, 97, 4), np.float64) if trace else None
+        _chk(lib().pmk_refine(self.h, n, _p(coord), _p(normal), _p(dscale), _p(views), _p(nviews), views.shape[1], _p(streams), C.c_uint64(seed), _p(ncc), _p(tr)))
+        return coord, normal, ncc, tr
+
+    def post_process(self, coord, normal, ncc, views, nviews, maxv: Optional[int] = None):
+        """Optim::postProcess (optim.cpp:260-290), store-independent part."""
+        coord, normal, views, nviews = self._cv(coord, normal, views, nviews)
+        ncc = np.ascontiguousarray(ncc, np.float32)
+        n, stride = views.shape
+        maxv = maxv or self.nviews
+        ret, images, nimg = np.zeros(n, np.int32), np.zeros((n, maxv), np.int32), np.zeros(n, np.int32)
+        grids, tmp = np.zeros((n, maxv, 2), np.int32), np.zeros(n, np.float32)
+        _chk(lib().pmk_post_process(self.h, n, _p(coord), _p(normal), _p(ncc), _p(views), _p(nviews), stride, maxv, _p(ret), _p(images), _p(nimg), _p(grids), _p(tmp)))
+        return ret, images, nimg, grids, tmp
+
     def probe(self, view, coord, normal=None):
         view = np.ascontiguousarray(view, np.int32)
         coord = np.ascontiguousarray(coord, np.float32)
