@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PMK_ABI_VERSION 1
+#define PMK_ABI_VERSION 2
 #define PMK_MAX_LEVELS 6
 #define PMK_MAX_TAU 8
 
@@ -52,7 +52,10 @@ typedef struct pmk_config {
     float ncc_threshold;        /* Option::m_nccThreshold                                          */
     float max_angle_threshold;  /* Option::m_maxAngleThreshold, radians                            */
     float quad_threshold;       /* Option::m_quadThreshold                                         */
-    int max_patches;            /* capacity of the device patch store; 0 = 8 per cell of all views */
+    int max_patches;            /* capacity of the device patch store; 0 = 2 per cell of all views */
+    int cell_capacity;          /* slots per grid cell (m_pgrids + m_vpgrids entries); 0 = 96, at most 128 */
+    int jitter_mode;            /* 0: the reference's pixel jitter (propagate.cpp:139-141 re-seeds its engine on every
+                                   call, so it is the same four draws each time); 1: Philox4x32 per (iter, view, cell, call, try) */
 } pmk_config;
 
 /* Thresholds held by PmMvps (pmmvps/pmmvps.hpp:36-87); read back for parity checks. */
@@ -140,6 +143,45 @@ int pmk_refine(pmk_ctx* ctx, int n, float* coord4, float* normal4, const float* 
 int pmk_post_process(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* ncc, const int* views,
                      const int* nviews, int stride, int maxv, int* ret, int* images_out, int* nimages_out, int* grids_out,
                      float* tmp_out);
+
+/* ---- device patch store: PatchManager's m_pgrids / m_vpgrids / m_dpgrids and m_ppatches as structure-of-arrays in HBM ----
+ * A patch record crosses this boundary as coord4, normal4, scal4 = {m_ncc, m_dscale, m_ascale, m_tmp}, images[maxv] + nimages,
+ * grids[maxv][2] = Patch::m_grids, and the same for m_vimages / m_vgrids (patch.hpp:33-66). */
+int pmk_store_clear(pmk_ctx* ctx);                           /* PatchManager::init (patch_manager.cpp:24-52) */
+/* PatchManager::readPatches body (patch_manager.cpp:450-462): m_tmp = score2(nccThreshold), m_vimages cleared, setGrids
+ * (:241-249), addPatch (:158-189).  Image entries are view indexes (image2index already applied). */
+int pmk_store_add(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images,
+                  const int* nimages, int stride);
+/* PatchManager::collectPatches (patch_manager.cpp:75-104): number of patches reachable from the grids */
+int pmk_store_count(pmk_ctx* ctx, int* n_out);
+/* m_ppatches after collectPatches, in the reference's collect order; any output pointer may be NULL */
+int pmk_store_get(pmk_ctx* ctx, int nmax, int maxv, float* coord4, float* normal4, float* scal4, int* images, int* nimages,
+                  int* grids, int* vimages, int* nvimages, int* vgrids, int* n_out);
+int pmk_store_depth_map(pmk_ctx* ctx, int view, int* ids);   /* m_dpgrids[view] as patch ids, -1 = m_MAXDEPTH */
+int pmk_store_cell_counts(pmk_ctx* ctx, int view, int which, int* counts);  /* sizes of m_pgrids (0) / m_vpgrids (1) cells */
+int pmk_store_colors(pmk_ctx* ctx, int nmax, uint8_t* rgb);  /* PatchManager::writePly colours (patch_manager.cpp:566-581) */
+
+/* K4 -- Propagate::run(iter) (propagate.cpp:28-64): propagatePmImage / propagatePatch / generatePatch (:72-237) for every view in
+ * order, each as an anti-diagonal wavefront over dest cells (schedule PMS1), with preProcess, refinePatch (PMR1, `seed`)
+ * and postProcess including its store-reading tail (setVImagesVGrids, check; optim.cpp:290-296).  stats16 (optional): calls, tries,
+ * generatePatch == NULL, lost to the worst patch's ncc, preProcess failures (m_fcount0), postProcess failures (m_fcount1), added,
+ * replaced, trimmed, hypothesis NCC evaluations. */
+int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16);
+/* the same for wavefront steps [diag_first, diag_first + diag_count) of one view (parity tests step the sweep) */
+int pmk_propagate_diagonals(pmk_ctx* ctx, int iter, int image, int diag_first, int diag_count, uint64_t seed, uint64_t* stats16);
+
+/* K5 -- PatchManager::collectPatches + Filter::setDepthMapsVGridsVPGridsAddPatchV(additive) (filter.cpp:628-655): patch ids become
+ * the reference's m_ppatches indices; depth maps, m_vimages / m_vgrids and m_vpgrids are rebuilt. */
+int pmk_filter_rebuild(pmk_ctx* ctx, int additive, int* n_out);
+/* One filter of Filter::run on a rebuilt store; per-patch results in collect order (any may be NULL):
+ *   stage 1 filterOutside (filter.cpp:51-106)       f_out = computeGain (:108-146)
+ *   stage 2 filterExact (:148-263)                  i_out = removed flag, i_out2 = new m_images.size()
+ *   stage 3 filterNeighbor(1) (:265-336)            i_out = m_rejects, i_out2 = findNeighbors count, f_out = filterQuad residual (-1: not run)
+ *   stage 4 filterSmallGroups (:432-525)            i_out = removed flag
+ * killed_out = patches removed.  The grids are rebuilt by the next pmk_filter_rebuild, as in Filter::run. */
+int pmk_filter_stage(pmk_ctx* ctx, int stage, int nmax, float* f_out, int* i_out, int* i_out2, int* killed_out);
+/* K5..K9 -- Filter::run (filter.cpp:25-49).  counts6 (optional): patches before, removed by each of the four filters, patches after. */
+int pmk_filter(pmk_ctx* ctx, int* counts6);
 
 /* Probes of the device-side building blocks, for parity tests (each item independent):
  *   project  : Camera::project at the working level        (camera.cpp:310-326)   -> out3

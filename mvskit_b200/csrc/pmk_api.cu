@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "pmk_cand.cuh"
+#include "pmk_filter.cuh"
 
 using namespace pmk;
 
@@ -75,8 +75,11 @@ struct Scratch {
 
 }  // namespace
 
+struct pmk_store;
+
 struct pmk_ctx {
     pmk_config cfg;
+    pmk_store* store = nullptr;             // device patch store (pmk_store_host.cuh), created on first use
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
@@ -173,6 +176,10 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
 int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
                 void* incc, void* ncc, void* levels) {
     static const int minb = getenv("PMK_K1_MINB") ? atoi(getenv("PMK_K1_MINB")) : 4;   // tuning knob: CTAs/SM the kernel is compiled for
+#ifdef PMK_WS_ONLY
+    if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+    (void)minb;
+#else
     switch (ctx->cfg.wsize) {
         case 5: return launch_k1<5, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
         case 7: return minb == 3 ? launch_k1<7, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels)
@@ -180,6 +187,7 @@ int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, cons
         case 9: return launch_k1<9, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
         case 11: return launch_k1<11, 2>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
     }
+#endif
     return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11");
 }
 
@@ -245,6 +253,14 @@ int cand_grid_for(pmk_ctx* ctx, int nwarps_needed) {
     return std::max(1, std::min(ctx->cand_grid, (nwarps_needed + CAND_WARPS - 1) / CAND_WARPS));
 }
 
+// PMK_WS_ONLY=<w> (dev builds: python -m mvskit_b200.build --fast) compiles the kernels for one window size only
+#ifdef PMK_WS_ONLY
+#define WS_DISPATCH(ws, CALL)                                 \
+    switch (ws) {                                             \
+        case PMK_WS_ONLY: { constexpr int WS = PMK_WS_ONLY; CALL; } break; \
+        default: return fail(PMK_ERR_ARG, "pmk: this development build only has wsize " + std::to_string(PMK_WS_ONLY)); \
+    }
+#else
 #define WS_DISPATCH(ws, CALL)                                 \
     switch (ws) {                                             \
         case 5: { constexpr int WS = 5; CALL; } break;        \
@@ -253,8 +269,11 @@ int cand_grid_for(pmk_ctx* ctx, int nwarps_needed) {
         case 11: { constexpr int WS = 11; CALL; } break;      \
         default: return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11"); \
     }
+#endif
 
 }  // namespace
+
+#include "pmk_store_host.cuh"
 
 extern "C" {
 
@@ -271,6 +290,8 @@ void pmk_default_config(pmk_config* c) {
     c->max_angle_threshold = 10.0f * M_PI / 180.0f;
     c->quad_threshold = 2.5f;
     c->max_patches = 0;
+    c->cell_capacity = 0;
+    c->jitter_mode = 0;
 }
 
 int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
@@ -326,6 +347,7 @@ void pmk_destroy(pmk_ctx* ctx) {
     cudaFree(ctx->d_counters);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
+    delete ctx->store;
     delete ctx;
 }
 
@@ -787,6 +809,257 @@ int pmk_flush_l2(pmk_ctx* ctx) {
         CUDA_TRY(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
     }
     CUDA_TRY(cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    return PMK_OK;
+}
+
+// ---- device patch store ---------------------------------------------------------------------------------------------------------
+int pmk_store_clear(pmk_ctx* ctx) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_store_clear: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    const StoreDev& d = s->d;
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, SC_COUNT * sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d.ccount, 0, (size_t)d.total_cells * sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d.dmap, 0xff, (size_t)d.total_cells * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d.state, 0, ((size_t)d.cap + d.stage_cap) * sizeof(int), ctx->stream));
+    s->n = 0;
+    s->canonical = true;
+    return PMK_OK;
+}
+
+int pmk_store_add(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages, int stride) {
+    if (!ctx || !coord4 || !normal4 || !scal4 || !images || !nimages) return fail(PMK_ERR_ARG, "pmk_store_add: null argument");
+    if (n <= 0) return PMK_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    StoreDev& d = s->d;
+    if ((rc = store_check_overflow(ctx))) return rc;
+    if (s->n + n > d.cap) return fail(PMK_ERR_CAPACITY, "pmk_store_add: patch store full (raise pmk_config.max_patches)");
+    for (int i = 0; i < n; ++i) {
+        if (nimages[i] < 1 || nimages[i] > std::min(stride, d.maxv)) return fail(PMK_ERR_ARG, "pmk_store_add: bad image count");
+        for (int k = 0; k < nimages[i]; ++k) {
+            const int v = images[(size_t)i * stride + k];
+            if (v < 0 || v >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_store_add: image index out of range");
+        }
+    }
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    cudaStream_t st = ctx->stream;
+    const int first = s->n;
+    CUDA_TRY(cudaMemcpyAsync(d.coord + first, coord4, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d.normal + first, normal4, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d.scal + first, scal4, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d.nimg + first, nimages, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(d.images + (size_t)first * d.maxv, (size_t)d.maxv * 4, images, (size_t)stride * 4, (size_t)std::min(stride, d.maxv) * 4, n, cudaMemcpyHostToDevice, st));
+    int birth0 = 0;
+    CUDA_TRY(cudaMemcpyAsync(&birth0, d.counters + SC_BIRTH, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    k_store_add<<<std::max(1, std::min(ctx->sm_count * 4, (n + 3) / 4)), 128, 0, st>>>(sp, first, n, (unsigned int)birth0);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    s->n += n;
+    const int c2[2] = {s->n, birth0 + n};
+    CUDA_TRY(cudaMemcpyAsync(d.counters + SC_N, c2, sizeof(c2), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    s->canonical = false;
+    return store_check_overflow(ctx);
+}
+
+int pmk_store_count(pmk_ctx* ctx, int* n_out) {
+    if (!ctx || !n_out) return fail(PMK_ERR_ARG, "pmk_store_count: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    if ((rc = store_check_overflow(ctx))) return rc;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    return store_order(ctx, sp, n_out);
+}
+
+int pmk_store_get(pmk_ctx* ctx, int nmax, int maxv, float* coord4, float* normal4, float* scal4, int* images, int* nimages, int* grids,
+                  int* vimages, int* nvimages, int* vgrids, int* n_out) {
+    if (!ctx || !n_out) return fail(PMK_ERR_ARG, "pmk_store_get: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    if ((rc = store_check_overflow(ctx))) return rc;
+    pmk_store* s = ctx->store;
+    const StoreDev& d = s->d;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    int nalive = 0;
+    if ((rc = store_order(ctx, sp, &nalive))) return rc;
+    *n_out = nalive;
+    const int n = std::min(nalive, nmax);
+    if (n <= 0) return PMK_OK;
+    cudaStream_t st = ctx->stream;
+    auto fetch = [&](auto* src, void* dst, int row, int out_row, size_t elem) -> int {
+        if (!dst) return PMK_OK;
+        const long long total = (long long)n * row;
+        typedef typename std::remove_pointer<decltype(src)>::type T;
+        k_gather_rows<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, (T*)s->gather_tmp, s->vals2, total, row);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)out_row * elem, s->gather_tmp, (size_t)row * elem, (size_t)std::min(row, out_row) * elem, n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return PMK_OK;
+    };
+    if ((rc = fetch(d.coord, coord4, 1, 1, 16)) || (rc = fetch(d.normal, normal4, 1, 1, 16)) || (rc = fetch(d.scal, scal4, 1, 1, 16)) ||
+        (rc = fetch(d.nimg, nimages, 1, 1, 4)) || (rc = fetch(d.nvimg, nvimages, 1, 1, 4)) ||
+        (rc = fetch(d.images, images, d.maxv, maxv, 4)) || (rc = fetch(d.vimages, vimages, d.maxv, maxv, 4)))
+        return rc;
+    // grids come back as (ix, iy) pairs like Patch::m_grids
+    std::vector<int> packed((size_t)n * maxv);
+    for (int which = 0; which < 2; ++which) {
+        int* out = which ? vgrids : grids;
+        if (!out) continue;
+        std::fill(packed.begin(), packed.end(), 0);
+        if ((rc = fetch(which ? d.vcells : d.cells, packed.data(), d.maxv, maxv, 4))) return rc;
+        for (size_t i = 0; i < packed.size(); ++i) { out[2 * i] = packed[i] & 0xffff; out[2 * i + 1] = (int)((unsigned)packed[i] >> 16); }
+    }
+    return PMK_OK;
+}
+
+int pmk_store_depth_map(pmk_ctx* ctx, int view, int* ids) {
+    if (!ctx || !ids) return fail(PMK_ERR_ARG, "pmk_store_depth_map: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_store_depth_map: view out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    const int c0 = s->cell_base[view], nc = s->cell_base[view + 1] - c0;
+    std::vector<unsigned long long> keys(nc);
+    CUDA_TRY(cudaMemcpyAsync(keys.data(), s->d.dmap + c0, (size_t)nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nc; ++i) ids[i] = keys[i] == ~0ull ? -1 : (int)(keys[i] & 0xffffffffu);
+    return PMK_OK;
+}
+
+int pmk_store_cell_counts(pmk_ctx* ctx, int view, int which, int* counts) {
+    if (!ctx || !counts) return fail(PMK_ERR_ARG, "pmk_store_cell_counts: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_store_cell_counts: view out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    const int c0 = s->cell_base[view], nc = s->cell_base[view + 1] - c0, cap = s->d.cell_cap;
+    std::vector<int> cnt(nc), slots((size_t)nc * cap);
+    CUDA_TRY(cudaMemcpyAsync(cnt.data(), s->d.ccount + c0, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(slots.data(), s->d.cslots + (size_t)c0 * cap, (size_t)nc * cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < nc; ++c) {
+        int k = 0;
+        for (int i = 0; i < std::min(cnt[c], cap); ++i) {
+            const int e = slots[(size_t)c * cap + i];
+            if ((e & 0x7fffffff) == SLOT_TOMB) continue;
+            if ((which != 0) == (e < 0)) ++k;
+        }
+        counts[c] = k;
+    }
+    return PMK_OK;
+}
+
+int pmk_store_colors(pmk_ctx* ctx, int nmax, uint8_t* rgb) {
+    if (!ctx || !rgb) return fail(PMK_ERR_ARG, "pmk_store_colors: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    if (!s->canonical) return fail(PMK_ERR_STATE, "pmk_store_colors: call pmk_filter_rebuild first (ids must be in collect order)");
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    const int n = std::min(s->n, nmax);
+    if (n <= 0) return PMK_OK;
+    k_patch_colors<<<(n + 127) / 128, 128, 0, ctx->stream>>>(sp, n, (unsigned char*)s->gather_tmp);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rgb, s->gather_tmp, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+static int read_stats(pmk_ctx* ctx, uint64_t* stats16) {
+    if (!stats16) return PMK_OK;
+    CUDA_TRY(cudaMemcpyAsync(stats16, ctx->store->stats, SS_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_propagate_diagonals(pmk_ctx* ctx, int iter, int image, int diag_first, int diag_count, uint64_t seed, uint64_t* stats16) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_propagate_diagonals: null ctx");
+    if (image < 0 || image >= ctx->cfg.nviews || diag_first < 0 || diag_count < 0) return fail(PMK_ERR_ARG, "pmk_propagate_diagonals: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(ctx->store->stats, 0, SS_COUNT * sizeof(uint64_t), ctx->stream));
+    if ((rc = sweep_image(ctx, iter, image, diag_first, diag_count, seed))) return rc;
+    if ((rc = read_stats(ctx, stats16))) return rc;
+    return store_check_overflow(ctx);
+}
+
+int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_propagate: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(ctx->store->stats, 0, SS_COUNT * sizeof(uint64_t), ctx->stream));
+    for (int image = 0; image < ctx->cfg.nviews; ++image) {                               // propagate.cpp:73
+        const ViewConst& vc = ctx->h_views[image];
+        if ((rc = sweep_image(ctx, iter, image, 0, vc.gw + vc.gh - 1, seed))) return rc;
+        if ((rc = store_check_overflow(ctx))) return rc;
+    }
+    return read_stats(ctx, stats16);
+}
+
+int pmk_filter_rebuild(pmk_ctx* ctx, int additive, int* n_out) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_filter_rebuild: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    if ((rc = store_rebuild(ctx, additive))) return rc;
+    if (n_out) *n_out = ctx->store->n;
+    return PMK_OK;
+}
+
+int pmk_filter_stage(pmk_ctx* ctx, int stage, int nmax, float* f_out, int* i_out, int* i_out2, int* killed_out) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_filter_stage: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    if (!s->canonical) return fail(PMK_ERR_STATE, "pmk_filter_stage: call pmk_filter_rebuild first");
+    const int n = std::min(s->n, nmax);
+    int killed = 0;
+    if ((rc = filter_stage(ctx, stage, &killed))) return rc;
+    if (killed_out) *killed_out = killed;
+    if (n > 0) {
+        if (f_out && (stage == 1 || stage == 3)) CUDA_TRY(cudaMemcpyAsync(f_out, s->f_tmp, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (i_out && stage != 1) CUDA_TRY(cudaMemcpyAsync(i_out, s->i_tmp, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (i_out2 && stage == 3) CUDA_TRY(cudaMemcpyAsync(i_out2, s->i_tmp3, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (i_out2 && stage == 2) CUDA_TRY(cudaMemcpyAsync(i_out2, s->d.nimg, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return store_check_overflow(ctx);
+}
+
+int pmk_filter(pmk_ctx* ctx, int* counts6) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_filter: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    int c[6] = {0, 0, 0, 0, 0, 0};
+    if ((rc = store_rebuild(ctx, 0))) return rc;                     // filter.cpp:26
+    c[0] = ctx->store->n;
+    for (int stage = 1; stage <= 4; ++stage) {                       // filterOutside, filterExact, filterNeighbor(1), filterSmallGroups
+        if ((rc = filter_stage(ctx, stage, &c[stage]))) return rc;
+        if ((rc = store_rebuild(ctx, 1))) return rc;                 // filter.cpp:31,36,41,46
+    }
+    c[5] = ctx->store->n;
+    if (counts6) std::memcpy(counts6, c, sizeof(c));
     return PMK_OK;
 }
 

@@ -12,6 +12,10 @@
 
 namespace pmk {
 
+#ifndef PMK_CAND_INLINE
+#define PMK_CAND_INLINE __forceinline__
+#endif
+
 constexpr int CAND_WARPS = 4;          // warps per CTA in the candidate kernels
 constexpr int PMR1_LEVELS = 12;        // refinement schedule "PMR1" (CPU twin: oracle/shim/nlopt.hpp)
 constexpr int PMR1_CANDS = 8;
@@ -523,6 +527,31 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k2_set_inccs(const CandParams
 }
 
 
+// Optim::preProcess (optim.cpp:137-163) on the candidate {X, N, ws.images[0..nv)}: returns the reference's return value;
+// nv / dscale / ascale are the patch's m_images.size(), m_dscale, m_ascale afterwards (nv = 0 when checkAngles clears the list)
+template <int WS>
+__device__ PMK_CAND_INLINE int warp_pre_process(const CandParams& cp, WarpScratch& ws, V4 X, V4 N, int& nv, float& dscale, float& ascale, int lane) {
+    constexpr int GW = WS <= 8 ? 8 : 16;
+    const Params& p = cp.p;
+    int r = -1;
+    dscale = 0.0f; ascale = 0.0f;
+    if (nv >= 1) {
+        nv = warp_add_images(p, X, N, ws.images, nv, CAND_MAXV, ws.mark, lane);                     // optim.cpp:139
+        warp_set_inccs<WS, GW>(p, X, N, ws.images, nv, 0, ws.inccs, lane);                           // constraintImages, :141
+        nv = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold_before, lane);
+        __syncwarp();
+        nv = warp_sort_images(cp, X, N, ws, nv, lane);                                               // :143
+        __syncwarp();
+        if (nv > 0) warp_set_scales(p, X, ws.images, nv, dscale, ascale, ws.units, lane);            // :145-147
+        if (nv >= p.min_image_num) {                                                                 // :149
+            if (warp_check_angles(cp, X, ws, nv, lane)) r = 0;                                       // :153-160
+            else nv = 0;
+        }
+    } else nv = 0;
+    __syncwarp();
+    return r;
+}
+
 // Optim::preProcess (optim.cpp:137-163) for fresh candidates {coord, normal, images}
 template <int WS>
 __global__ void __launch_bounds__(CAND_WARPS * 32) k_pre_process(const CandParams cp, int n, const float4* __restrict__ coord,
@@ -530,10 +559,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_pre_process(const CandParam
                                                                  const int* __restrict__ nviews, int stride, int maxv,
                                                                  int* __restrict__ ret, int* __restrict__ images_out, int* __restrict__ nimages_out,
                                                                  float* __restrict__ dscale_out, float* __restrict__ ascale_out) {
-    constexpr int GW = WS <= 8 ? 8 : 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch& ws = warp_scratch(smem_raw);
-    const Params& p = cp.p;
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
     for (int h = gwarp; h < n; h += gridDim.x * CAND_WARPS) {
@@ -542,22 +569,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_pre_process(const CandParam
         int nv = min(min(__ldg(nviews + h), stride), CAND_MAXV);
         for (int i = lane; i < nv; i += 32) ws.images[i] = __ldg(views + (size_t)h * stride + i);
         __syncwarp();
-        int r = -1;
-        float dscale = 0.0f, ascale = 0.0f;
-        if (nv >= 1) {
-            nv = warp_add_images(p, X, N, ws.images, nv, CAND_MAXV, ws.mark, lane);                     // optim.cpp:139
-            warp_set_inccs<WS, GW>(p, X, N, ws.images, nv, 0, ws.inccs, lane);                           // constraintImages, :141
-            nv = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold_before, lane);
-            __syncwarp();
-            nv = warp_sort_images(cp, X, N, ws, nv, lane);                                               // :143
-            __syncwarp();
-            if (nv > 0) warp_set_scales(p, X, ws.images, nv, dscale, ascale, ws.units, lane);            // :145-147
-            if (nv >= p.min_image_num) {                                                                 // :149
-                if (warp_check_angles(cp, X, ws, nv, lane)) r = 0;                                       // :153-160
-                else nv = 0;
-            }
-        } else nv = 0;
-        __syncwarp();
+        float dscale, ascale;
+        const int r = warp_pre_process<WS>(cp, ws, X, N, nv, dscale, ascale, lane);
         if (lane == 0) { ret[h] = r; nimages_out[h] = nv; dscale_out[h] = dscale; ascale_out[h] = ascale; }
         for (int i = lane; i < maxv; i += 32) images_out[(size_t)h * maxv + i] = i < nv ? ws.images[i] : -1;
         __syncwarp();
@@ -595,108 +608,202 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cost_func(const CandParams 
     }
 }
 
-// Optim::refinePatch (optim.cpp:470-547) with the PMR1 schedule in place of NLopt BOBYQA
+// Optim::refinePatch (optim.cpp:470-547) with the PMR1 schedule in place of NLopt BOBYQA, on {X, N, ws.images[0..nv)}.
+// X / N are updated in place; returns m_ncc = 1 - unrobustincc(computeINCC) with the pre-refinement weights (:539).
+template <int WS>
+__device__ PMK_CAND_INLINE float warp_refine(const CandParams& cp, WarpScratch& ws, V4& X, V4& N, int nv, float dscale, uint64_t stream,
+                                             double* tr, int lane) {
+    constexpr int GW = WS <= 8 ? 8 : 16;
+    constexpr int G = 32 / GW;
+    const Params& p = cp.p;
+    const int grp = lane / GW, col = lane % GW;
+    const float cmask = col < WS ? 1.0f : 0.0f;
+    const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
+    const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
+    RefineCtx rc;
+    rc.center = X;
+    rc.ref = ws.images[0];
+    rc.ray = sub4(X, ld4(p.views[rc.ref].center));
+    rc.ray = div4(rc.ray, norm4(rc.ray));
+    rc.dscale = dscale;
+    compute_weights(p, X, N, ws.images, nv, ws.units, lane);          // m_weights of the UNREFINED patch (optim.cpp:490)
+    double best[3];
+    encode(cp, rc, X, N, best);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) best[i] = fmax(fmin(best[i], ub[i]), lb[i]);
+    const unsigned gm = group_mask<GW>(lane);
+    double fbest = group_cost<WS, GW>(cp, rc, best, ws.images, nv, col, cmask, gm);
+    __syncwarp();
+    if (tr && lane == 0) { tr[0] = best[0]; tr[1] = best[1]; tr[2] = best[2]; tr[3] = fbest; }
+    double r[3] = {4.0, 4.0, 4.0};
+#pragma unroll 1
+    for (int level = 0; level < PMR1_LEVELS; ++level) {
+        double fwin = 0.0, xwin[3] = {0.0, 0.0, 0.0};
+        int cwin = -1;
+#pragma unroll 1
+        for (int cb = 0; cb < PMR1_CANDS; cb += G) {
+            const int cnd = cb + grp;                 // this group's candidate of the level
+            uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)level, (uint32_t)cnd};
+            philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
+            double xc[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) xc[i] = fmax(fmin(__dadd_rn(best[i], __dmul_rn(r[i], uniform_pm1(ctr[i]))), ub[i]), lb[i]);
+            const double fc = group_cost<WS, GW>(cp, rc, xc, ws.images, nv, col, cmask, gm);
+            if (tr && col == 0 && cnd < PMR1_CANDS) { double* q = tr + (size_t)(1 + level * PMR1_CANDS + cnd) * 4; q[0] = xc[0]; q[1] = xc[1]; q[2] = xc[2]; q[3] = fc; }
+            // argmin over the candidates seen so far, lowest candidate index on ties (strict <, in index order)
+            if (cnd < PMR1_CANDS && (cwin < 0 || fc < fwin)) { fwin = fc; cwin = cnd; xwin[0] = xc[0]; xwin[1] = xc[1]; xwin[2] = xc[2]; }
+        }
+        __syncwarp();
+        // combine the groups: smallest cost, then smallest candidate index
+#pragma unroll
+        for (int o = GW; o < 32; o <<= 1) {
+            const double of = __shfl_xor_sync(0xffffffffu, fwin, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, cwin, o);
+            const double o0 = __shfl_xor_sync(0xffffffffu, xwin[0], o), o1 = __shfl_xor_sync(0xffffffffu, xwin[1], o), o2 = __shfl_xor_sync(0xffffffffu, xwin[2], o);
+            if (oc >= 0 && (cwin < 0 || of < fwin || (of == fwin && oc < cwin))) { fwin = of; cwin = oc; xwin[0] = o0; xwin[1] = o1; xwin[2] = o2; }
+        }
+        if (fwin < fbest) { fbest = fwin; best[0] = xwin[0]; best[1] = xwin[1]; best[2] = xwin[2]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = __dmul_rn(r[i], 0.6);
+    }
+    // optim.cpp:534-541: decode, normal.w = 0, ncc = 1.0 - unrobustincc(computeINCC(...)) with the stale weights
+    V4 Xf, Nf;
+    decode(cp, rc, best, Xf, Nf);
+    const float incc = group_incc<WS, GW>(p, Xf, Nf, ws.images, nv, ws.units, col, cmask, gm);
+    __syncwarp();
+    X = Xf;
+    N = V4{Nf.x, Nf.y, Nf.z, 0.0f};
+    return __double2float_rn(1.0 - (double)unrobustincc(incc));
+}
+
 template <int WS>
 __global__ void __launch_bounds__(CAND_WARPS * 32) k3_refine(const CandParams cp, int n, float4* __restrict__ coord, float4* __restrict__ normal,
                                                              const float* __restrict__ dscale, const int* __restrict__ views,
                                                              const int* __restrict__ nviews, int stride, const uint64_t* __restrict__ streams,
                                                              float* __restrict__ ncc_out, double* __restrict__ trace) {
-    constexpr int GW = WS <= 8 ? 8 : 16;
-    constexpr int G = 32 / GW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch& ws = warp_scratch(smem_raw);
-    const Params& p = cp.p;
     const int lane = threadIdx.x & 31;
-    const int grp = lane / GW, col = lane % GW;
-    const float cmask = col < WS ? 1.0f : 0.0f;
     const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
-    const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
-    const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
     for (int h = gwarp; h < n; h += gridDim.x * CAND_WARPS) {
         const float4 c = coord[h], m = normal[h];
-        const V4 X{c.x, c.y, c.z, c.w}, N{m.x, m.y, m.z, m.w};
+        V4 X{c.x, c.y, c.z, c.w}, N{m.x, m.y, m.z, m.w};
         const int nv = min(min(__ldg(nviews + h), stride), CAND_MAXV);
         for (int i = lane; i < nv; i += 32) ws.images[i] = __ldg(views + (size_t)h * stride + i);
         __syncwarp();
-        RefineCtx rc;
-        rc.center = X;
-        rc.ref = ws.images[0];
-        rc.ray = sub4(X, ld4(p.views[rc.ref].center));
-        rc.ray = div4(rc.ray, norm4(rc.ray));
-        rc.dscale = __ldg(dscale + h);
-        compute_weights(p, X, N, ws.images, nv, ws.units, lane);          // m_weights of the UNREFINED patch (optim.cpp:490)
-        double best[3];
-        encode(cp, rc, X, N, best);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) best[i] = fmax(fmin(best[i], ub[i]), lb[i]);
-        const unsigned gm = group_mask<GW>(lane);
-        double fbest = group_cost<WS, GW>(cp, rc, best, ws.images, nv, col, cmask, gm);
-        __syncwarp();
-        double* tr = trace ? trace + (size_t)h * PMR1_EVALS * 4 : nullptr;
-        if (tr && lane == 0) { tr[0] = best[0]; tr[1] = best[1]; tr[2] = best[2]; tr[3] = fbest; }
-        double r[3] = {4.0, 4.0, 4.0};
-        const uint64_t stream = __ldg(streams + h);
-#pragma unroll 1
-        for (int level = 0; level < PMR1_LEVELS; ++level) {
-            double fwin = 0.0, xwin[3] = {0.0, 0.0, 0.0};
-            int cwin = -1;
-#pragma unroll 1
-            for (int cb = 0; cb < PMR1_CANDS; cb += G) {
-                const int cnd = cb + grp;                 // this group's candidate of the level
-                uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)level, (uint32_t)cnd};
-                philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
-                double xc[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) xc[i] = fmax(fmin(__dadd_rn(best[i], __dmul_rn(r[i], uniform_pm1(ctr[i]))), ub[i]), lb[i]);
-                const double fc = group_cost<WS, GW>(cp, rc, xc, ws.images, nv, col, cmask, gm);
-                if (tr && col == 0 && cnd < PMR1_CANDS) { double* q = tr + (size_t)(1 + level * PMR1_CANDS + cnd) * 4; q[0] = xc[0]; q[1] = xc[1]; q[2] = xc[2]; q[3] = fc; }
-                // argmin over the candidates seen so far, lowest candidate index on ties (strict <, in index order)
-                if (cnd < PMR1_CANDS && (cwin < 0 || fc < fwin)) { fwin = fc; cwin = cnd; xwin[0] = xc[0]; xwin[1] = xc[1]; xwin[2] = xc[2]; }
-            }
-            __syncwarp();
-            // combine the groups: smallest cost, then smallest candidate index
-#pragma unroll
-            for (int o = GW; o < 32; o <<= 1) {
-                const double of = __shfl_xor_sync(0xffffffffu, fwin, o);
-                const int oc = __shfl_xor_sync(0xffffffffu, cwin, o);
-                const double o0 = __shfl_xor_sync(0xffffffffu, xwin[0], o), o1 = __shfl_xor_sync(0xffffffffu, xwin[1], o), o2 = __shfl_xor_sync(0xffffffffu, xwin[2], o);
-                if (oc >= 0 && (cwin < 0 || of < fwin || (of == fwin && oc < cwin))) { fwin = of; cwin = oc; xwin[0] = o0; xwin[1] = o1; xwin[2] = o2; }
-            }
-            if (fwin < fbest) { fbest = fwin; best[0] = xwin[0]; best[1] = xwin[1]; best[2] = xwin[2]; }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) r[i] = __dmul_rn(r[i], 0.6);
-        }
-        // optim.cpp:534-541: decode, normal.w = 0, ncc = 1.0 - unrobustincc(computeINCC(...)) with the stale weights
-        V4 Xf, Nf;
-        decode(cp, rc, best, Xf, Nf);
-        const float incc = group_incc<WS, GW>(p, Xf, Nf, ws.images, nv, ws.units, col, cmask, gm);
-        __syncwarp();
+        const float ncc = warp_refine<WS>(cp, ws, X, N, nv, __ldg(dscale + h), __ldg(streams + h), trace ? trace + (size_t)h * PMR1_EVALS * 4 : nullptr, lane);
         if (lane == 0) {
-            coord[h] = make_float4(Xf.x, Xf.y, Xf.z, Xf.w);
-            normal[h] = make_float4(Nf.x, Nf.y, Nf.z, 0.0f);
-            ncc_out[h] = __double2float_rn(1.0 - (double)unrobustincc(incc));
+            coord[h] = make_float4(X.x, X.y, X.z, X.w);
+            normal[h] = make_float4(N.x, N.y, N.z, 0.0f);
+            ncc_out[h] = ncc;
         }
         __syncwarp();
     }
 }
 
+// Optim::setRefImage (optim.cpp:348-383) on ws.images[0..nv): pairwise robust INCC, reference = argmin of the row sums
+// (accumulate(row, 0.0f) in index order; first minimum wins, start value INT_MAX / 2), swapped into slot 0.
+template <int WS>
+__device__ PMK_CAND_INLINE void warp_set_ref_image(const CandParams& cp, WarpScratch& ws, V4 X, V4 N, int nv, int wslot, int lane) {
+    constexpr int GW = WS <= 8 ? 8 : 16;
+    constexpr int G = 32 / GW;
+    constexpr int TEXW = WS * WS * 3;
+    const Params& p = cp.p;
+    const int grp = lane / GW, col = lane % GW;
+    const float cmask = col < WS ? 1.0f : 0.0f;
+    float* tex = cp.tex_scratch + (size_t)wslot * p.nviews * (TEXW + 4);
+    float* mat = cp.mat_scratch + (size_t)wslot * p.nviews * p.nviews;
+    V4 px, py;
+    get_paxes(p.views[ws.images[0]], X, N, p.level_scale, px, py);
+    float t[WS][3];
+    float inv;
+    for (int base = 0; base < nv; base += G) {
+        const int i = base + grp;
+        const int lv = group_grab<WS, GW>(p, i < nv ? ws.images[i] : -1, X, N, px, py, col, cmask, t, inv);
+        if (i < nv) {
+            float* dst = tex + (size_t)i * (TEXW + 4);
+            if (col < WS)
+#pragma unroll
+                for (int y = 0; y < WS; ++y) { float* q = dst + (y * WS + col) * 3; q[0] = t[y][0] * inv; q[1] = t[y][1] * inv; q[2] = t[y][2] * inv; }
+            if (col == 0) dst[TEXW] = lv >= 0 ? 1.0f : 0.0f;
+        }
+    }
+    __syncwarp();
+    for (int q = lane; q < nv * nv; q += 32) {
+        const int i = q / nv, j = q % nv;
+        if (j < i) continue;
+        float v = 0.0f;
+        if (j > i) {
+            const float* a = tex + (size_t)i * (TEXW + 4);
+            const float* b = tex + (size_t)j * (TEXW + 4);
+            v = 2.0f;
+            if (a[TEXW] != 0.0f && b[TEXW] != 0.0f) {
+                float dp = 0.0f;
+                for (int e = 0; e < TEXW; ++e) dp = fmaf(a[e], b[e], dp);
+                v = robustincc(xsub(1.0f, dp * (1.0f / (float)TEXW)));
+            }
+        }
+        mat[i * nv + j] = v; mat[j * nv + i] = v;
+    }
+    __syncwarp();
+    float best = 1073741824.0f;
+    int bi = -1;
+    for (int i = lane; i < nv; i += 32) {
+        float sum = 0.0f;
+        for (int j = 0; j < nv; ++j) sum = xadd(sum, mat[i * nv + j]);
+        if (sum < best) { best = sum; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    }
+    __syncwarp();
+    if (lane == 0 && bi > 0) { const int tmp = ws.images[0]; ws.images[0] = ws.images[bi]; ws.images[bi] = tmp; }
+    __syncwarp();
+}
+
 // Optim::postProcess (optim.cpp:260-290), the part that does not read the patch store (everything before
-// setVImagesVGrids / check).  tmp_out = Patch::score2(nccThreshold).
+// setVImagesVGrids / check), on {X, N, ws.images[0..nv)}.  Returns 0 / -1; nv = m_images.size() on success.
+// `wslot` selects this warp's slice of the pairwise scratch.
+template <int WS>
+__device__ PMK_CAND_INLINE int warp_post_process(const CandParams& cp, WarpScratch& ws, V4 X, V4 N, int& nv, int wslot, int lane) {
+    constexpr int GW = WS <= 8 ? 8 : 16;
+    const Params& p = cp.p;
+    int r = -1;
+    do {
+        if (nv < p.min_image_num) break;                                                             // :261
+        // getMask: the synthetic / maskless case returns -1 != 0 (photoSet.cpp:223-233), nothing to do   :265
+        nv = warp_add_images(p, X, N, ws.images, nv, CAND_MAXV, ws.mark, lane);                      // :268
+        warp_set_inccs<WS, GW>(p, X, N, ws.images, nv, 0, ws.inccs, lane);                           // :269
+        nv = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, lane);
+        __syncwarp();
+        nv = warp_filter_by_angle(p, X, N, ws.images, nv, lane);                                     // :270
+        __syncwarp();
+        if (nv < p.min_image_num) break;                                                             // :272
+        warp_set_ref_image<WS>(cp, ws, X, N, nv, wslot, lane);                                       // :277
+        warp_set_inccs<WS, GW>(p, X, N, ws.images, nv, 0, ws.inccs, lane);                           // :279
+        nv = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, lane);
+        __syncwarp();
+        if (nv < p.min_image_num) break;                                                             // :281
+        r = 0;
+    } while (false);
+    __syncwarp();
+    return r;
+}
+
+// tmp_out = Patch::score2(nccThreshold).
 template <int WS>
 __global__ void __launch_bounds__(CAND_WARPS * 32) k_post_process(const CandParams cp, int n, const float4* __restrict__ coord,
                                                                   const float4* __restrict__ normal, const float* __restrict__ ncc,
                                                                   const int* __restrict__ views, const int* __restrict__ nviews, int stride, int maxv,
                                                                   int* __restrict__ ret, int* __restrict__ images_out, int* __restrict__ nimages_out,
                                                                   int* __restrict__ grids_out, float* __restrict__ tmp_out) {
-    constexpr int GW = WS <= 8 ? 8 : 16;
-    constexpr int G = 32 / GW;
-    constexpr int TEXW = WS * WS * 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch& ws = warp_scratch(smem_raw);
     const Params& p = cp.p;
     const int lane = threadIdx.x & 31;
-    const int grp = lane / GW, col = lane % GW;
-    const float cmask = col < WS ? 1.0f : 0.0f;
     const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
     for (int h = gwarp; h < n; h += gridDim.x * CAND_WARPS) {
         const float4 c = __ldg(coord + h), m = __ldg(normal + h);
@@ -704,79 +811,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_post_process(const CandPara
         int nv = min(min(__ldg(nviews + h), stride), CAND_MAXV);
         for (int i = lane; i < nv; i += 32) ws.images[i] = __ldg(views + (size_t)h * stride + i);
         __syncwarp();
-        int r = -1;
-        do {
-            if (nv < p.min_image_num) break;                                                             // :261
-            // getMask: the synthetic / maskless case returns -1 != 0 (photoSet.cpp:223-233), nothing to do   :265
-            nv = warp_add_images(p, X, N, ws.images, nv, CAND_MAXV, ws.mark, lane);                      // :268
-            warp_set_inccs<WS, GW>(p, X, N, ws.images, nv, 0, ws.inccs, lane);                           // :269
-            nv = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, lane);
-            __syncwarp();
-            nv = warp_filter_by_angle(p, X, N, ws.images, nv, lane);                                     // :270
-            __syncwarp();
-            if (nv < p.min_image_num) break;                                                             // :272
-            // setRefImage (optim.cpp:348-383): pairwise robust INCC, reference = argmin of the row sums
-            {
-                float* tex = cp.tex_scratch + (size_t)gwarp * p.nviews * (TEXW + 4);
-                float* mat = cp.mat_scratch + (size_t)gwarp * p.nviews * p.nviews;
-                V4 px, py;
-                get_paxes(p.views[ws.images[0]], X, N, p.level_scale, px, py);
-                float t[WS][3];
-                float inv;
-                for (int base = 0; base < nv; base += G) {
-                    const int i = base + grp;
-                    const int lv = group_grab<WS, GW>(p, i < nv ? ws.images[i] : -1, X, N, px, py, col, cmask, t, inv);
-                    if (i < nv) {
-                        float* dst = tex + (size_t)i * (TEXW + 4);
-                        if (col < WS)
-#pragma unroll
-                            for (int y = 0; y < WS; ++y) { float* q = dst + (y * WS + col) * 3; q[0] = t[y][0] * inv; q[1] = t[y][1] * inv; q[2] = t[y][2] * inv; }
-                        if (col == 0) dst[TEXW] = lv >= 0 ? 1.0f : 0.0f;
-                    }
-                }
-                __syncwarp();
-                for (int q = lane; q < nv * nv; q += 32) {
-                    const int i = q / nv, j = q % nv;
-                    if (j < i) continue;
-                    float v = 0.0f;
-                    if (j > i) {
-                        const float* a = tex + (size_t)i * (TEXW + 4);
-                        const float* b = tex + (size_t)j * (TEXW + 4);
-                        v = 2.0f;
-                        if (a[TEXW] != 0.0f && b[TEXW] != 0.0f) {
-                            float dp = 0.0f;
-                            for (int e = 0; e < TEXW; ++e) dp = fmaf(a[e], b[e], dp);
-                            v = robustincc(xsub(1.0f, dp * (1.0f / (float)TEXW)));
-                        }
-                    }
-                    mat[i * nv + j] = v; mat[j * nv + i] = v;
-                }
-                __syncwarp();
-                // accumulate(row, 0.0f) in index order; first minimum wins (strict <), start value INT_MAX / 2
-                float best = 1073741824.0f;
-                int bi = -1;
-                for (int i = lane; i < nv; i += 32) {
-                    float sum = 0.0f;
-                    for (int j = 0; j < nv; ++j) sum = xadd(sum, mat[i * nv + j]);
-                    if (sum < best) { best = sum; bi = i; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (oi >= 0 && (bi < 0 || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
-                }
-                __syncwarp();
-                if (lane == 0 && bi > 0) { const int tmp = ws.images[0]; ws.images[0] = ws.images[bi]; ws.images[bi] = tmp; }
-                __syncwarp();
-            }
-            warp_set_inccs<WS, GW>(p, X, N, ws.images, nv, 0, ws.inccs, lane);                           // :279
-            nv = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, lane);
-            __syncwarp();
-            if (nv < p.min_image_num) break;                                                             // :281
-            r = 0;
-        } while (false);
-        __syncwarp();
+        const int r = warp_post_process<WS>(cp, ws, X, N, nv, gwarp, lane);
         const int nout = r == 0 ? nv : 0;
         if (lane == 0) {
             ret[h] = r; nimages_out[h] = nout;

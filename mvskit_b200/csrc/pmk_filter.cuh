@@ -1,0 +1,296 @@
+// mvskit_b200/csrc/pmk_filter.cuh -- K5..K10: the store rebuild and the four filters of Filter::run (pmmvps/filter.cpp:25-49).
+//
+//   rebuild  = PatchManager::collectPatches (patch_manager.cpp:75-104) + Filter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:628-655):
+//              K5a collect keys -> radix sort -> K5b gather (ids become the reference's m_ppatches indices), K5c register m_pgrids,
+//              K5d depth maps (atomicMin on depth|id: nearest patch, first in collect order on ties), K5e setVImagesVGrids + m_vpgrids
+//   K6  filterOutside  (filter.cpp:51-106)   computeGain for every patch against one snapshot, then remove gain < 0
+//   K7  filterExact    (filter.cpp:148-263)  per registration: visible in its cell or a 4-neighbour; rebuild m_images in view order,
+//                                            setRefImage (pairwise INCC), setGrids; drop below minImageNum
+//   K8  filterNeighbor (filter.cpp:265-336)  < 6 neighbours or quadric residual >= m_quadThreshold
+//   K9  filterSmallGroups (filter.cpp:432-578) directed isNeighbor edges in the +-1 cells of the reference view (device),
+//                                            breadth-first labelling in m_ppatches order (host, order-dependent in the reference)
+#pragma once
+
+#include "pmk_sweep.cuh"
+
+namespace pmk {
+
+// ---- K5a: collect key = first appearance in the reference's scan (view, cell, creation order) ------------------------------------
+__global__ void k5_collect_keys(const StoreParams sp, int n, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    const StoreDev& st = sp.st;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    unsigned long long key = ~0ull;
+    if (st.state[p] == 1) {
+        const int ni = st.nimg[p];
+        for (int i = 0; i < ni; ++i) {
+            const int img = st.images[(size_t)p * st.maxv + i], c = st.cells[(size_t)p * st.maxv + i];
+            const unsigned long long k = ((unsigned long long)img << 56) | ((unsigned long long)(cell_y(c) * sp.cp.p.views[img].gw + cell_x(c)) << 32) | st.birth[p];
+            key = k < key ? k : key;
+        }
+        if (ni == 0) key = ~0ull - 1;           // registered nowhere: the reference can no longer reach it
+    }
+    keys[p] = key;
+    vals[p] = p;
+}
+
+__global__ void k5_count_alive(const unsigned long long* __restrict__ keys, int n, int* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    // keys are sorted ascending: the alive prefix ends where the key reaches the sentinels
+    const bool alive = keys[p] < ~0ull - 1;
+    const bool next_alive = (p + 1 < n) && keys[p + 1] < ~0ull - 1;
+    if (alive && !next_alive) *out = p + 1;
+}
+
+// ---- K5b: gather the surviving patches into collect order (dst arrays are the second buffer set) -----------------------------------
+__global__ void k5_gather(const StoreDev src, const StoreDev dst, const int* __restrict__ perm, int nalive) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = gwarp; q < nalive; q += nwarps) {
+        const int p = perm[q];
+        const int ni = src.nimg[p], nv = src.nvimg[p];
+        if (lane == 0) {
+            dst.coord[q] = src.coord[p]; dst.normal[q] = src.normal[p]; dst.scal[q] = src.scal[p];
+            dst.nimg[q] = ni; dst.nvimg[q] = nv; dst.state[q] = 1; dst.birth[q] = src.birth[p];
+        }
+        for (int i = lane; i < ni; i += 32) { dst.images[(size_t)q * dst.maxv + i] = src.images[(size_t)p * src.maxv + i]; dst.cells[(size_t)q * dst.maxv + i] = src.cells[(size_t)p * src.maxv + i]; }
+        for (int i = lane; i < nv; i += 32) { dst.vimages[(size_t)q * dst.maxv + i] = src.vimages[(size_t)p * src.maxv + i]; dst.vcells[(size_t)q * dst.maxv + i] = src.vcells[(size_t)p * src.maxv + i]; }
+    }
+}
+
+// ---- K5c: m_pgrids from the patch lists ----------------------------------------------------------------------------------------------
+__global__ void k5_register(const StoreParams sp, int n, int first, int with_v, int with_depth) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = first + gwarp; q < n; q += nwarps) {
+        if (sp.st.state[q] != 1) continue;
+        warp_register_patch(sp, q, with_v != 0, with_depth != 0, lane);
+    }
+}
+
+// ---- K5d: Filter::setDepthMapsSub (filter.cpp:587-626), one thread per (patch, view) -------------------------------------------------
+__global__ void k5_depth_maps(const StoreParams sp, int n) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nviews = sp.cp.p.nviews;
+    if (t >= (long long)n * nviews) return;
+    const int q = (int)(t / nviews), v = (int)(t % nviews);
+    if (sp.st.state[q] != 1) return;
+    update_depth_map(sp, q, f4v(sp.st.coord[q]), v);
+}
+
+// ---- K5e: Filter::setVGridsVPGrids + addPatchV (filter.cpp:657-687) ------------------------------------------------------------------
+__global__ void __launch_bounds__(CAND_WARPS * 32) k5_set_vimages(const StoreParams sp, int n, int additive) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& ws = warp_scratch(smem_raw);
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    for (int q = gwarp; q < n; q += gridDim.x * CAND_WARPS) {
+        if (st.state[q] != 1) continue;
+        const int nvv0 = additive ? st.nvimg[q] : 0;
+        const int nvv = warp_set_vimages(sp, ws, f4v(st.coord[q]), f4v(st.normal[q]), st.images + (size_t)q * st.maxv, st.nimg[q],
+                                         st.vimages + (size_t)q * st.maxv, st.vcells + (size_t)q * st.maxv, nvv0, lane);
+        if (lane == 0) st.nvimg[q] = nvv;
+        __syncwarp();
+        for (int i = lane; i < nvv; i += 32) {
+            const int img = st.vimages[(size_t)q * st.maxv + i], c = st.vcells[(size_t)q * st.maxv + i];
+            insert_into_cell(st, cell_global(sp, img, cell_x(c), cell_y(c)), (int)((unsigned)q | SLOT_V));
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ PatchLists lists_of(const StoreDev& st, int q) {
+    return PatchLists{st.images + (size_t)q * st.maxv, st.cells + (size_t)q * st.maxv, st.nimg[q],
+                      st.vimages + (size_t)q * st.maxv, st.vcells + (size_t)q * st.maxv, st.nvimg[q]};
+}
+
+// ---- K6: Filter::filterOutsideSub (filter.cpp:98-106) ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CAND_WARPS * 32) k6_gains(const StoreParams sp, int n, float* __restrict__ gains) {
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    const Overlay none{-1, nullptr, 0, nullptr, 0};
+    for (int q = gwarp; q < n; q += gridDim.x * CAND_WARPS) {
+        if (st.state[q] != 1) { if (lane == 0) gains[q] = 0.0f; continue; }
+        const float g = warp_compute_gain(sp, load_geo(st, q), st.scal[q].x, lists_of(st, q), none, lane);
+        if (lane == 0) gains[q] = g;
+    }
+}
+
+// remove[q] != 0 -> the patch leaves the store at the next rebuild (PatchManager::removePatch; the grids are rebuilt from
+// the patch lists before anything reads them again, filter.cpp:29-48)
+__global__ void k_kill_flagged(const StoreDev st, int n, const float* __restrict__ gains, const int* __restrict__ flags, int* __restrict__ killed) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || st.state[q] != 1) return;
+    const bool kill = gains ? gains[q] < 0.0f : flags[q] != 0;
+    if (kill) { st.state[q] = 0; atomicAdd(killed, 1); }
+}
+
+// ---- K7: Filter::filterExact (filter.cpp:148-263) -------------------------------------------------------------------------------------
+template <int WS>
+__global__ void __launch_bounds__(CAND_WARPS * 32) k7_exact(const StoreParams sp, int n, int* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& ws = warp_scratch(smem_raw);
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    for (int q = gwarp; q < n; q += gridDim.x * CAND_WARPS) {
+        if (st.state[q] != 1) { if (lane == 0) flags[q] = 0; continue; }
+        const V4 X = f4v(st.coord[q]), N = f4v(st.normal[q]);
+        const int ni = min(st.nimg[q], CAND_MAXV);
+        const float thr = sp.neighbor_threshold1;
+        // safe[i] (filter.cpp:226-246): visible in its own cell or in one of the 4 neighbours
+        for (int i = lane; i < ni; i += 32) {
+            const int img = st.images[(size_t)q * st.maxv + i], c = st.cells[(size_t)q * st.maxv + i];
+            const int x = cell_x(c), y = cell_y(c), w = p.views[img].gw, h = p.views[img].gh;
+            int safe = 0;
+            if (is_visible(sp, X, N, img, x, y, thr)) safe = 1;
+            else if (0 < x && is_visible(sp, X, N, img, x - 1, y, thr)) safe = 1;
+            else if (x < w - 1 && is_visible(sp, X, N, img, x + 1, y, thr)) safe = 1;
+            else if (0 < y && is_visible(sp, X, N, img, x, y - 1, thr)) safe = 1;
+            else if (y < h - 1 && is_visible(sp, X, N, img, x, y + 1, thr)) safe = 1;
+            ws.idx[i] = img;
+            ws.alive[i] = (unsigned char)safe;
+        }
+        __syncwarp();
+        // m_newimages: the safe views in ascending view order (the outer loop of filterExactSub runs over views)
+        int cnt = 0;
+        for (int i = lane; i < ni; i += 32) {
+            if (!ws.alive[i]) continue;
+            int rank = 0;
+            for (int j = 0; j < ni; ++j) if (ws.alive[j] && (ws.idx[j] < ws.idx[i] || (ws.idx[j] == ws.idx[i] && j < i))) ++rank;
+            ws.images[rank] = ws.idx[i];
+        }
+        for (int i = 0; i < ni; ++i) cnt += ws.alive[i] ? 1 : 0;
+        __syncwarp();
+        int kill = 0;
+        if (p.min_image_num <= cnt) {
+            warp_set_ref_image<WS>(sp.cp, ws, X, N, cnt, gwarp, lane);                           // :252
+        } else kill = 1;                                                                        // :256-259
+        for (int i = lane; i < cnt; i += 32) {                                                  // setGrids (:253)
+            const int img = ws.images[i];
+            const V3 ic = project(p.views[img].P, X);
+            st.images[(size_t)q * st.maxv + i] = img;
+            st.cells[(size_t)q * st.maxv + i] = pack_cell(cell_of(ic.x, p.csize), cell_of(ic.y, p.csize));
+        }
+        if (lane == 0) { st.nimg[q] = cnt; flags[q] = kill; }
+        __syncwarp();
+    }
+}
+
+// ---- K8: Filter::filterNeighborSub (filter.cpp:316-336) -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CAND_WARPS * 32) k8_neighbor(const StoreParams sp, int n, int* __restrict__ flags, int* __restrict__ nn_out, float* __restrict__ res_out) {
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    const Overlay none{-1, nullptr, 0, nullptr, 0};
+    int* nb = sp.nb_scratch + (size_t)gwarp * NB_CAP;
+    for (int q = gwarp; q < n; q += gridDim.x * CAND_WARPS) {
+        if (st.state[q] != 1) { if (lane == 0) { flags[q] = 0; if (nn_out) nn_out[q] = 0; if (res_out) res_out[q] = 0.0f; } continue; }
+        const PGeo me = load_geo(st, q);
+        const PatchLists pl = lists_of(st, q);
+        const int nn = warp_find_neighbors(sp, me, pl, 4.0f, 2, none, nb, lane);
+        int rej = 0;
+        float res = -1.0f;
+        if (nn < 6) rej = 1;
+        else if (warp_filter_quad(sp, me, pl, nb, nn, &res, lane)) rej = 1;
+        if (lane == 0) { flags[q] = rej; if (nn_out) nn_out[q] = nn; if (res_out) res_out[q] = res; }
+        __syncwarp();
+    }
+}
+
+// ---- K9: directed isNeighbor edges for Filter::filterSmallGroupsSub (filter.cpp:527-578).  pass 0 counts, pass 1 fills. -----------------
+__global__ void __launch_bounds__(CAND_WARPS * 32) k9_group_edges(const StoreParams sp, int n, int pass, int* __restrict__ deg, const int* __restrict__ offs, int* __restrict__ adj) {
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    for (int q = gwarp; q < n; q += gridDim.x * CAND_WARPS) {
+        if (st.state[q] != 1) { if (pass == 0 && lane == 0) deg[q] = 0; continue; }
+        const PGeo me = load_geo(st, q);
+        const int img = me.ref, c0 = st.cells[(size_t)q * st.maxv];
+        const int ix = cell_x(c0), iy = cell_y(c0);
+        const ViewConst& vc = p.views[img];
+        int cnt = 0;
+        const int o0 = pass ? offs[q] : 0;
+        for (int w = 0; w < 9; ++w) {
+            const int yt = iy + w / 3 - 1, xt = ix + w % 3 - 1;
+            if (yt < 0 || vc.gh <= yt || xt < 0 || vc.gw <= xt) continue;
+            const int c = cell_global(sp, img, xt, yt);
+            const int m = min(st.ccount[c], st.cell_cap);
+            for (int base = 0; base < m; base += 32) {
+                const int s = base + lane;
+                bool hit = false;
+                int id = 0;
+                if (s < m) {
+                    const int e = st.cslots[(size_t)c * st.cell_cap + s];
+                    if ((e & 0x7fffffff) != SLOT_TOMB) {
+                        id = e & 0x7fffffff;
+                        if (id != q && st.state[id] == 1) hit = is_neighbor(sp, me, load_geo(st, id), sp.neighbor_threshold2) != 0;
+                    }
+                }
+                const unsigned msk = __ballot_sync(0xffffffffu, hit);
+                if (pass && hit) adj[o0 + cnt + __popc(msk & ((1u << lane) - 1u))] = id;
+                cnt += __popc(msk);
+            }
+        }
+        if (pass == 0 && lane == 0) deg[q] = cnt;
+        __syncwarp();
+    }
+}
+
+// PatchManager::writePly colour (patch_manager.cpp:566-581): mean over m_images of Image::getColor at the projection, rounded
+__global__ void k_patch_colors(const StoreParams sp, int n, unsigned char* __restrict__ rgb) {
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const V4 X = f4v(st.coord[q]);
+    float r = 0.f, g = 0.f, b = 0.f;
+    const int ni = st.nimg[q];
+    for (int i = 0; i < ni; ++i) {
+        const ViewConst& vc = p.views[st.images[(size_t)q * st.maxv + i]];
+        const V3 ic = project(vc.P, X);
+        const float x = fminf(fmaxf(ic.x, 0.0f), (float)(vc.w[p.level] - 2)), y = fminf(fmaxf(ic.y, 0.0f), (float)(vc.h[p.level] - 2));
+        float cr, cg, cb;
+        bilinear(vc.img[p.level], vc.w[p.level], x, y, cr, cg, cb);
+        r += cr; g += cg; b += cb;
+    }
+    const float inv = ni > 0 ? 1.0f / (float)ni : 0.0f;
+    rgb[3 * q] = (unsigned char)min(255, (int)floorf(r * inv + 0.5f));
+    rgb[3 * q + 1] = (unsigned char)min(255, (int)floorf(g * inv + 0.5f));
+    rgb[3 * q + 2] = (unsigned char)min(255, (int)floorf(b * inv + 0.5f));
+}
+
+// PatchManager::readPatches body (patch_manager.cpp:450-462) for patches already copied to slots [first, first + n):
+// m_tmp = score2(m_nccThreshold), m_vimages cleared, setGrids, addPatch.  One warp per patch.
+__global__ void k_store_add(const StoreParams sp, int first, int n, unsigned int birth0) {
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = gwarp; k < n; k += nwarps) {
+        const int q = first + k;
+        const V4 X = f4v(st.coord[q]);
+        const int ni = st.nimg[q];
+        for (int i = lane; i < ni; i += 32) {
+            const V3 ic = project(p.views[st.images[(size_t)q * st.maxv + i]].P, X);
+            st.cells[(size_t)q * st.maxv + i] = pack_cell(cell_of(ic.x, p.csize), cell_of(ic.y, p.csize));
+        }
+        if (lane == 0) {
+            float4 sc = st.scal[q];
+            sc.w = xmul(max_std(0.0f, xsub(sc.x, p.ncc_threshold)), (float)ni);
+            st.scal[q] = sc;
+            st.nvimg[q] = 0; st.state[q] = 1; st.birth[q] = birth0 + (unsigned int)k;
+        }
+        __syncwarp();
+        const bool deep = p.depth != 0;
+        warp_register_patch(sp, q, deep, deep, lane);
+        __syncwarp();
+    }
+}
+
+}  // namespace pmk

@@ -1,0 +1,379 @@
+// mvskit_b200/csrc/pmk_store_host.cuh -- host side of the device patch store: allocation, the rebuild
+// (collect + compact + register + depth maps + visible lists), the sweep driver (Propagate::run) and Filter::run.
+// Included by pmk_api.cu after pmk_ctx is defined.
+#pragma once
+
+#include <algorithm>
+#include <random>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "pmk_filter.cuh"
+
+struct pmk_store {
+    pmk::StoreDev d;                    // device pointers
+    int n = 0;                          // patches allocated (host mirror of SC_N)
+    int max_tasks = 0;
+    int* cell_base_d = nullptr;
+    std::vector<int> cell_base;         // host copy
+    // scratch
+    int* rem_list = nullptr; int* task_new = nullptr; int* final_id = nullptr;
+    unsigned long long* stats = nullptr;
+    unsigned long long* keys = nullptr; unsigned long long* keys2 = nullptr;
+    int* vals = nullptr; int* vals2 = nullptr;
+    void* cub_tmp = nullptr; size_t cub_bytes = 0;
+    void* gather_tmp = nullptr; size_t gather_bytes = 0;
+    float* f_tmp = nullptr; int* i_tmp = nullptr; int* i_tmp2 = nullptr; int* i_tmp3 = nullptr;
+    int* nb_scratch = nullptr;
+    int* small = nullptr;               // a few device ints for results
+    float jitter[4];
+    bool canonical = false;             // patch ids are the reference's m_ppatches indices (collect order, no holes)
+};
+
+namespace {
+
+using namespace pmk;
+
+template <typename T>
+int dalloc(pmk_ctx* ctx, T** p, size_t count) {
+    CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    ctx->owned.push_back(*p);
+    return PMK_OK;
+}
+
+int store_params(pmk_ctx* ctx, StoreParams& sp, uint64_t seed) {
+    int rc = cand_params(ctx, sp.cp, seed);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    sp.st = s->d;
+    sp.neighbor_cos = cosf(120.0f / M_PI * 180.0f);                 // pmmvps.cpp:124, value preserved
+    sp.neighbor_radius_cos = cos(120.0f * M_PI / 180.0f);           // pmmvps.cpp:150
+    sp.neighbor_threshold = ctx->neighbor_threshold;
+    sp.neighbor_threshold1 = ctx->neighbor_threshold1;
+    sp.neighbor_threshold2 = ctx->neighbor_threshold2;
+    sp.quad_threshold = ctx->cfg.quad_threshold;
+    sp.max_patches_cell = 2 * ctx->cfg.csize * ctx->cfg.csize;     // propagate.cpp:24-25
+    sp.nb_scratch = s->nb_scratch;
+    return PMK_OK;
+}
+
+int store_init(pmk_ctx* ctx) {
+    if (ctx->store) return PMK_OK;
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    if (ctx->cfg.nviews > CAND_MAXV) return fail(PMK_ERR_ARG, "pmk: the patch store supports at most 128 views");
+    if (2 * ctx->cfg.csize * ctx->cfg.csize > 32) return fail(PMK_ERR_ARG, "pmk: csize too large for the sweep (2*csize^2 <= 32)");
+    pmk_store* s = new pmk_store();
+    ctx->store = s;
+    const int nv = ctx->cfg.nviews;
+    s->cell_base.assign(nv + 1, 0);
+    int max_diag = 1;
+    for (int v = 0; v < nv; ++v) {
+        const ViewConst& vc = ctx->h_views[v];
+        if (vc.gw >= 65535 || vc.gh >= 32767) return fail(PMK_ERR_ARG, "pmk: cell grid too large for packed cell indices");
+        s->cell_base[v + 1] = s->cell_base[v] + vc.gw * vc.gh;
+        max_diag = std::max(max_diag, std::min(vc.gw, vc.gh));
+    }
+    StoreDev& d = s->d;
+    d.total_cells = s->cell_base[nv];
+    d.maxv = nv;
+    d.cell_cap = ctx->cfg.cell_capacity > 0 ? ctx->cfg.cell_capacity : 96;
+    if (d.cell_cap > LIST_MAX) return fail(PMK_ERR_ARG, "pmk: cell_capacity exceeds 128");
+    d.cap = ctx->cfg.max_patches > 0 ? ctx->cfg.max_patches : 2 * d.total_cells;
+    s->max_tasks = max_diag;
+    d.stage_cap = s->max_tasks * NEW_MAX;
+    const size_t tot = (size_t)d.cap + d.stage_cap;
+    if ((rc = dalloc(ctx, &d.coord, tot)) || (rc = dalloc(ctx, &d.normal, tot)) || (rc = dalloc(ctx, &d.scal, tot)) ||
+        (rc = dalloc(ctx, &d.nimg, tot)) || (rc = dalloc(ctx, &d.nvimg, tot)) || (rc = dalloc(ctx, &d.state, tot)) || (rc = dalloc(ctx, &d.birth, tot)) ||
+        (rc = dalloc(ctx, &d.images, tot * d.maxv)) || (rc = dalloc(ctx, &d.cells, tot * d.maxv)) ||
+        (rc = dalloc(ctx, &d.vimages, tot * d.maxv)) || (rc = dalloc(ctx, &d.vcells, tot * d.maxv)) ||
+        (rc = dalloc(ctx, &d.counters, SC_COUNT)) || (rc = dalloc(ctx, &s->cell_base_d, nv + 1)) ||
+        (rc = dalloc(ctx, &d.ccount, d.total_cells)) || (rc = dalloc(ctx, &d.cslots, (size_t)d.total_cells * d.cell_cap)) ||
+        (rc = dalloc(ctx, &d.dmap, d.total_cells)))
+        return rc;
+    d.cell_base = s->cell_base_d;
+    CUDA_TRY(cudaMemcpyAsync(s->cell_base_d, s->cell_base.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = dalloc(ctx, &s->rem_list, d.cap)) || (rc = dalloc(ctx, &s->task_new, s->max_tasks)) || (rc = dalloc(ctx, &s->final_id, d.stage_cap)) ||
+        (rc = dalloc(ctx, &s->stats, SS_COUNT)) || (rc = dalloc(ctx, &s->keys, d.cap)) || (rc = dalloc(ctx, &s->keys2, d.cap)) ||
+        (rc = dalloc(ctx, &s->vals, d.cap)) || (rc = dalloc(ctx, &s->vals2, d.cap)) || (rc = dalloc(ctx, &s->f_tmp, d.cap)) ||
+        (rc = dalloc(ctx, &s->i_tmp, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp2, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp3, d.cap + 1)) || (rc = dalloc(ctx, &s->small, 16)))
+        return rc;
+    CandParams cp;
+    if ((rc = cand_params(ctx, cp, 0))) return rc;                       // sizes cand_grid and the pairwise scratch
+    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * NB_CAP))) return rc;
+    s->gather_bytes = (size_t)d.cap * d.maxv * sizeof(int);
+    s->gather_bytes = std::max(s->gather_bytes, (size_t)d.cap * sizeof(float4));
+    CUDA_TRY(cudaMalloc(&s->gather_tmp, s->gather_bytes));
+    ctx->owned.push_back(s->gather_tmp);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, s->keys, s->keys2, s->vals, s->vals2, d.cap, 0, 64, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, s->i_tmp, s->i_tmp2, d.cap + 1, ctx->stream);
+    s->cub_bytes = std::max(b1, b2);
+    CUDA_TRY(cudaMalloc(&s->cub_tmp, s->cub_bytes));
+    ctx->owned.push_back(s->cub_tmp);
+    // the reference re-constructs std::default_random_engine on every propagatePatch call (propagate.cpp:139-141), so
+    // its jitter is always the first four draws; same libstdc++, same values
+    {
+        std::default_random_engine generator;
+        std::uniform_real_distribution<float> distribution(-0.5, 0.5);
+        for (int i = 0; i < 4; ++i) s->jitter[i] = distribution(generator);
+    }
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, SC_COUNT * sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d.ccount, 0, (size_t)d.total_cells * sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d.dmap, 0xff, (size_t)d.total_cells * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d.state, 0, tot * sizeof(int), ctx->stream));
+    s->n = 0;
+    s->canonical = true;
+    return PMK_OK;
+}
+
+int store_check_overflow(pmk_ctx* ctx) {
+    pmk_store* s = ctx->store;
+    int c[SC_COUNT];
+    CUDA_TRY(cudaMemcpyAsync(c, s->d.counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    s->n = c[SC_N];
+    if (c[SC_OVERFLOW]) return fail(PMK_ERR_CAPACITY, "pmk: " + std::to_string(c[SC_OVERFLOW]) + " cell registrations dropped (raise pmk_config.cell_capacity)");
+    if (c[SC_FULL]) return fail(PMK_ERR_CAPACITY, "pmk: patch store full, " + std::to_string(c[SC_FULL]) + " patches dropped (raise pmk_config.max_patches)");
+    if (c[SC_NBOVER]) return fail(PMK_ERR_CAPACITY, "pmk: findNeighbors scratch overflow");
+    return PMK_OK;
+}
+
+template <typename T>
+int gather_rows(pmk_ctx* ctx, T* arr, const int* perm, int nalive, int row);
+
+template <typename T>
+__global__ void k_gather_rows(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ perm, long long total, int row) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long q = t / row; const int i = (int)(t % row);
+    dst[t] = src[(size_t)perm[q] * row + i];
+}
+
+template <typename T>
+int gather_rows(pmk_ctx* ctx, T* arr, const int* perm, int nalive, int row) {
+    if (nalive <= 0) return PMK_OK;
+    pmk_store* s = ctx->store;
+    const long long total = (long long)nalive * row;
+    k_gather_rows<T><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(arr, (T*)s->gather_tmp, perm, total, row);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(arr, s->gather_tmp, (size_t)total * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PMK_OK;
+}
+
+__global__ void k_fill_state(int* state, int nalive, int n) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) state[q] = q < nalive ? 1 : 0;
+}
+
+// PatchManager::collectPatches order (patch_manager.cpp:75-104): s->vals2[0..nalive) = patch ids in m_ppatches order
+int store_order(pmk_ctx* ctx, const StoreParams& sp, int* nalive_out) {
+    pmk_store* s = ctx->store;
+    cudaStream_t st = ctx->stream;
+    const int n = s->n;
+    int nalive = 0;
+    if (n > 0) {
+        k5_collect_keys<<<(n + 255) / 256, 256, 0, st>>>(sp, n, s->keys, s->vals);
+        ctx->launches++;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_tmp, s->cub_bytes, s->keys, s->keys2, s->vals, s->vals2, n, 0, 64, st));
+        ctx->launches++;
+        CUDA_TRY(cudaMemsetAsync(s->small, 0, sizeof(int), st));
+        k5_count_alive<<<(n + 255) / 256, 256, 0, st>>>(s->keys2, n, s->small);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&nalive, s->small, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    *nalive_out = nalive;
+    return PMK_OK;
+}
+
+// collectPatches + setDepthMapsVGridsVPGridsAddPatchV(additive): after this, patch ids are the reference's m_ppatches indices
+int store_rebuild(pmk_ctx* ctx, int additive) {
+    pmk_store* s = ctx->store;
+    StoreParams sp;
+    int rc = store_params(ctx, sp, 0);
+    if (rc) return rc;
+    StoreDev& d = s->d;
+    cudaStream_t st = ctx->stream;
+    if ((rc = store_check_overflow(ctx))) return rc;
+    const int n = s->n;
+    int nalive = 0;
+    if ((rc = store_order(ctx, sp, &nalive))) return rc;
+    if (n > 0) {
+        if ((rc = gather_rows(ctx, d.coord, s->vals2, nalive, 1)) || (rc = gather_rows(ctx, d.normal, s->vals2, nalive, 1)) ||
+            (rc = gather_rows(ctx, d.scal, s->vals2, nalive, 1)) || (rc = gather_rows(ctx, d.nimg, s->vals2, nalive, 1)) ||
+            (rc = gather_rows(ctx, d.nvimg, s->vals2, nalive, 1)) || (rc = gather_rows(ctx, d.birth, s->vals2, nalive, 1)) ||
+            (rc = gather_rows(ctx, d.images, s->vals2, nalive, d.maxv)) || (rc = gather_rows(ctx, d.cells, s->vals2, nalive, d.maxv)) ||
+            (rc = gather_rows(ctx, d.vimages, s->vals2, nalive, d.maxv)) || (rc = gather_rows(ctx, d.vcells, s->vals2, nalive, d.maxv)))
+            return rc;
+        k_fill_state<<<(n + 255) / 256, 256, 0, st>>>(d.state, nalive, n);
+        ctx->launches++;
+    }
+    s->n = nalive;
+    CUDA_TRY(cudaMemcpyAsync(d.counters + SC_N, &s->n, sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d.ccount, 0, (size_t)d.total_cells * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(d.dmap, 0xff, (size_t)d.total_cells * sizeof(unsigned long long), st));
+    if (nalive > 0) {
+        const int blocks = std::min(ctx->sm_count * 8, (nalive + 3) / 4);
+        k5_register<<<blocks, 128, 0, st>>>(sp, nalive, 0, 0, 0);
+        ctx->launches++;
+        const long long tot = (long long)nalive * ctx->cfg.nviews;
+        k5_depth_maps<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(sp, nalive);
+        ctx->launches++;
+        const int grid = std::max(1, std::min(ctx->cand_grid, (nalive + CAND_WARPS - 1) / CAND_WARPS));
+        k5_set_vimages<<<grid, CAND_WARPS * 32, CAND_WARPS * sizeof(WarpScratch), st>>>(sp, nalive, additive);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    s->canonical = true;
+    return store_check_overflow(ctx);
+}
+
+int kill_flagged(pmk_ctx* ctx, const float* gains, const int* flags, int* killed) {
+    pmk_store* s = ctx->store;
+    if (s->n <= 0) { *killed = 0; return PMK_OK; }
+    CUDA_TRY(cudaMemsetAsync(s->small, 0, sizeof(int), ctx->stream));
+    k_kill_flagged<<<(s->n + 255) / 256, 256, 0, ctx->stream>>>(s->d, s->n, gains, flags, s->small);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(killed, s->small, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    s->canonical = false;
+    return PMK_OK;
+}
+
+// Filter::filterSmallGroups (filter.cpp:432-525): edges on the device, breadth-first labelling on the host in id order
+int small_groups(pmk_ctx* ctx, const StoreParams& sp, int* flags_dev, int* removed) {
+    pmk_store* s = ctx->store;
+    const int n = s->n;
+    *removed = 0;
+    if (n <= 0) return PMK_OK;
+    cudaStream_t st = ctx->stream;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    k9_group_edges<<<grid, CAND_WARPS * 32, 0, st>>>(sp, n, 0, s->i_tmp, nullptr, nullptr);
+    ctx->launches++;
+    CUDA_TRY(cudaMemsetAsync(s->i_tmp + n, 0, sizeof(int), st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->cub_tmp, s->cub_bytes, s->i_tmp, s->i_tmp2, n + 1, st));
+    ctx->launches++;
+    std::vector<int> offs(n + 1);
+    CUDA_TRY(cudaMemcpyAsync(offs.data(), s->i_tmp2, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int nedges = offs[n];
+    int* adj_d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&adj_d, std::max(nedges, 1) * sizeof(int)));
+    k9_group_edges<<<grid, CAND_WARPS * 32, 0, st>>>(sp, n, 1, nullptr, s->i_tmp2, adj_d);
+    ctx->launches++;
+    std::vector<int> adj(std::max(nedges, 1));
+    cudaError_t e = cudaMemcpyAsync(adj.data(), adj_d, (size_t)nedges * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(adj_d);
+    if (e != cudaSuccess) return fail(PMK_ERR_CUDA, std::string("small_groups: ") + cudaGetErrorString(e));
+    std::vector<int> label(n, -1), queue;
+    queue.reserve(n);
+    int id = -1;
+    for (int pid = 0; pid < n; ++pid) {
+        if (label[pid] != -1) continue;
+        label[pid] = ++id;
+        queue.clear();
+        queue.push_back(pid);
+        for (size_t h = 0; h < queue.size(); ++h) {
+            const int cur = queue[h];
+            for (int k = offs[cur]; k < offs[cur + 1]; ++k) {
+                const int q = adj[k];
+                if (label[q] != -1) continue;
+                label[q] = id;
+                queue.push_back(q);
+            }
+        }
+    }
+    ++id;
+    std::vector<int> size(id, 0);
+    for (int pid = 0; pid < n; ++pid) ++size[label[pid]];
+    const int threshold = std::max(20, n / 10000);
+    std::vector<int> flags(n, 0);
+    for (int pid = 0; pid < n; ++pid) if (size[label[pid]] < threshold) { flags[pid] = 1; ++*removed; }
+    CUDA_TRY(cudaMemcpyAsync(flags_dev, flags.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PMK_OK;
+}
+
+// one filter stage on a clean store; outputs stay in s->f_tmp / s->i_tmp / s->i_tmp3 for pmk_filter_stage
+int filter_stage(pmk_ctx* ctx, int stage, int* killed) {
+    pmk_store* s = ctx->store;
+    StoreParams sp;
+    int rc = store_params(ctx, sp, 0);
+    if (rc) return rc;
+    *killed = 0;
+    const int n = s->n;
+    if (n <= 0) return PMK_OK;
+    cudaStream_t st = ctx->stream;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    const size_t smem = CAND_WARPS * sizeof(WarpScratch);
+    switch (stage) {
+        case 1:
+            k6_gains<<<grid, CAND_WARPS * 32, 0, st>>>(sp, n, s->f_tmp);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return kill_flagged(ctx, s->f_tmp, nullptr, killed);
+        case 2:
+            WS_DISPATCH(ctx->cfg.wsize, (k7_exact<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, n, s->i_tmp)));
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return kill_flagged(ctx, nullptr, s->i_tmp, killed);
+        case 3:
+            k8_neighbor<<<grid, CAND_WARPS * 32, 0, st>>>(sp, n, s->i_tmp, s->i_tmp3, s->f_tmp);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return kill_flagged(ctx, nullptr, s->i_tmp, killed);
+        case 4:
+            if ((rc = small_groups(ctx, sp, s->i_tmp, killed))) return rc;
+            { int k2 = 0; return kill_flagged(ctx, nullptr, s->i_tmp, &k2); }
+    }
+    return fail(PMK_ERR_ARG, "pmk_filter_stage: unknown stage");
+}
+
+template <int WS>
+int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
+    pmk_store* s = ctx->store;
+    cudaStream_t st = ctx->stream;
+    const size_t smem = CAND_WARPS * (sizeof(WarpScratch) + sizeof(SweepScratch));
+    const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + CAND_WARPS - 1) / CAND_WARPS));
+    CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
+    k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, sa);
+    k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
+    k4_apply_scan<<<1, 256, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
+    k4_apply_add<<<std::max(1, std::min(ctx->sm_count * 2, sa.ntasks)), 128, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
+    ctx->launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    return PMK_OK;
+}
+
+// wavefront steps [diag_first, diag_first + diag_count) of Propagate::propagatePmImage for one view
+int sweep_image(pmk_ctx* ctx, int iter, int image, int diag_first, int diag_count, uint64_t seed) {
+    pmk_store* s = ctx->store;
+    StoreParams sp;
+    int rc = store_params(ctx, sp, seed);
+    if (rc) return rc;
+    const ViewConst& vc = ctx->h_views[image];
+    const int gw = vc.gw, gh = vc.gh, ndiag = gw + gh - 1;
+    const int inc = (iter % 2 == 1) ? -1 : 1;                         // propagate.cpp:80-86
+    SweepArgs sa;
+    sa.img = image; sa.inc = inc; sa.iter = iter;
+    sa.jitter_mode = ctx->cfg.jitter_mode;
+    for (int i = 0; i < 4; ++i) sa.jitter[i] = s->jitter[i];
+    sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats;
+    for (int k = diag_first; k < diag_first + diag_count && k < ndiag; ++k) {
+        const int d = inc > 0 ? k : ndiag - 1 - k;
+        sa.diag = d;
+        sa.xlo = std::max(0, d - gh + 1);
+        sa.ntasks = std::min(gw - 1, d) - sa.xlo + 1;
+        if (sa.ntasks <= 0) continue;
+        WS_DISPATCH(ctx->cfg.wsize, { if ((rc = launch_sweep<WS>(ctx, sp, sa))) return rc; });
+    }
+    s->canonical = false;
+    return PMK_OK;
+}
+
+}  // namespace

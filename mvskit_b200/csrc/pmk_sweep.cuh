@@ -1,0 +1,419 @@
+// mvskit_b200/csrc/pmk_sweep.cuh -- K4: Propagate::propagatePmImage / propagatePatch / generatePatch
+// (pmmvps/propagate.cpp:72-237) as an anti-diagonal wavefront over DEST cells.
+//
+// Schedule "PMS1".  The reference sweeps the cells of one view in raster order (Gauss-Seidel): source cell k hands its
+// patches to cells k + inc and k + inc * gwidth.  Everything written into dest cell D = (x, y) therefore comes from
+// (x, y - inc) [visited first] and (x - inc, y), both on the previous anti-diagonal, and nothing on D's own anti-diagonal
+// reads or writes D.  One wavefront step = one anti-diagonal of one view; one warp owns one dest cell and replays, in the
+// reference's order, every propagatePatch call that targets it: sort, trim to MAX_NUM_OF_PATCHES, two tries per call
+// (fill an empty slot at the jittered cell centre, or challenge the worst patch at its own pixel), generatePatch,
+// computeNcc, preProcess, refinePatch (PMR1), postProcess, removePatch / addPatch.  All grid mutations other than D's own
+// list are staged and applied between steps (k4_apply_*), so a step reads one consistent snapshot and is deterministic.
+// Differences from the raster order, by construction: (a) the row wrap of `index + inc` at a row end and the out-of-range
+// `index + inc * gwidth` on the last row (propagate.cpp:106-108, an out-of-bounds access in the reference) are skipped;
+// (b) postProcess's store reads (setVImagesVGrids, check) see the snapshot of the step start plus D's own changes.
+#pragma once
+
+#include "pmk_store.cuh"
+
+namespace pmk {
+
+enum SweepStat { SS_CALLS = 0, SS_TRIES, SS_GEN_NULL, SS_NCC_LOSE, SS_FAIL0, SS_FAIL1, SS_ADDED, SS_REPLACED, SS_TRIMMED, SS_EVALS, SS_COUNT = 16 };
+
+struct SweepArgs {
+    int img, inc, diag, ntasks, xlo;       // dest cells (xlo + t, diag - xlo - t), t in [0, ntasks)
+    int iter;                              // Propagate::run(iter)
+    int jitter_mode;                       // 0: the reference's four constant draws (propagate.cpp:139-141), 1: Philox per try
+    float jitter[4];
+    int* rem_list;                         // patches removed this step (SC_REM counts them)
+    int* task_new;                         // [max_tasks] staged entries used by each task
+    unsigned long long* stats;             // SweepStat
+};
+
+struct SweepScratch {
+    int l_id[LIST_MAX];
+    float l_ncc[LIST_MAX];
+    int src_id[SRC_MAX];
+    int removed[LIST_MAX + NEW_MAX];
+    int vimg[CAND_MAXV];
+    int vcell[CAND_MAXV];
+    int cells[CAND_MAXV];
+};
+
+// PatchManager::sortPatches (patch_manager.cpp:406-433), descending: the reference's O(n^2) swap sort, verbatim semantics
+__device__ __forceinline__ void swap_sort_desc(int* id, float* ncc, int n) {
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (ncc[i] < ncc[j]) { const float t = ncc[i]; ncc[i] = ncc[j]; ncc[j] = t; const int u = id[i]; id[i] = id[j]; id[j] = u; }
+}
+
+// m_pgrids entries of global cell c in the reference's vector order (ascending creation), then sortPatches(desc).
+// Returns the count (clamped to LIST_MAX).  only_ref >= 0 keeps, after sorting and truncating to `keep`, the patches whose
+// reference image is only_ref (propagate.cpp:102).
+__device__ __forceinline__ int warp_load_cell(const StoreParams& sp, int c, int* id, float* ncc, int lane) {
+    const StoreDev& st = sp.st;
+    const int n = min(st.ccount[c], st.cell_cap);
+    int m = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int s = base + lane;
+        int e = SLOT_TOMB;
+        if (s < n) e = st.cslots[(size_t)c * st.cell_cap + s];
+        const bool ok = e != SLOT_TOMB && e >= 0 && st.state[e] == 1;
+        const unsigned msk = __ballot_sync(0xffffffffu, ok);
+        if (ok) { const int pos = m + __popc(msk & ((1u << lane) - 1u)); if (pos < LIST_MAX) { id[pos] = e; ncc[pos] = st.scal[e].x; } }
+        m = min(LIST_MAX, m + __popc(msk));
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 1; i < m; ++i) {                    // vector order = creation order
+            const int e = id[i]; const float v = ncc[i]; const unsigned b = st.birth[e];
+            int j = i - 1;
+            while (j >= 0 && st.birth[id[j]] > b) { id[j + 1] = id[j]; ncc[j + 1] = ncc[j]; --j; }
+            id[j + 1] = e; ncc[j + 1] = v;
+        }
+    }
+    __syncwarp();
+    return m;
+}
+
+// PatchManager::computeNcc (patch_manager.cpp:401-404) by the whole warp: views spread over the evaluator groups
+template <int WS>
+__device__ __forceinline__ float warp_compute_ncc(const Params& p, WarpScratch& ws, V4 X, V4 N, int nv, int lane) {
+    constexpr int GW = WS <= 8 ? 8 : 16;
+    compute_weights(p, X, N, ws.images, nv, ws.units, lane);
+    float incc = 2.0f;
+    if (nv >= 2) {
+        const int sz = min(p.tau, nv);
+        warp_set_inccs<WS, GW>(p, X, N, ws.images, sz, 1, ws.inccs, lane);
+        float score = 0.0f, tw = 0.0f;
+        bool ref_ok = false;
+        for (int i = 1; i < sz; ++i) {
+            const float v = ws.inccs[i];
+            if (v != 2.0f) { ref_ok = true; tw = xadd(tw, ws.units[i]); score = xadd(score, xmul(v, ws.units[i])); }
+        }
+        (void)ref_ok;
+        incc = (tw == 0.0f) ? 2.0f : xdiv(score, tw);
+    }
+    __syncwarp();
+    return xsub(1.0f, unrobustincc(incc));
+}
+
+template <int WS>
+__global__ void __launch_bounds__(CAND_WARPS * 32) k4_sweep(const StoreParams sp, const SweepArgs sa) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& ws = warp_scratch(smem_raw);
+    SweepScratch& ss = reinterpret_cast<SweepScratch*>(smem_raw + CAND_WARPS * sizeof(WarpScratch))[threadIdx.x >> 5];
+    const CandParams& cp = sp.cp;
+    const Params& p = cp.p;
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    const int img = sa.img, inc = sa.inc;
+    const ViewConst& vimgc = p.views[img];
+    const int gw = vimgc.gw, gh = vimgc.gh;
+    const int maxp = sp.max_patches_cell;
+    unsigned long long stat[SS_COUNT];
+#pragma unroll
+    for (int i = 0; i < SS_COUNT; ++i) stat[i] = 0;
+
+    for (int task = gwarp; task < sa.ntasks; task += gridDim.x * CAND_WARPS) {
+        const int x = sa.xlo + task, y = sa.diag - x;
+        const int cD = st.cell_base[img] + y * gw + x;
+        int nrem = 0, nnew = 0;
+        // ---- D's list: sortPatches + trim (propagate.cpp:123-134) ----
+        int nl = warp_load_cell(sp, cD, ss.l_id, ss.l_ncc, lane);
+        for (int i = 0; i < nl; ++i) {
+            if (ss.l_ncc[i] < 0.0f) {                                   // sortPatches recomputes a negative m_ncc (patch_manager.cpp:411-415)
+                const int e = ss.l_id[i];
+                const int nv = min(st.nimg[e], CAND_MAXV);
+                for (int k = lane; k < nv; k += 32) ws.images[k] = st.images[(size_t)e * st.maxv + k];
+                __syncwarp();
+                const float v = warp_compute_ncc<WS>(p, ws, f4v(st.coord[e]), f4v(st.normal[e]), nv, lane);
+                if (lane == 0) { ss.l_ncc[i] = v; st.scal[e].x = v; }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) swap_sort_desc(ss.l_id, ss.l_ncc, nl);
+        __syncwarp();
+        if (nl > maxp) {
+            for (int i = maxp + lane; i < nl; i += 32) ss.removed[nrem + i - maxp] = ss.l_id[i];
+            stat[SS_TRIMMED] += nl - maxp;
+            nrem += nl - maxp; nl = maxp;
+        }
+        __syncwarp();
+        // ---- sources: (x, y - inc) first, then (x - inc, y); each cell's sorted top-maxp, reference view == img ----
+        int nsrc = 0;
+        for (int side = 0; side < 2; ++side) {
+            const int sx = side == 0 ? x : x - inc, sy = side == 0 ? y - inc : y;
+            if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
+            int* tid = ss.vimg; float* tncc = reinterpret_cast<float*>(ss.vcell);       // scratch, free until postProcess
+            int m = warp_load_cell(sp, st.cell_base[img] + sy * gw + sx, tid, tncc, lane);
+            if (lane == 0) swap_sort_desc(tid, tncc, m);
+            __syncwarp();
+            m = min(m, maxp);
+            for (int i = 0; i < m && nsrc < SRC_MAX; ++i) {
+                const int e = tid[i];
+                if (st.images[(size_t)e * st.maxv] == img) { if (lane == 0) ss.src_id[nsrc] = e; ++nsrc; }
+            }
+            __syncwarp();
+        }
+        // ---- the propagatePatch calls (propagate.cpp:122-218) ----
+        for (int call = 0; call < nsrc; ++call) {
+            const int src = ss.src_id[call];
+            const V4 sX = f4v(st.coord[src]), sN = f4v(st.normal[src]);
+            const int sref = st.images[(size_t)src * st.maxv];
+            const int snv = min(st.nimg[src], CAND_MAXV);
+            // one PMR1 stream per call: (iter, view, dest cell, call ordinal)
+            const uint64_t stream = ((uint64_t)(unsigned)sa.iter << 56) ^ ((uint64_t)(unsigned)img << 40) ^ ((uint64_t)(unsigned)(y * gw + x) << 8) ^ (uint64_t)call;
+            stat[SS_CALLS] += 1;
+            for (int k = 0; k < 2; ++k) {                                                   // MAX_NUM_OF_PROPAG
+                stat[SS_TRIES] += 1;
+                const int np = nl;
+                V3 ic;
+                float wncc = 0.0f;
+                if (np < maxp) {
+                    float jx = sa.jitter[2 * k], jy = sa.jitter[2 * k + 1];
+                    if (sa.jitter_mode == 1) {
+                        uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), 0x4a495454u, (uint32_t)k};
+                        philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
+                        jx = (float)(0.5 * uniform_pm1(ctr[0])); jy = (float)(0.5 * uniform_pm1(ctr[1]));
+                    }
+                    const float cxf = (float)(p.csize * (2 * x + 1) - 1) / 2.0f, cyf = (float)(p.csize * (2 * y + 1) - 1) / 2.0f;
+                    ic = V3{xadd(cxf, xmul(jx, (float)p.csize)), xadd(cyf, xmul(jy, (float)p.csize)), xadd(1.0f, 0.0f)};
+                } else {
+                    const int w = ss.l_id[maxp - 1];
+                    wncc = ss.l_ncc[maxp - 1];
+                    ic = project(vimgc.P, f4v(st.coord[w]));
+                }
+                // ---- generatePatch (propagate.cpp:220-237) ----
+                const ViewConst& vr = p.views[sref];
+                const float depth = dot4(ld4(vr.oaxis), sX);
+                const float b0 = xsub(xmul(depth, ic.x), vr.P[3]), b1 = xsub(xmul(depth, ic.y), vr.P[7]), b2 = xsub(xmul(depth, ic.z), vr.P[11]);
+                V4 X, N = sN;                                                              // Camera::unproject (camera.cpp:329-337)
+                X.x = xadd(xadd(xmul(vr.Minv[0], b0), xmul(vr.Minv[1], b1)), xmul(vr.Minv[2], b2));
+                X.y = xadd(xadd(xmul(vr.Minv[4], b0), xmul(vr.Minv[5], b1)), xmul(vr.Minv[6], b2));
+                X.z = xadd(xadd(xmul(vr.Minv[8], b0), xmul(vr.Minv[9], b1)), xmul(vr.Minv[10], b2));
+                X.w = 1.0f;
+                int nv = 0;                                                                // setGridsImages (patch_manager.cpp:223-239)
+                for (int base = 0; base < snv; base += 32) {
+                    const int i = base + lane;
+                    bool keep = false;
+                    int v = 0;
+                    if (i < snv) {
+                        v = st.images[(size_t)src * st.maxv + i];
+                        const V3 q = project(p.views[v].P, X);
+                        const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
+                        keep = 0 <= ix && ix < p.views[v].gw && 0 <= iy && iy < p.views[v].gh;
+                    }
+                    const unsigned msk = __ballot_sync(0xffffffffu, keep);
+                    if (keep) ws.images[nv + __popc(msk & ((1u << lane) - 1u))] = v;
+                    nv += __popc(msk);
+                }
+                __syncwarp();
+                if (nv == 0) { stat[SS_GEN_NULL] += 1; continue; }
+                float ncc = warp_compute_ncc<WS>(p, ws, X, N, nv, lane);
+                ncc = __shfl_sync(0xffffffffu, ncc, 0);
+                stat[SS_EVALS] += 1;
+                if (np >= maxp && ncc < wncc) { stat[SS_NCC_LOSE] += 1; continue; }
+                // ---- patch optimisation (propagate.cpp:176-193) ----
+                float dscale, ascale;
+                if (warp_pre_process<WS>(cp, ws, X, N, nv, dscale, ascale, lane) == -1) { stat[SS_FAIL0] += 1; continue; }
+                ncc = warp_refine<WS>(cp, ws, X, N, nv, dscale, stream, nullptr, lane);
+                ncc = __shfl_sync(0xffffffffu, ncc, 0);
+                X = V4{__shfl_sync(0xffffffffu, X.x, 0), __shfl_sync(0xffffffffu, X.y, 0), __shfl_sync(0xffffffffu, X.z, 0), __shfl_sync(0xffffffffu, X.w, 0)};
+                N = V4{__shfl_sync(0xffffffffu, N.x, 0), __shfl_sync(0xffffffffu, N.y, 0), __shfl_sync(0xffffffffu, N.z, 0), 0.0f};
+                stat[SS_EVALS] += PMR1_EVALS + 1;
+                int r = warp_post_process<WS>(cp, ws, X, N, nv, gwarp, lane);
+                int nvv = 0;
+                float tmp = 0.0f;
+                if (r == 0) {
+                    for (int i = lane; i < nv; i += 32) {                                  // setGrids (optim.cpp:285)
+                        const V3 q = project(p.views[ws.images[i]].P, X);
+                        ss.cells[i] = pack_cell(cell_of(q.x, p.csize), cell_of(q.y, p.csize));
+                    }
+                    __syncwarp();
+                    tmp = xmul(max_std(0.0f, xsub(ncc, p.ncc_threshold)), (float)nv);      // m_tmp = score2 (optim.cpp:288)
+                    if (p.depth) nvv = warp_set_vimages(sp, ws, X, N, ws.images, nv, ss.vimg, ss.vcell, 0, lane);   // :290-292
+                    if (2 <= p.depth) {                                                    // Optim::check (optim.cpp:300-323)
+                        PGeo me; me.X = X; me.N = N; me.dscale = dscale; me.ref = ws.images[0];
+                        const PatchLists pl{ws.images, ss.cells, nv, ss.vimg, ss.vcell, nvv};
+                        const Overlay ov{cD, ss.l_id, nl, ss.removed, nrem};
+                        const float gain = warp_compute_gain(sp, me, ncc, pl, ov, lane);
+                        tmp = gain;
+                        if (gain < 0.0f) r = -1;
+                        else {
+                            int* nb = sp.nb_scratch + (size_t)gwarp * NB_CAP;
+                            const int nn = warp_find_neighbors(sp, me, pl, 4.0f, 2, ov, nb, lane);
+                            if (6 < nn && warp_filter_quad(sp, me, pl, nb, nn, nullptr, lane)) r = -1;
+                        }
+                    }
+                }
+                if (r == -1) { stat[SS_FAIL1] += 1; continue; }
+                // ---- removePatch(worst) / addPatch(new) (propagate.cpp:195-207); grid updates are staged ----
+                if (np == maxp) {
+                    const int w = ss.l_id[maxp - 1];
+                    if (w >= st.cap) { if (lane == 0) st.state[w] = 0; }                   // staged this step: never reaches the grids
+                    else { if (lane == 0) ss.removed[nrem] = w; ++nrem; }
+                    --nl;
+                    stat[SS_REPLACED] += 1;
+                } else stat[SS_ADDED] += 1;
+                __syncwarp();
+                const int sid = st.cap + task * NEW_MAX + nnew;
+                ++nnew;
+                if (lane == 0) {
+                    st.coord[sid] = v4f(X); st.normal[sid] = v4f(N);
+                    st.scal[sid] = make_float4(ncc, dscale, ascale, tmp);
+                    st.nimg[sid] = nv; st.nvimg[sid] = nvv; st.state[sid] = 1;
+                    st.birth[sid] = 0xffffffffu;
+                }
+                bool inD = false;
+                for (int i = lane; i < nv; i += 32) {
+                    st.images[(size_t)sid * st.maxv + i] = ws.images[i];
+                    st.cells[(size_t)sid * st.maxv + i] = ss.cells[i];
+                    if (ws.images[i] == img && cell_x(ss.cells[i]) == x && cell_y(ss.cells[i]) == y) inD = true;
+                }
+                for (int i = lane; i < nvv; i += 32) {
+                    st.vimages[(size_t)sid * st.maxv + i] = ss.vimg[i];
+                    st.vcells[(size_t)sid * st.maxv + i] = ss.vcell[i];
+                }
+                inD = __any_sync(0xffffffffu, inD);
+                if (inD) {
+                    if (lane == 0) { ss.l_id[nl] = sid; ss.l_ncc[nl] = ncc; }
+                    ++nl;
+                    __syncwarp();
+                    if (lane == 0) swap_sort_desc(ss.l_id, ss.l_ncc, nl);
+                }
+                __syncwarp();
+            }
+        }
+        // ---- hand the step's mutations to k4_apply ----
+        if (lane == 0) sa.task_new[task] = nnew;
+        if (nrem > 0) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(st.counters + SC_REM, nrem);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int i = lane; i < nrem; i += 32) sa.rem_list[base + i] = ss.removed[i];
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < SS_COUNT; ++i) if (stat[i]) atomicAdd(sa.stats + i, stat[i]);
+}
+
+// ---- apply: removals ---------------------------------------------------------------------------------------------------------------
+// PatchManager::removePatch (patch_manager.cpp:303-325): erase the patch from every cell it is registered in.  One warp per patch.
+__device__ __forceinline__ void erase_from_cell(const StoreDev& st, int c, int entry) {
+    const int n = min(st.ccount[c], st.cell_cap);
+    for (int s = 0; s < n; ++s)
+        if (st.cslots[(size_t)c * st.cell_cap + s] == entry) { st.cslots[(size_t)c * st.cell_cap + s] = SLOT_TOMB; }
+}
+
+__global__ void k4_apply_remove(const StoreParams sp, const int* __restrict__ rem_list, int nrem_max) {
+    const StoreDev& st = sp.st;
+    const int nrem = min(st.counters[SC_REM], nrem_max);
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = gwarp; r < nrem; r += nwarps) {
+        const int id = rem_list[r];
+        if (st.state[id] != 1) continue;                   // listed twice (cannot happen within one cell; defensive)
+        __syncwarp();
+        const int ni = st.nimg[id], nv = st.nvimg[id];
+        for (int i = lane; i < ni; i += 32) {
+            const int img = st.images[(size_t)id * st.maxv + i], c = st.cells[(size_t)id * st.maxv + i];
+            erase_from_cell(st, cell_global(sp, img, cell_x(c), cell_y(c)), id);
+        }
+        for (int i = lane; i < nv; i += 32) {
+            const int img = st.vimages[(size_t)id * st.maxv + i], c = st.vcells[(size_t)id * st.maxv + i];
+            erase_from_cell(st, cell_global(sp, img, cell_x(c), cell_y(c)), (int)((unsigned)id | SLOT_V));
+        }
+        __syncwarp();
+        if (lane == 0) st.state[id] = 0;
+    }
+}
+
+// register `entry` in cell c: reuse an erased slot, else append
+__device__ __forceinline__ void insert_into_cell(const StoreDev& st, int c, int entry) {
+    int* slots = st.cslots + (size_t)c * st.cell_cap;
+    const int n = min(st.ccount[c], st.cell_cap);
+    for (int s = 0; s < n; ++s)
+        if (slots[s] == SLOT_TOMB && atomicCAS(slots + s, SLOT_TOMB, entry) == SLOT_TOMB) return;
+    const int s = atomicAdd(st.ccount + c, 1);
+    if (s < st.cell_cap) slots[s] = entry;
+    else { atomicSub(st.ccount + c, 1); atomicAdd(st.counters + SC_OVERFLOW, 1); }
+}
+
+// PatchManager::addPatch (patch_manager.cpp:158-189) for patch `id` whose lists are already in the store
+__device__ __forceinline__ void warp_register_patch(const StoreParams& sp, int id, bool with_v, bool with_depth, int lane) {
+    const StoreDev& st = sp.st;
+    const int ni = st.nimg[id];
+    for (int i = lane; i < ni; i += 32) {
+        const int img = st.images[(size_t)id * st.maxv + i], c = st.cells[(size_t)id * st.maxv + i];
+        insert_into_cell(st, cell_global(sp, img, cell_x(c), cell_y(c)), id);
+    }
+    if (with_v) {
+        const int nv = st.nvimg[id];
+        for (int i = lane; i < nv; i += 32) {
+            const int img = st.vimages[(size_t)id * st.maxv + i], c = st.vcells[(size_t)id * st.maxv + i];
+            insert_into_cell(st, cell_global(sp, img, cell_x(c), cell_y(c)), (int)((unsigned)id | SLOT_V));
+        }
+    }
+    if (with_depth) {
+        const V4 X = f4v(st.coord[id]);
+        for (int v = lane; v < sp.cp.p.nviews; v += 32) update_depth_map(sp, id, X, v);
+    }
+}
+
+// one block: exclusive scan of the staged-and-alive counts -> final ids; bumps SC_N / SC_BIRTH.  final_id[task * NEW_MAX + j] = id or -1
+__global__ void k4_apply_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, int* __restrict__ final_id) {
+    const StoreDev& st = sp.st;
+    __shared__ int s_base;
+    if (threadIdx.x == 0) {
+        int n = st.counters[SC_N];
+        unsigned int b = (unsigned int)st.counters[SC_BIRTH];
+        for (int t = 0; t < ntasks; ++t) {
+            const int k = task_new[t];
+            for (int j = 0; j < k; ++j) {
+                const int sid = st.cap + t * NEW_MAX + j;
+                int fid = -1;
+                if (st.state[sid] == 1) {
+                    if (n < st.cap) { fid = n++; st.birth[sid] = b++; }
+                    else atomicAdd(st.counters + SC_FULL, 1);
+                }
+                final_id[t * NEW_MAX + j] = fid;
+            }
+        }
+        st.counters[SC_N] = n;
+        st.counters[SC_BIRTH] = (int)b;
+        s_base = n;
+    }
+    __syncthreads();
+    (void)s_base;
+}
+
+// copy every staged, surviving patch to its final slot and register it (one warp per staged entry)
+__global__ void k4_apply_add(const StoreParams sp, const int* __restrict__ task_new, int ntasks, const int* __restrict__ final_id) {
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = gwarp; w < ntasks * NEW_MAX; w += nwarps) {
+        const int t = w / NEW_MAX, j = w % NEW_MAX;
+        if (j >= task_new[t]) continue;
+        const int fid = final_id[w];
+        if (fid < 0) continue;
+        const int sid = st.cap + w;
+        if (lane == 0) {
+            st.coord[fid] = st.coord[sid]; st.normal[fid] = st.normal[sid]; st.scal[fid] = st.scal[sid];
+            st.nimg[fid] = st.nimg[sid]; st.nvimg[fid] = st.nvimg[sid]; st.state[fid] = 1; st.birth[fid] = st.birth[sid];
+        }
+        const int ni = st.nimg[sid], nv = st.nvimg[sid];
+        for (int i = lane; i < ni; i += 32) { st.images[(size_t)fid * st.maxv + i] = st.images[(size_t)sid * st.maxv + i]; st.cells[(size_t)fid * st.maxv + i] = st.cells[(size_t)sid * st.maxv + i]; }
+        for (int i = lane; i < nv; i += 32) { st.vimages[(size_t)fid * st.maxv + i] = st.vimages[(size_t)sid * st.maxv + i]; st.vcells[(size_t)fid * st.maxv + i] = st.vcells[(size_t)sid * st.maxv + i]; }
+        __syncwarp();
+        const bool deep = sp.cp.p.depth != 0;                 // addPatch returns before m_vpgrids / depth maps at m_depth == 0 (:173-175)
+        warp_register_patch(sp, fid, deep, deep, lane);
+        __syncwarp();
+    }
+}
+
+}  // namespace pmk

@@ -26,7 +26,7 @@ class PmkError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("nviews", C.c_int), ("level", C.c_int), ("csize", C.c_int), ("wsize", C.c_int),
                 ("min_image_num", C.c_int), ("ncc_threshold", C.c_float), ("max_angle_threshold", C.c_float),
-                ("quad_threshold", C.c_float), ("max_patches", C.c_int)]
+                ("quad_threshold", C.c_float), ("max_patches", C.c_int), ("cell_capacity", C.c_int), ("jitter_mode", C.c_int)]
 
 
 class Thresholds(C.Structure):
@@ -86,16 +86,33 @@ class DeviceBuffer:
             self.ptr = C.c_void_p()
 
 
+class Patches:
+    """numpy-side patch records in the layout of include/pmk.h (scal = ncc, dscale, ascale, tmp)."""
+
+    def __init__(self, n: int, maxv: int):
+        self.n, self.maxv = n, maxv
+        self.coord = np.zeros((n, 4), np.float32)
+        self.normal = np.zeros((n, 4), np.float32)
+        self.scal = np.zeros((n, 4), np.float32)
+        self.images = np.full((n, maxv), -1, np.int32)
+        self.nimages = np.zeros(n, np.int32)
+        self.grids = np.zeros((n, maxv, 2), np.int32)
+        self.vimages = np.full((n, maxv), -1, np.int32)
+        self.nvimages = np.zeros(n, np.int32)
+        self.vgrids = np.zeros((n, maxv, 2), np.int32)
+
+
 class Context:
     """One per GPU.  Mirrors PmMvps::init's effect on the device (pmmvps/pmmvps.cpp:18-68)."""
 
     def __init__(self, nviews: int, device: int = 0, level: int = 1, csize: int = 2, wsize: int = 7, min_image_num: int = 3,
-                 ncc_threshold: float = 0.7, max_patches: int = 0):
+                 ncc_threshold: float = 0.7, max_patches: int = 0, cell_capacity: int = 0, jitter_mode: int = 0):
         L = lib()
         cfg = Config()
         L.pmk_default_config(C.byref(cfg))
         cfg.device, cfg.nviews, cfg.level, cfg.csize, cfg.wsize = device, nviews, level, csize, wsize
         cfg.min_image_num, cfg.ncc_threshold, cfg.max_patches = min_image_num, ncc_threshold, max_patches
+        cfg.cell_capacity, cfg.jitter_mode = cell_capacity, jitter_mode
         self.cfg = cfg
         self.h = C.c_void_p()
         _chk(L.pmk_create(C.byref(cfg), C.byref(self.h)))
@@ -245,6 +262,78 @@ class Context:
         ixy, ok = np.empty((n, 2), np.int32), np.empty(n, np.int32)
         _chk(lib().pmk_probe(self.h, n, _p(view), _p(coord), _p(normal), _p(proj), _p(unit), _p(px), _p(py), _p(ixy), _p(ok)))
         return dict(project=proj, unit=unit, px=px, py=py, cell=ixy, cell_ok=ok)
+
+    # -- device patch store, sweep and filters ----------------------------------------------------------------
+    def store_clear(self):
+        _chk(lib().pmk_store_clear(self.h))
+
+    def store_add(self, coord, normal, scal, images, nimages):
+        """PatchManager::readPatches body: setGrids + addPatch for each record."""
+        coord, normal, images, nimages = self._cv(coord, normal, images, nimages)
+        scal = np.ascontiguousarray(scal, np.float32)
+        _chk(lib().pmk_store_add(self.h, len(coord), _p(coord), _p(normal), _p(scal), _p(images), _p(nimages), images.shape[1]))
+
+    def store_count(self) -> int:
+        n = C.c_int()
+        _chk(lib().pmk_store_count(self.h, C.byref(n)))
+        return n.value
+
+    def store_get(self, maxv: Optional[int] = None) -> "Patches":
+        n = self.store_count()
+        out = Patches(n, maxv or self.nviews)
+        got = C.c_int()
+        _chk(lib().pmk_store_get(self.h, n, out.maxv, _p(out.coord), _p(out.normal), _p(out.scal), _p(out.images), _p(out.nimages), _p(out.grids),
+                                 _p(out.vimages), _p(out.nvimages), _p(out.vgrids), C.byref(got)))
+        assert got.value == n
+        return out
+
+    def store_depth_map(self, view: int) -> np.ndarray:
+        gw, gh = self.grid_dims(view)
+        ids = np.zeros((gh, gw), np.int32)
+        _chk(lib().pmk_store_depth_map(self.h, view, _p(ids)))
+        return ids
+
+    def store_cell_counts(self, view: int, which: int = 0) -> np.ndarray:
+        gw, gh = self.grid_dims(view)
+        out = np.zeros((gh, gw), np.int32)
+        _chk(lib().pmk_store_cell_counts(self.h, view, which, _p(out)))
+        return out
+
+    def store_colors(self, n: int) -> np.ndarray:
+        out = np.zeros((n, 3), np.uint8)
+        _chk(lib().pmk_store_colors(self.h, n, _p(out)))
+        return out
+
+    SWEEP_STATS = ("calls", "tries", "gen_null", "ncc_lose", "fail0", "fail1", "added", "replaced", "trimmed", "evals")
+
+    def propagate(self, it: int, seed: int) -> dict:
+        """Propagate::run(iter)."""
+        st = np.zeros(16, np.uint64)
+        _chk(lib().pmk_propagate(self.h, it, C.c_uint64(seed), _p(st)))
+        return dict(zip(self.SWEEP_STATS, (int(v) for v in st)))
+
+    def propagate_diagonals(self, it: int, image: int, first: int, count: int, seed: int) -> dict:
+        st = np.zeros(16, np.uint64)
+        _chk(lib().pmk_propagate_diagonals(self.h, it, image, first, count, C.c_uint64(seed), _p(st)))
+        return dict(zip(self.SWEEP_STATS, (int(v) for v in st)))
+
+    def filter_rebuild(self, additive: int) -> int:
+        n = C.c_int()
+        _chk(lib().pmk_filter_rebuild(self.h, additive, C.byref(n)))
+        return n.value
+
+    def filter_stage(self, stage: int, n: int):
+        """-> (f_out, i_out, i_out2, killed); see include/pmk.h for what each stage reports."""
+        f, i1, i2 = np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        k = C.c_int()
+        _chk(lib().pmk_filter_stage(self.h, stage, n, _p(f), _p(i1), _p(i2), C.byref(k)))
+        return f, i1, i2, k.value
+
+    def filter(self):
+        """Filter::run -> [before, removed by outside / exact / neighbor / small groups, after]."""
+        c = np.zeros(6, np.int32)
+        _chk(lib().pmk_filter(self.h, _p(c)))
+        return [int(v) for v in c]
 
     # -- plumbing ------------------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> DeviceBuffer:

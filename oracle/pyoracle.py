@@ -285,6 +285,65 @@ class RefLib:
         self.L.pmref_is_neighbor(len(a), _p(a), _p(b), C.c_float(thr), _p(out))
         return out
 
+    # -- schedule PMS1 through the reference's propagatePatch; Filter::run stage by stage -----------------
+    def propagate_dest(self, image: int, x: int, y: int, inc: int, it: int) -> int:
+        return int(self.L.pmref_propagate_dest(image, x, y, inc, it))
+
+    def propagate_diag(self, image: int, diag: int, inc: int, it: int) -> int:
+        return int(self.L.pmref_propagate_diag(image, diag, inc, it))
+
+    def refine_seed(self, seed: int):
+        self.L.pmref_refine_seed(C.c_ulonglong(seed))
+
+    def cell_ids(self, view: int, index: int, which: int = 0, cap: int = 256) -> np.ndarray:
+        ids = np.zeros(cap, np.int32)
+        n = int(self.L.pmref_cell_ids(view, index, which, _p(ids), cap))
+        return ids[:min(n, cap)]
+
+    def filter_rebuild(self, additive: int):
+        self.L.pmref_filter_rebuild(additive)
+
+    def stage_begin(self) -> int:
+        self._nstage = int(self.L.pmref_stage_begin())
+        return self._nstage
+
+    def filter_stage(self, stage: int):
+        self.L.pmref_filter_stage(stage)
+
+    def stage_alive(self) -> np.ndarray:
+        out = np.zeros(self._nstage, np.int32)
+        self.L.pmref_stage_alive(_p(out))
+        return out
+
+    def stage_patches(self, maxv=None) -> PatchBatch:
+        out = PatchBatch(self._nstage, maxv or self.nviews)
+        io = out.io()
+        self.L.pmref_stage_patches(C.byref(io))
+        return out
+
+    def stage_gains(self) -> np.ndarray:
+        out = np.zeros(self._nstage, np.float32)
+        self.L.pmref_stage_gains(_p(out))
+        return out
+
+    def stage_rejects(self) -> np.ndarray:
+        out = np.zeros(self._nstage, np.int32)
+        self.L.pmref_stage_rejects(_p(out))
+        return out
+
+    def stage_neighbors(self):
+        cnt, quad = np.zeros(self._nstage, np.int32), np.zeros(self._nstage, np.int32)
+        self.L.pmref_stage_neighbors(_p(cnt), _p(quad))
+        return cnt, quad
+
+    def check(self, coord, normal, scal, views):
+        coord, normal, scal, views = _f32(coord), _f32(normal), _f32(scal), _i32(views)
+        out = PatchBatch(1, self.nviews)
+        io = out.io()
+        gain = C.c_float()
+        r = int(self.L.pmref_check(_p(coord), _p(normal), _p(scal), _p(views), len(views), C.byref(gain), C.byref(io)))
+        return r, float(gain.value), out
+
     def run(self):
         alive = C.c_int()
         secs = float(self.L.pmref_run(C.byref(alive)))

@@ -467,4 +467,111 @@ double pmref_run(int* alive) {
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// ---- schedule PMS1 driven through the reference's own propagatePatch ---------------------------------------------------------
+// One dest cell (x, y) of `image`: trim it like propagatePatch / propagatePmImage do (sortPatches, removePatch beyond
+// MAX_NUM_OF_PATCHES), then replay every Propagate::propagatePatch call that the raster sweep would aim at it: the sorted
+// top-MAX patches of (x, y - inc), then of (x - inc, y), whose reference image is `image` (propagate.cpp:87-108).  The PMR1
+// stream of a call is (iter << 56) ^ (image << 40) ^ (cell << 8) ^ call, the same function the CUDA sweep uses.
+int pmref_propagate_dest(int image, int x, int y, int inc, int iter) {
+    PatchManager& pm = g_pm->m_patchManager;
+    const int gw = pm.m_gwidths[image], gh = pm.m_gheights[image];
+    const int maxp = g_pm->m_propagate.MAX_NUM_OF_PATCHES;
+    const int index = y * gw + x;
+    {
+        std::vector<Ppatch> cur = pm.m_pgrids[image][index];          // copy: removePatch edits the cell
+        pm.sortPatches(cur, 0);
+        for (int i = (int)cur.size() - 1; i >= maxp; --i) pm.removePatch(cur[i]);
+    }
+    std::vector<Ppatch> sources;
+    for (int side = 0; side < 2; ++side) {
+        const int sx = side == 0 ? x : x - inc, sy = side == 0 ? y - inc : y;
+        if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
+        std::vector<Ppatch> src = pm.m_pgrids[image][sy * gw + sx];
+        pm.sortPatches(src, 0);
+        if ((int)src.size() > maxp) src.resize(maxp);
+        for (size_t n = 0; n < src.size(); ++n) if (src[n]->m_images[0] == image) sources.push_back(src[n]);
+    }
+    for (size_t call = 0; call < sources.size(); ++call) {
+        pmr1::state().stream = ((unsigned long long)(unsigned)iter << 56) ^ ((unsigned long long)(unsigned)image << 40) ^
+                               ((unsigned long long)(unsigned)index << 8) ^ (unsigned long long)call;
+        g_pm->m_propagate.propagatePatch(sources[call], image, index);
+    }
+    return (int)sources.size();
+}
+
+// one wavefront step: every dest cell of anti-diagonal `diag` of `image`
+int pmref_propagate_diag(int image, int diag, int inc, int iter) {
+    PatchManager& pm = g_pm->m_patchManager;
+    const int gw = pm.m_gwidths[image], gh = pm.m_gheights[image];
+    int calls = 0;
+    for (int x = std::max(0, diag - gh + 1); x <= std::min(gw - 1, diag); ++x) calls += pmref_propagate_dest(image, x, diag - x, inc, iter);
+    return calls;
+}
+
+// ids (m_ppatches indexes after the last pmref_collect) of the m_pgrids / m_vpgrids entries of one cell
+int pmref_cell_ids(int view, int index, int which, int* ids, int cap) {
+    const std::vector<Ppatch>& g = which ? g_pm->m_patchManager.m_vpgrids[view][index] : g_pm->m_patchManager.m_pgrids[view][index];
+    for (size_t i = 0; i < g.size() && (int)i < cap; ++i) ids[i] = g[i]->m_id;
+    return (int)g.size();
+}
+
+// ---- Filter::run, stage by stage (the stage functions are protected in filter.hpp:36-52; see the access note above) --------------
+static std::vector<Ppatch> g_prev;
+
+// Filter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:628-655)
+void pmref_filter_rebuild(int additive) { g_pm->m_filter.setDepthMapsVGridsVPGridsAddPatchV(additive); }
+
+// collectPatches(0) and remember m_ppatches so per-patch results can be reported in this order after a stage
+int pmref_stage_begin(void) {
+    g_pm->m_patchManager.collectPatches(0);
+    g_prev = g_pm->m_patchManager.m_ppatches;
+    return (int)g_prev.size();
+}
+
+// stage: 1 filterOutside (:51-106), 2 filterExact (:148-263), 3 filterNeighbor(1) (:265-336), 4 filterSmallGroups (:432-525)
+void pmref_filter_stage(int stage) {
+    switch (stage) {
+        case 1: g_pm->m_filter.filterOutside(); break;
+        case 2: g_pm->m_filter.filterExact(); break;
+        case 3: g_pm->m_filter.filterNeighbor(1); break;
+        case 4: g_pm->m_filter.filterSmallGroups(); break;
+    }
+}
+
+// alive[i] = 1 when the i-th patch of the last pmref_stage_begin is still reachable from the grids
+void pmref_stage_alive(int* alive) {
+    g_pm->m_patchManager.collectPatches(0);
+    std::map<const Patch*, int> now;
+    const std::vector<Ppatch>& pp = g_pm->m_patchManager.m_ppatches;
+    for (size_t i = 0; i < pp.size(); ++i) now[pp[i].get()] = 1;
+    for (size_t i = 0; i < g_prev.size(); ++i) alive[i] = now.count(g_prev[i].get()) ? 1 : 0;
+}
+
+void pmref_stage_patches(PatchIO* out) { for (size_t i = 0; i < g_prev.size(); ++i) patch_out(*g_prev[i], *out, (int)i); }
+void pmref_stage_gains(float* g) { for (size_t i = 0; i < g_pm->m_filter.m_gains.size(); ++i) g[i] = g_pm->m_filter.m_gains[i]; }
+void pmref_stage_rejects(int* r) { for (size_t i = 0; i < g_pm->m_filter.m_rejects.size(); ++i) r[i] = g_pm->m_filter.m_rejects[i]; }
+
+// PatchManager::findNeighbors(patch, 4, 2, 1) sizes and Filter::filterQuad decisions for the remembered patches
+void pmref_stage_neighbors(int* count, int* quad) {
+    for (size_t i = 0; i < g_prev.size(); ++i) {
+        std::vector<Ppatch> nb;
+        g_pm->m_patchManager.findNeighbors(*g_prev[i], nb, 4, 2, 1);
+        count[i] = (int)nb.size();
+        quad[i] = nb.size() >= 6 ? g_pm->m_filter.filterQuad(*g_prev[i], nb) : -1;
+    }
+}
+
+// PatchManager::setVImagesVGrids / Optim::check on a free-standing patch record (optim.cpp:290-323)
+int pmref_check(const float* coord4, const float* normal4, const float* scal4, const int* views, int nviews, float* gain_out, PatchIO* out) {
+    Patch patch;
+    fill_patch(patch, coord4, normal4, views, nviews);
+    patch.m_ncc = scal4[0]; patch.m_dscale = scal4[1]; patch.m_ascale = scal4[2];
+    g_pm->m_patchManager.setGrids(patch);
+    g_pm->m_patchManager.setVImagesVGrids(patch);
+    const int r = g_pm->m_optim.check(patch);
+    if (gain_out) *gain_out = patch.m_tmp;
+    if (out) patch_out(patch, *out, 0);
+    return r;
+}
+
 }  // extern "C"
