@@ -52,10 +52,12 @@ typedef struct pmk_config {
     float ncc_threshold;        /* Option::m_nccThreshold                                          */
     float max_angle_threshold;  /* Option::m_maxAngleThreshold, radians                            */
     float quad_threshold;       /* Option::m_quadThreshold                                         */
-    int max_patches;            /* capacity of the device patch store; 0 = 2 per cell of all views */
+    int max_patches;            /* capacity of the device patch store; 0 = 4 per cell of all views */
     int cell_capacity;          /* slots per grid cell (m_pgrids + m_vpgrids entries); 0 = 96, at most 128 */
     int jitter_mode;            /* 0: the reference's pixel jitter (propagate.cpp:139-141 re-seeds its engine on every
                                    call, so it is the same four draws each time); 1: Philox4x32 per (iter, view, cell, call, try) */
+    int sweep_group;            /* views whose wavefronts advance together in Propagate::run: 1 = one view after the other like
+                                   the reference (propagate.cpp:73); g > 1 = g views per pass (more parallel work per step) */
 } pmk_config;
 
 /* Thresholds held by PmMvps (pmmvps/pmmvps.hpp:36-87); read back for parity checks. */
@@ -89,6 +91,7 @@ int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int
 
 int pmk_get_thresholds(pmk_ctx* ctx, pmk_thresholds* out);
 int pmk_set_depth(pmk_ctx* ctx, int depth);                 /* PmMvps::m_depth (pmmvps.hpp:61)      */
+int pmk_set_ncc_thresholds(pmk_ctx* ctx, float ncc_threshold, float ncc_threshold_before); /* PmMvps::m_nccThreshold / m_nccThresholdBefore (public, pmmvps.hpp:36,81) */
 int pmk_update_threshold(pmk_ctx* ctx);                     /* PmMvps::updateThreshold + ++m_depth (pmmvps.cpp:70-74,106) */
 int pmk_get_camera(pmk_ctx* ctx, int view, int level, pmk_camera* out);
 int pmk_get_level_dims(pmk_ctx* ctx, int view, int level, int* width, int* height); /* Image::getWidth/getHeight */

@@ -61,5 +61,25 @@ def build(force: bool = False, verbose: bool = False, fast: bool = False) -> str
     return OUT
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_EXE = os.path.join(HOST_DIR, "pmmvps_b200")
+
+
+def build_host(force: bool = False) -> str:
+    """g++ build of the host-side mirror of the reference's classes + driver (mvskit_b200/host/), linked against libpmk.so."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("pmmvps.cpp", "main.cpp")]
+    deps = srcs + [os.path.join(HOST_DIR, "pmmvps.hpp"), os.path.join(HERE, "..", "include", "pmk.h")]
+    if not force and os.path.exists(HOST_EXE) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_EXE) for d in deps):
+        return HOST_EXE
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-std=c++14", "-O2", "-ffp-contract=off", "-Wall", "-o", HOST_EXE] + srcs + ["-L" + HERE, "-lpmk", "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building the host driver")
+    return HOST_EXE
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv, fast="--fast" in sys.argv))
+    print(build_host(force=True))

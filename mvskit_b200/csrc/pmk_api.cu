@@ -292,6 +292,7 @@ void pmk_default_config(pmk_config* c) {
     c->max_patches = 0;
     c->cell_capacity = 0;
     c->jitter_mode = 0;
+    c->sweep_group = 1;
 }
 
 int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
@@ -446,6 +447,14 @@ int pmk_get_thresholds(pmk_ctx* ctx, pmk_thresholds* t) {
 int pmk_set_depth(pmk_ctx* ctx, int depth) {
     if (!ctx) return fail(PMK_ERR_ARG, "pmk_set_depth: null ctx");
     ctx->depth = depth;
+    refresh_params(ctx);
+    return PMK_OK;
+}
+
+int pmk_set_ncc_thresholds(pmk_ctx* ctx, float ncc, float before) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_set_ncc_thresholds: null ctx");
+    ctx->ncc_threshold = ncc;
+    ctx->ncc_threshold_before = before;
     refresh_params(ctx);
     return PMK_OK;
 }
@@ -969,12 +978,13 @@ int pmk_store_colors(pmk_ctx* ctx, int nmax, uint8_t* rgb) {
     int rc = store_init(ctx);
     if (rc) return rc;
     pmk_store* s = ctx->store;
-    if (!s->canonical) return fail(PMK_ERR_STATE, "pmk_store_colors: call pmk_filter_rebuild first (ids must be in collect order)");
     StoreParams sp;
     if ((rc = store_params(ctx, sp, 0))) return rc;
-    const int n = std::min(s->n, nmax);
+    int nalive = 0;
+    if ((rc = store_order(ctx, sp, &nalive))) return rc;
+    const int n = std::min(nalive, nmax);
     if (n <= 0) return PMK_OK;
-    k_patch_colors<<<(n + 127) / 128, 128, 0, ctx->stream>>>(sp, n, (unsigned char*)s->gather_tmp);
+    k_patch_colors<<<(n + 127) / 128, 128, 0, ctx->stream>>>(sp, n, s->vals2, (unsigned char*)s->gather_tmp);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(rgb, s->gather_tmp, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream));
@@ -996,7 +1006,7 @@ int pmk_propagate_diagonals(pmk_ctx* ctx, int iter, int image, int diag_first, i
     int rc = store_init(ctx);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(ctx->store->stats, 0, SS_COUNT * sizeof(uint64_t), ctx->stream));
-    if ((rc = sweep_image(ctx, iter, image, diag_first, diag_count, seed))) return rc;
+    if ((rc = sweep_views(ctx, iter, image, 1, diag_first, diag_count, seed))) return rc;
     if ((rc = read_stats(ctx, stats16))) return rc;
     return store_check_overflow(ctx);
 }
@@ -1007,9 +1017,9 @@ int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16) {
     int rc = store_init(ctx);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(ctx->store->stats, 0, SS_COUNT * sizeof(uint64_t), ctx->stream));
-    for (int image = 0; image < ctx->cfg.nviews; ++image) {                               // propagate.cpp:73
-        const ViewConst& vc = ctx->h_views[image];
-        if ((rc = sweep_image(ctx, iter, image, 0, vc.gw + vc.gh - 1, seed))) return rc;
+    const int group = ctx->store->group;
+    for (int image = 0; image < ctx->cfg.nviews; image += group) {                        // propagate.cpp:73, `group` views at a time
+        if ((rc = sweep_views(ctx, iter, image, std::min(group, ctx->cfg.nviews - image), 0, 1 << 30, seed))) return rc;
         if ((rc = store_check_overflow(ctx))) return rc;
     }
     return read_stats(ctx, stats16);

@@ -243,11 +243,12 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k9_group_edges(const StorePar
 }
 
 // PatchManager::writePly colour (patch_manager.cpp:566-581): mean over m_images of Image::getColor at the projection, rounded
-__global__ void k_patch_colors(const StoreParams sp, int n, unsigned char* __restrict__ rgb) {
+__global__ void k_patch_colors(const StoreParams sp, int n, const int* __restrict__ perm, unsigned char* __restrict__ rgb) {
     const StoreDev& st = sp.st;
     const Params& p = sp.cp.p;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int q = perm[k];
     const V4 X = f4v(st.coord[q]);
     float r = 0.f, g = 0.f, b = 0.f;
     const int ni = st.nimg[q];
@@ -260,9 +261,9 @@ __global__ void k_patch_colors(const StoreParams sp, int n, unsigned char* __res
         r += cr; g += cg; b += cb;
     }
     const float inv = ni > 0 ? 1.0f / (float)ni : 0.0f;
-    rgb[3 * q] = (unsigned char)min(255, (int)floorf(r * inv + 0.5f));
-    rgb[3 * q + 1] = (unsigned char)min(255, (int)floorf(g * inv + 0.5f));
-    rgb[3 * q + 2] = (unsigned char)min(255, (int)floorf(b * inv + 0.5f));
+    rgb[3 * k] = (unsigned char)min(255, (int)floorf(r * inv + 0.5f));
+    rgb[3 * k + 1] = (unsigned char)min(255, (int)floorf(g * inv + 0.5f));
+    rgb[3 * k + 2] = (unsigned char)min(255, (int)floorf(b * inv + 0.5f));
 }
 
 // PatchManager::readPatches body (patch_manager.cpp:450-462) for patches already copied to slots [first, first + n):

@@ -14,6 +14,8 @@ struct pmk_store {
     pmk::StoreDev d;                    // device pointers
     int n = 0;                          // patches allocated (host mirror of SC_N)
     int max_tasks = 0;
+    int rank = 0, nranks = 1;             // multi-GPU: this context sweeps band `rank` of `nranks` of every view's rows
+    int group = 1;                        // views swept concurrently (pmk_config.sweep_group)
     int* cell_base_d = nullptr;
     std::vector<int> cell_base;         // host copy
     // scratch
@@ -79,8 +81,18 @@ int store_init(pmk_ctx* ctx) {
     d.maxv = nv;
     d.cell_cap = ctx->cfg.cell_capacity > 0 ? ctx->cfg.cell_capacity : 96;
     if (d.cell_cap > LIST_MAX) return fail(PMK_ERR_ARG, "pmk: cell_capacity exceeds 128");
-    d.cap = ctx->cfg.max_patches > 0 ? ctx->cfg.max_patches : 2 * d.total_cells;
-    s->max_tasks = max_diag;
+    if (ctx->cfg.max_patches > 0) d.cap = ctx->cfg.max_patches;
+    else {
+        // one iteration creates up to ~1.5 patches per cell before Filter::run compacts the store; removed patches keep their
+        // slot until then.  Default: 4 per cell of all views, at most half of the free device memory.
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_patch = 3 * 16 + 4 * 4 + 4 * (size_t)nv * 4 + 48;
+        const size_t by_mem = free_b / 2 / per_patch;
+        d.cap = (int)std::min<size_t>(std::min<size_t>((size_t)4 * d.total_cells, by_mem), (size_t)0x3fffffff);
+    }
+    s->group = ctx->cfg.sweep_group <= 0 ? 1 : std::min(std::min(ctx->cfg.sweep_group, nv), (int)GROUP_MAX);
+    s->max_tasks = max_diag * s->group;
     d.stage_cap = s->max_tasks * NEW_MAX;
     const size_t tot = (size_t)d.cap + d.stage_cap;
     if ((rc = dalloc(ctx, &d.coord, tot)) || (rc = dalloc(ctx, &d.normal, tot)) || (rc = dalloc(ctx, &d.scal, tot)) ||
@@ -350,26 +362,42 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     return PMK_OK;
 }
 
-// wavefront steps [diag_first, diag_first + diag_count) of Propagate::propagatePmImage for one view
-int sweep_image(pmk_ctx* ctx, int iter, int image, int diag_first, int diag_count, uint64_t seed) {
+// Wavefront steps [step_first, step_first + step_count) of Propagate::propagatePmImage for views [img_first, img_first + nimg):
+// step k carries anti-diagonal k (from the far corner on odd iterations, propagate.cpp:80-86) of every view of the group.
+// (rank, nranks): this GPU only takes the dest cells whose row lies in its band of each view's grid (multi-GPU partition).
+int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first, int step_count, uint64_t seed) {
     pmk_store* s = ctx->store;
     StoreParams sp;
     int rc = store_params(ctx, sp, seed);
     if (rc) return rc;
-    const ViewConst& vc = ctx->h_views[image];
-    const int gw = vc.gw, gh = vc.gh, ndiag = gw + gh - 1;
-    const int inc = (iter % 2 == 1) ? -1 : 1;                         // propagate.cpp:80-86
+    if (nimg > GROUP_MAX) return fail(PMK_ERR_ARG, "pmk: sweep group too large");
+    const int inc = (iter % 2 == 1) ? -1 : 1;
     SweepArgs sa;
-    sa.img = image; sa.inc = inc; sa.iter = iter;
+    std::memset(&sa, 0, sizeof(sa));
+    sa.inc = inc; sa.iter = iter;
     sa.jitter_mode = ctx->cfg.jitter_mode;
     for (int i = 0; i < 4; ++i) sa.jitter[i] = s->jitter[i];
     sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats;
-    for (int k = diag_first; k < diag_first + diag_count && k < ndiag; ++k) {
-        const int d = inc > 0 ? k : ndiag - 1 - k;
-        sa.diag = d;
-        sa.xlo = std::max(0, d - gh + 1);
-        sa.ntasks = std::min(gw - 1, d) - sa.xlo + 1;
+    int max_steps = 0;
+    for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
+    for (int k = step_first; k < step_first + step_count && k < max_steps; ++k) {
+        sa.ngroup = 0; sa.ntasks = 0;
+        for (int g = 0; g < nimg; ++g) {
+            const ViewConst& vc = ctx->h_views[img_first + g];
+            const int gw = vc.gw, gh = vc.gh, ndiag = gw + gh - 1;
+            if (k >= ndiag) continue;
+            const int d = inc > 0 ? k : ndiag - 1 - k;
+            // rows of this rank's band
+            const int ylo = (int)((long long)gh * s->rank / s->nranks), yhi = (int)((long long)gh * (s->rank + 1) / s->nranks);
+            const int xlo = std::max(std::max(0, d - gh + 1), d - yhi + 1), xhi = std::min(std::min(gw - 1, d), d - ylo);
+            if (xhi < xlo) continue;
+            const int m = sa.ngroup++;
+            sa.g_img[m] = img_first + g; sa.g_diag[m] = d; sa.g_xlo[m] = xlo; sa.g_off[m] = sa.ntasks;
+            sa.ntasks += xhi - xlo + 1;
+        }
+        sa.g_off[sa.ngroup] = sa.ntasks;
         if (sa.ntasks <= 0) continue;
+        if (sa.ntasks > s->max_tasks) return fail(PMK_ERR_CAPACITY, "pmk: sweep step exceeds the staging capacity");
         WS_DISPATCH(ctx->cfg.wsize, { if ((rc = launch_sweep<WS>(ctx, sp, sa))) return rc; });
     }
     s->canonical = false;

@@ -20,8 +20,13 @@ namespace pmk {
 
 enum SweepStat { SS_CALLS = 0, SS_TRIES, SS_GEN_NULL, SS_NCC_LOSE, SS_FAIL0, SS_FAIL1, SS_ADDED, SS_REPLACED, SS_TRIMMED, SS_EVALS, SS_COUNT = 16 };
 
+constexpr int GROUP_MAX = 128;         // views whose wavefronts one step can carry
+
 struct SweepArgs {
-    int img, inc, diag, ntasks, xlo;       // dest cells (xlo + t, diag - xlo - t), t in [0, ntasks)
+    // dest cells of this step: for group member g, view g_img[g], cells (g_xlo[g] + t, g_diag[g] - g_xlo[g] - t),
+    // t in [0, g_off[g + 1] - g_off[g]); task index = g_off[g] + t
+    int ngroup, ntasks, inc;
+    int g_img[GROUP_MAX], g_diag[GROUP_MAX], g_xlo[GROUP_MAX], g_off[GROUP_MAX + 1];
     int iter;                              // Propagate::run(iter)
     int jitter_mode;                       // 0: the reference's four constant draws (propagate.cpp:139-141), 1: Philox per try
     float jitter[4];
@@ -108,16 +113,19 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k4_sweep(const StoreParams sp
     const StoreDev& st = sp.st;
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
-    const int img = sa.img, inc = sa.inc;
-    const ViewConst& vimgc = p.views[img];
-    const int gw = vimgc.gw, gh = vimgc.gh;
+    const int inc = sa.inc;
     const int maxp = sp.max_patches_cell;
     unsigned long long stat[SS_COUNT];
 #pragma unroll
     for (int i = 0; i < SS_COUNT; ++i) stat[i] = 0;
 
     for (int task = gwarp; task < sa.ntasks; task += gridDim.x * CAND_WARPS) {
-        const int x = sa.xlo + task, y = sa.diag - x;
+        int g = 0;
+        while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+        const int img = sa.g_img[g];
+        const ViewConst& vimgc = p.views[img];
+        const int gw = vimgc.gw, gh = vimgc.gh;
+        const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
         const int cD = st.cell_base[img] + y * gw + x;
         int nrem = 0, nnew = 0;
         // ---- D's list: sortPatches + trim (propagate.cpp:123-134) ----

@@ -1,0 +1,45 @@
+// mvskit_b200/host/main.cpp -- the reference's driver (test/test.cpp:155-161) on the B200 path:
+//     pmmvps_b200 <prefix/> [option-file] [--device N] [--group G] [--filter-only ITER]
+// `--filter-only ITER` is test/test_filter.cpp: m_depth = 1, readPatches(ITER), Filter::run.
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "pmmvps.hpp"
+
+int main(int argc, char* argv[]) {
+    if (argc < 2) {
+        std::cerr << "usage: " << argv[0] << " <prefix/> [option] [--device N] [--group G] [--filter-only ITER]" << std::endl;
+        return 2;
+    }
+    std::string prefix = argv[1], optname = "option";
+    int device = 0, group = 1, filter_only = -1;
+    for (int i = 2; i < argc; ++i) {
+        if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--group") && i + 1 < argc) group = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--filter-only") && i + 1 < argc) filter_only = atoi(argv[++i]);
+        else optname = argv[i];
+    }
+    if (prefix.empty() || prefix[prefix.size() - 1] != '/') prefix += "/";
+
+    Option option;
+    option.init(prefix, optname);
+
+    PmMvps pmmvps;
+    pmmvps.m_device = device;
+    pmmvps.m_sweepGroup = group;
+    pmmvps.init(option);
+
+    if (filter_only >= 0) {
+        pmmvps.m_depth = 1;
+        pmmvps.m_patchManager.readPatches(filter_only);
+        pmmvps.m_filter.run();
+        pmmvps.m_patchManager.writePatches(prefix + "ply/filtered", true, true, false);
+    } else {
+        pmmvps.run();
+        pmmvps.m_patchManager.writePatches(prefix + "ply/final", false, true, false);
+    }
+    pmmvps.m_patchManager.collectPatches();
+    std::cout << "patches " << pmmvps.m_patchManager.m_ppatches.size() << std::endl;
+    return 0;
+}

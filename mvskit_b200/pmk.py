@@ -26,7 +26,7 @@ class PmkError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("nviews", C.c_int), ("level", C.c_int), ("csize", C.c_int), ("wsize", C.c_int),
                 ("min_image_num", C.c_int), ("ncc_threshold", C.c_float), ("max_angle_threshold", C.c_float),
-                ("quad_threshold", C.c_float), ("max_patches", C.c_int), ("cell_capacity", C.c_int), ("jitter_mode", C.c_int)]
+                ("quad_threshold", C.c_float), ("max_patches", C.c_int), ("cell_capacity", C.c_int), ("jitter_mode", C.c_int), ("sweep_group", C.c_int)]
 
 
 class Thresholds(C.Structure):
@@ -106,13 +106,13 @@ class Context:
     """One per GPU.  Mirrors PmMvps::init's effect on the device (pmmvps/pmmvps.cpp:18-68)."""
 
     def __init__(self, nviews: int, device: int = 0, level: int = 1, csize: int = 2, wsize: int = 7, min_image_num: int = 3,
-                 ncc_threshold: float = 0.7, max_patches: int = 0, cell_capacity: int = 0, jitter_mode: int = 0):
+                 ncc_threshold: float = 0.7, max_patches: int = 0, cell_capacity: int = 0, jitter_mode: int = 0, sweep_group: int = 1):
         L = lib()
         cfg = Config()
         L.pmk_default_config(C.byref(cfg))
         cfg.device, cfg.nviews, cfg.level, cfg.csize, cfg.wsize = device, nviews, level, csize, wsize
         cfg.min_image_num, cfg.ncc_threshold, cfg.max_patches = min_image_num, ncc_threshold, max_patches
-        cfg.cell_capacity, cfg.jitter_mode = cell_capacity, jitter_mode
+        cfg.cell_capacity, cfg.jitter_mode, cfg.sweep_group = cell_capacity, jitter_mode, sweep_group
         self.cfg = cfg
         self.h = C.c_void_p()
         _chk(L.pmk_create(C.byref(cfg), C.byref(self.h)))

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Run init -> (propagate, filter, updateThreshold) x ITER on one GPU for a synthetic config and print per-stage numbers.
+   python tools/run_pipeline.py --config 1 --scale 0.5 --iters 3 --group 5"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mvskit_b200 import pmk, synth  # noqa: E402
+
+
+def seeds_arrays(scene):
+    recs = scene.seeds()
+    n, V = len(recs), scene.nviews
+    coord, normal, scal = np.ones((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+    images, nimg = np.zeros((n, V), np.int32), np.zeros(n, np.int32)
+    for i, (X, N, ds, ids) in enumerate(recs):
+        coord[i, :3], normal[i, :3] = X, N
+        scal[i] = (1.0, ds, 0.0, 0.0)
+        images[i, :len(ids)] = ids
+        nimg[i] = len(ids)
+    return coord, normal, scal, images, nimg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=1)
+    ap.add_argument("--scale", type=float, default=0.5)
+    ap.add_argument("--nviews", type=int, default=None)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--group", type=int, default=1)
+    ap.add_argument("--cell-capacity", type=int, default=0)
+    a = ap.parse_args()
+    scene = synth.make_scene(a.config, scale=a.scale, nviews=a.nviews).render()
+    ctx = pmk.Context(nviews=scene.nviews, sweep_group=a.group, cell_capacity=a.cell_capacity)
+    ctx.set_scene(scene.P, scene.images)
+    coord, normal, scal, images, nimg = seeds_arrays(scene)
+    ctx.set_depth(0); ctx.store_clear(); ctx.store_add(coord, normal, scal, images, nimg); ctx.set_depth(1)
+    print("seeds", len(coord), "views", scene.nviews, "grid", ctx.grid_dims(0), "group", a.group, flush=True)
+    T0 = time.time()
+    for it in range(a.iters):
+        t = time.time(); st = ctx.propagate(it, 0x5EED0001); ctx.sync(); t1 = time.time() - t
+        nprop = ctx.store_count()
+        t = time.time(); c = ctx.filter(); ctx.sync(); t2 = time.time() - t
+        ctx.update_threshold()
+        g = ctx.store_get()
+        q = None
+        if a.config == 1:
+            q = np.quantile(np.abs(g.coord[:, 2]) / scene.scene_scale, [0.5, 0.9, 0.99])
+        elif a.config == 2:
+            r = np.linalg.norm(g.coord[:, :3], axis=1)
+            on_sphere = np.abs(r - 1.0) < 0.05
+            q = (float(on_sphere.mean()), np.quantile(np.abs(r[on_sphere] - 1.0) / scene.scene_scale, [0.5, 0.9]))
+        print(f"iter {it}: propagate {t1:.2f}s -> {nprop} patches, {st['evals'] / t1 / 1e6:.1f} M evals/s, stats {st}; filter {t2:.3f}s {c}; "
+              f"quality {q}; launches {ctx.launch_count()}", flush=True)
+    dt = time.time() - T0
+    print(f"total {dt:.2f} s; {g.n} patches; {g.n / dt:.0f} patches/s")
+
+
+if __name__ == "__main__":
+    main()
