@@ -200,6 +200,40 @@ def cpu_reference_evals_per_sec(scene, config, scale, hyp, cores: int, sample: i
 
 
 # ------------------------------------------------------------------------------------------------------
+# second BASELINE metric: end-to-end patches/sec of init -> (propagate, filter, updateThreshold) x ITER
+# ------------------------------------------------------------------------------------------------------
+def run_pipeline(ctx, scene, iters: int, seed: int = 0x5EED0001):
+    """PmMvps::run (pmmvps.cpp:76-114) through the C ABI on the scene already resident in `ctx`: seeds -> patch store,
+    then ITER x (Propagate::run, Filter::run, updateThreshold).  Wall time includes the seed upload and every host sync."""
+    from mvskit_b200 import synth
+    coord, normal, scal, images, nimg = synth.seed_arrays(scene)
+    l0 = ctx.launch_count()
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.set_depth(0)
+    ctx.store_clear()
+    ctx.store_add(coord, normal, scal, images, nimg)
+    ctx.set_depth(1)
+    evals, t_prop, t_filt, counts = 0, 0.0, 0.0, None
+    for it in range(iters):
+        t = time.perf_counter()
+        st = ctx.propagate(it, seed)
+        ctx.sync()
+        t_prop += time.perf_counter() - t
+        evals += st["evals"]
+        t = time.perf_counter()
+        counts = ctx.filter()
+        ctx.sync()
+        t_filt += time.perf_counter() - t
+        ctx.update_threshold()
+    n = ctx.store_count()
+    dt = time.perf_counter() - t0
+    return {"patches": n, "seconds": dt, "patches_per_sec": n / dt, "seeds": int(len(coord)), "iters": iters, "propagate_seconds": t_prop,
+            "filter_seconds": t_filt, "sweep_ncc_evals": int(evals), "sweep_ncc_evals_per_sec": evals / max(t_prop, 1e-9),
+            "last_filter_counts": counts, "gpu_launches": ctx.launch_count() - l0}
+
+
+# ------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,6 +245,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="evals in the cpu_baseline sample (1 core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-iters", type=int, default=3, help="ITER of the end-to-end patches/sec run (0 = skip)")
+    ap.add_argument("--sweep-group", type=int, default=0, help="views swept together in Propagate::run (0 = all)")
     ap.add_argument("--order", default="grid", choices=["grid", "random"], help="hypothesis order: Z-order of the reference pixel (patch-grid walk) or random")
     args = ap.parse_args()
 
@@ -260,7 +296,7 @@ def main():
     c, n, vw, nv = hyp
     N = len(c)
 
-    ctx = pmk.Context(nviews=scene.nviews, device=local_rank)
+    ctx = pmk.Context(nviews=scene.nviews, device=local_rank, sweep_group=args.sweep_group or scene.nviews)
     ctx.set_scene(scene.P, scene.images)
     launches0 = ctx.launch_count()
 
@@ -353,6 +389,11 @@ def main():
                          "note": "not HBM-bound: the pyramid stays L2/L1 resident; binding units per ncu (profiles/): L1TEX data pipe ~71%, issue slots ~74%", "peak_source": peak_src,
                          "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0)},
         }
+        if world == 1 and args.pipeline_iters > 0:
+            # BASELINE metric (2): patches alive after the last Filter::run / wall time of init -> propagate x ITER -> filter
+            pipe = run_pipeline(ctx, scene, args.pipeline_iters)
+            pipe["config"] = f"config{args.config} scale {args.scale:g}: {scene.nviews} views, seeds every 4th cell, sweep_group {args.sweep_group or scene.nviews}"
+            out["pipeline"] = pipe
         if world == 1 and not args.no_cpu_baseline:
             v, kind = cpu_reference_evals_per_sec(scene, args.config, args.scale, hyp, 1, min(args.cpu_sample, N))
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,

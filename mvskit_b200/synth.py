@@ -412,6 +412,20 @@ class Scene:
         return recs
 
 
+def seed_arrays(scene: "Scene", **kw):
+    """scene.seeds() as the record arrays pmk_store_add takes: coord4, normal4, scal4 = (ncc 1, dscale, 0, 0), images, nimages."""
+    recs = scene.seeds(**kw)
+    n, V = len(recs), scene.nviews
+    coord, normal, scal = np.ones((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+    images, nimg = np.zeros((n, V), np.int32), np.zeros(n, np.int32)
+    for i, (X, N, ds, ids) in enumerate(recs):
+        coord[i, :3], normal[i, :3] = X, N
+        scal[i] = (1.0, ds, 0.0, 0.0)
+        images[i, :len(ids)] = ids
+        nimg[i] = len(ids)
+    return coord, normal, scal, images, nimg
+
+
 def make_scene(config: int, scale: float = 1.0, nviews: Optional[int] = None) -> Scene:
     """BASELINE.json configs 1..5.  `scale` shrinks the image size (tests)."""
     def dims(w, h, f):

@@ -190,9 +190,18 @@ def test_sweep_on_full_cells_replaces_the_same_patches(ctx, reflib, populated, s
     assert tot["matched"] >= 0.9 * tot["new_gpu"] and tot["close"] >= 0.9 * tot["matched"], tot
 
 
+def _load_both(ctx, reflib, g, depth):
+    reflib.clear_patches()
+    reflib.set_depth(0)
+    reflib.add_patches(g.coord, g.normal, g.scal, g.images, g.nimages)
+    reflib.set_depth(depth)
+    _load(ctx, g, depth)
+
+
 def test_filter_stages_match_reference(ctx, reflib, populated):
     g = populated
     reflib.set_ncc_thresholds(0.7, 0.4)
+    _load_both(ctx, reflib, g, 1)
     # ---- rebuild (additive = 0) ----
     reflib.filter_rebuild(0)
     n = ctx.filter_rebuild(0)

@@ -12,19 +12,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvskit_b200 import pmk, synth  # noqa: E402
 
 
-def seeds_arrays(scene):
-    recs = scene.seeds()
-    n, V = len(recs), scene.nviews
-    coord, normal, scal = np.ones((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
-    images, nimg = np.zeros((n, V), np.int32), np.zeros(n, np.int32)
-    for i, (X, N, ds, ids) in enumerate(recs):
-        coord[i, :3], normal[i, :3] = X, N
-        scal[i] = (1.0, ds, 0.0, 0.0)
-        images[i, :len(ids)] = ids
-        nimg[i] = len(ids)
-    return coord, normal, scal, images, nimg
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=1)
@@ -37,7 +24,7 @@ def main():
     scene = synth.make_scene(a.config, scale=a.scale, nviews=a.nviews).render()
     ctx = pmk.Context(nviews=scene.nviews, sweep_group=a.group, cell_capacity=a.cell_capacity)
     ctx.set_scene(scene.P, scene.images)
-    coord, normal, scal, images, nimg = seeds_arrays(scene)
+    coord, normal, scal, images, nimg = synth.seed_arrays(scene)
     ctx.set_depth(0); ctx.store_clear(); ctx.store_add(coord, normal, scal, images, nimg); ctx.set_depth(1)
     print("seeds", len(coord), "views", scene.nviews, "grid", ctx.grid_dims(0), "group", a.group, flush=True)
     T0 = time.time()
