@@ -186,6 +186,16 @@ int pmk_filter_stage(pmk_ctx* ctx, int stage, int nmax, float* f_out, int* i_out
 /* K5..K9 -- Filter::run (filter.cpp:25-49).  counts6 (optional): patches before, removed by each of the four filters, patches after. */
 int pmk_filter(pmk_ctx* ctx, int* counts6);
 
+/* ---- multi-GPU: one process and one pmk_ctx per GPU; images and the patch store are replicated, the dest cells of every
+ * wavefront step are partitioned by row band (rank r of n takes rows [ylo, yhi) of every view's cell grid), and after each step
+ * the ranks exchange the step's new and removed patches (ncclAllGather over NVLink/NVSwitch) and all apply all of them in rank
+ * order, so every replica holds the same store.  The reference is single-threaded: there is no counterpart to cite. */
+int pmk_band_rows(int gheight, int rank, int nranks, int* ylo, int* yhi);     /* the partition function (host only) */
+int pmk_comm_unique_id(char* id128);                        /* rank 0: ncclGetUniqueId; ship the 128 bytes to every rank */
+int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128);     /* ncclCommInitRank; nranks == 1 needs no id */
+int pmk_comm_destroy(pmk_ctx* ctx);
+int pmk_store_checksum(pmk_ctx* ctx, uint64_t* out2);       /* {order-independent digest of the live patches, their count} */
+
 /* Probes of the device-side building blocks, for parity tests (each item independent):
  *   project  : Camera::project at the working level        (camera.cpp:310-326)   -> out3
  *   unit     : Optim::getUnit                              (optim.cpp:34-41)      -> out1

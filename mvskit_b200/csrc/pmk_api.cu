@@ -336,6 +336,7 @@ int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
 
 void pmk_destroy(pmk_ctx* ctx) {
     if (!ctx) return;
+    pmk_comm_destroy(ctx);
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->owned) cudaFree(p);
@@ -1070,6 +1071,86 @@ int pmk_filter(pmk_ctx* ctx, int* counts6) {
     }
     c[5] = ctx->store->n;
     if (counts6) std::memcpy(counts6, c, sizeof(c));
+    return PMK_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------------------------
+int pmk_band_rows(int gheight, int rank, int nranks, int* ylo, int* yhi) {
+    if (!ylo || !yhi || gheight < 0 || nranks < 1 || rank < 0 || rank >= nranks) return fail(PMK_ERR_ARG, "pmk_band_rows: bad argument");
+    *ylo = (int)((long long)gheight * rank / nranks);
+    *yhi = (int)((long long)gheight * (rank + 1) / nranks);
+    return PMK_OK;
+}
+
+int pmk_comm_unique_id(char* id128) {
+    if (!id128) return fail(PMK_ERR_ARG, "pmk_comm_unique_id: null argument");
+    NcclApi* api = nccl_api();
+    if (!api) return fail(PMK_ERR_STATE, "pmk_comm_unique_id: libnccl.so.2 not found");
+    ncclUniqueId id;
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    const ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+    std::memcpy(id128, &id, 128);
+    return PMK_OK;
+}
+
+int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return fail(PMK_ERR_ARG, "pmk_comm_init: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    if (s->nccl_comm) return fail(PMK_ERR_STATE, "pmk_comm_init: communicator already set");
+    s->rank = rank; s->nranks = nranks;
+    if (nranks == 1) return PMK_OK;
+    if (!id128) return fail(PMK_ERR_ARG, "pmk_comm_init: null id");
+    NcclApi* api = nccl_api();
+    if (!api) return fail(PMK_ERR_STATE, "pmk_comm_init: libnccl.so.2 not found");
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    const ncclResult_t r = api->CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+    s->nccl_comm = comm;
+    s->ml.rem_cap = 16384;
+    s->ml.rec_cap = std::max(1024, std::min(16384, s->max_tasks * 4));
+    s->ml.rec_words = 14 + 4 * s->d.maxv;
+    if ((rc = dalloc(ctx, &s->msg, s->ml.words())) || (rc = dalloc(ctx, &s->all_msgs, s->ml.words() * nranks)) ||
+        (rc = dalloc(ctx, &s->pack_ids, s->ml.rec_cap)) || (rc = dalloc(ctx, &s->rec_base, 2 * nranks)))
+        return rc;
+    return PMK_OK;
+}
+
+int pmk_comm_destroy(pmk_ctx* ctx) {
+    if (!ctx || !ctx->store) return PMK_OK;
+    pmk_store* s = ctx->store;
+    if (s->nccl_comm) {
+        CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        NcclApi* api = nccl_api();
+        if (api) api->CommDestroy((ncclComm_t)s->nccl_comm);
+        s->nccl_comm = nullptr;
+    }
+    s->rank = 0; s->nranks = 1;
+    return PMK_OK;
+}
+
+int pmk_store_checksum(pmk_ctx* ctx, uint64_t* out2) {
+    if (!ctx || !out2) return fail(PMK_ERR_ARG, "pmk_store_checksum: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    if ((rc = store_check_overflow(ctx))) return rc;
+    pmk_store* s = ctx->store;
+    unsigned long long* d = (unsigned long long*)s->keys;
+    CUDA_TRY(cudaMemsetAsync(d, 0, 16, ctx->stream));
+    if (s->n > 0) {
+        k_store_checksum<<<(s->n + 255) / 256, 256, 0, ctx->stream>>>(s->d, s->n, d);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(out2, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PMK_OK;
 }
 

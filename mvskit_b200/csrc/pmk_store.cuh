@@ -26,7 +26,7 @@ constexpr unsigned SLOT_V = 0x80000000u;
 constexpr int LIST_MAX = 128;          // longest dest-cell list the sweep keeps in shared memory (>= cell capacity)
 constexpr int NEW_MAX = 32;            // new patches one dest cell can stage in one wavefront step (2 per call, 16 calls)
 constexpr int SRC_MAX = 32;            // source patches feeding one dest cell (two cells of <= MAX_NUM_OF_PATCHES)
-constexpr int NB_CAP = 4096;           // findNeighbors scratch per warp
+constexpr int NB_CAP = 4096;           // findNeighbors scratch per warp (2 * NB_CAP ints: list + sort buffer)
 
 enum StoreCounter { SC_N = 0, SC_BIRTH = 1, SC_OVERFLOW = 2, SC_FULL = 3, SC_REM = 4, SC_NBOVER = 5, SC_COUNT = 16 };
 
@@ -313,6 +313,17 @@ __device__ __forceinline__ int warp_find_neighbors(const StoreParams& sp, const 
         nuni += __popc(m);
         __syncwarp();
     }
+    // ascending id order: the quadric fit sums over the neighbours, and replicated stores (multi-GPU) must sum in one order
+    int* tmp = out + NB_CAP;
+    for (int k = lane; k < nuni; k += 32) {
+        const int id = out[k];
+        int rank = 0;
+        for (int j = 0; j < nuni; ++j) rank += out[j] < id ? 1 : 0;
+        tmp[rank] = id;
+    }
+    __syncwarp();
+    for (int k = lane; k < nuni; k += 32) out[k] = tmp[k];
+    __syncwarp();
     return nuni;
 }
 

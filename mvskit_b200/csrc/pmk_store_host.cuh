@@ -8,6 +8,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "pmk_filter.cuh"
 
 struct pmk_store {
@@ -29,6 +32,10 @@ struct pmk_store {
     int* nb_scratch = nullptr;
     int* small = nullptr;               // a few device ints for results
     float jitter[4];
+    // multi-GPU exchange of the step mutations (pmk_comm_init)
+    void* nccl_comm = nullptr;
+    pmk::MsgLayout ml = {0, 0, 0};
+    int* msg = nullptr; int* all_msgs = nullptr; int* pack_ids = nullptr; int* rec_base = nullptr;
     bool canonical = false;             // patch ids are the reference's m_ppatches indices (collect order, no holes)
 };
 
@@ -112,7 +119,7 @@ int store_init(pmk_ctx* ctx) {
         return rc;
     CandParams cp;
     if ((rc = cand_params(ctx, cp, 0))) return rc;                       // sizes cand_grid and the pairwise scratch
-    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * NB_CAP))) return rc;
+    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * 2 * NB_CAP))) return rc;
     s->gather_bytes = (size_t)d.cap * d.maxv * sizeof(int);
     s->gather_bytes = std::max(s->gather_bytes, (size_t)d.cap * sizeof(float4));
     CUDA_TRY(cudaMalloc(&s->gather_tmp, s->gather_bytes));
@@ -346,6 +353,35 @@ int filter_stage(pmk_ctx* ctx, int stage, int* killed) {
     return fail(PMK_ERR_ARG, "pmk_filter_stage: unknown stage");
 }
 
+// NCCL is resolved at run time (dlopen) so that the library neither links a second NCCL into a process that already has
+// torch's, nor needs one when it runs on a single GPU.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+        if (api.handle) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    return (api.handle && api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather) ? &api : nullptr;
+}
+
 template <int WS>
 int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     pmk_store* s = ctx->store;
@@ -353,11 +389,25 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     const size_t smem = CAND_WARPS * (sizeof(WarpScratch) + sizeof(SweepScratch));
     const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + CAND_WARPS - 1) / CAND_WARPS));
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
-    k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, sa);
-    k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
-    k4_apply_scan<<<1, 256, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
-    k4_apply_add<<<std::max(1, std::min(ctx->sm_count * 2, sa.ntasks)), 128, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
-    ctx->launches += 4;
+    if (sa.ntasks > 0) { k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, sa); ctx->launches++; }
+    if (s->nranks <= 1) {
+        k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
+        k4_apply_scan<<<1, 32, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
+        k4_apply_add<<<std::max(1, std::min(ctx->sm_count * 2, sa.ntasks)), 128, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
+        ctx->launches += 3;
+    } else {
+        // pack this rank's mutations, all-gather over NVLink, apply every rank's in rank order
+        NcclApi* api = nccl_api();
+        if (!api || !s->nccl_comm) return fail(PMK_ERR_STATE, "pmk: multi-GPU sweep without a communicator (pmk_comm_init)");
+        k4_pack_scan<<<1, 32, 0, st>>>(sp, s->task_new, sa.ntasks, s->rem_list, s->ml, s->msg, s->pack_ids);
+        k4_pack_copy<<<ctx->sm_count, 128, 0, st>>>(sp, s->ml, s->msg, s->pack_ids);
+        const ncclResult_t nr = api->AllGather(s->msg, s->all_msgs, s->ml.words(), ncclInt32, (ncclComm_t)s->nccl_comm, st);
+        if (nr != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nr) : "error"));
+        k4_unpack_remove<<<ctx->sm_count, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks);
+        k4_unpack_scan<<<1, 32, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, s->rec_base);
+        k4_unpack_add<<<ctx->sm_count * 2, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, s->rec_base);
+        ctx->launches += 5;
+    }
     CUDA_TRY(cudaGetLastError());
     return PMK_OK;
 }
@@ -396,7 +446,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
             sa.ntasks += xhi - xlo + 1;
         }
         sa.g_off[sa.ngroup] = sa.ntasks;
-        if (sa.ntasks <= 0) continue;
+        if (sa.ntasks <= 0 && s->nranks <= 1) continue;
         if (sa.ntasks > s->max_tasks) return fail(PMK_ERR_CAPACITY, "pmk: sweep step exceeds the staging capacity");
         WS_DISPATCH(ctx->cfg.wsize, { if ((rc = launch_sweep<WS>(ctx, sp, sa))) return rc; });
     }

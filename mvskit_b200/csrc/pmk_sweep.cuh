@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k4_sweep(const StoreParams sp
                         tmp = gain;
                         if (gain < 0.0f) r = -1;
                         else {
-                            int* nb = sp.nb_scratch + (size_t)gwarp * NB_CAP;
+                            int* nb = sp.nb_scratch + (size_t)gwarp * 2 * NB_CAP;
                             const int nn = warp_find_neighbors(sp, me, pl, 4.0f, 2, ov, nb, lane);
                             if (6 < nn && warp_filter_quad(sp, me, pl, nb, nn, nullptr, lane)) r = -1;
                         }
@@ -422,6 +422,151 @@ __global__ void k4_apply_add(const StoreParams sp, const int* __restrict__ task_
         warp_register_patch(sp, fid, deep, deep, lane);
         __syncwarp();
     }
+}
+
+}  // namespace pmk
+
+// =====================================================================================================================
+// Multi-GPU: the store is replicated, the dest cells of a step are partitioned by row band, and the step's mutations
+// (new patches, removals) travel between the ranks as one fixed-layout message per rank (ncclAllGather over NVLink).
+// Every rank then applies ALL messages in rank order, so ids, creation numbers and grids stay identical everywhere.
+//   message = int hdr[4] {n_new, n_rem, overflow, 0} | int rem[rem_cap] | rec[rec_cap][14 + 4 * maxv]
+//   record  = coord4, normal4, scal4 (as int bits), nimg, nvimg, images[maxv], cells[maxv], vimages[maxv], vcells[maxv]
+// =====================================================================================================================
+namespace pmk {
+
+struct MsgLayout {
+    int rem_cap, rec_cap, rec_words;
+    __host__ __device__ size_t words() const { return 4 + (size_t)rem_cap + (size_t)rec_cap * rec_words; }
+};
+
+// one thread: list the staged patches that survived the step, fill the header
+__global__ void k4_pack_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, const int* __restrict__ rem_list, MsgLayout ml,
+                             int* __restrict__ msg, int* __restrict__ pack_ids) {
+    const StoreDev& st = sp.st;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0, over = 0;
+    for (int t = 0; t < ntasks; ++t) {
+        const int k = task_new[t];
+        for (int j = 0; j < k; ++j) {
+            const int sid = st.cap + t * NEW_MAX + j;
+            if (st.state[sid] != 1) continue;
+            if (n < ml.rec_cap) pack_ids[n++] = sid; else over = 1;
+        }
+    }
+    int nrem = st.counters[SC_REM];
+    if (nrem > ml.rem_cap) { nrem = ml.rem_cap; over = 1; }
+    msg[0] = n; msg[1] = nrem; msg[2] = over; msg[3] = 0;
+    for (int i = 0; i < nrem; ++i) msg[4 + i] = rem_list[i];
+}
+
+__global__ void k4_pack_copy(const StoreParams sp, MsgLayout ml, int* __restrict__ msg, const int* __restrict__ pack_ids) {
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = msg[0];
+    for (int r = gwarp; r < n; r += nwarps) {
+        const int sid = pack_ids[r];
+        int* rec = msg + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
+        if (lane == 0) {
+            const float4 c = st.coord[sid], m = st.normal[sid], s = st.scal[sid];
+            rec[0] = __float_as_int(c.x); rec[1] = __float_as_int(c.y); rec[2] = __float_as_int(c.z); rec[3] = __float_as_int(c.w);
+            rec[4] = __float_as_int(m.x); rec[5] = __float_as_int(m.y); rec[6] = __float_as_int(m.z); rec[7] = __float_as_int(m.w);
+            rec[8] = __float_as_int(s.x); rec[9] = __float_as_int(s.y); rec[10] = __float_as_int(s.z); rec[11] = __float_as_int(s.w);
+            rec[12] = st.nimg[sid]; rec[13] = st.nvimg[sid];
+        }
+        const int ni = st.nimg[sid], nv = st.nvimg[sid], mv = st.maxv;
+        for (int i = lane; i < ni; i += 32) { rec[14 + i] = st.images[(size_t)sid * mv + i]; rec[14 + mv + i] = st.cells[(size_t)sid * mv + i]; }
+        for (int i = lane; i < nv; i += 32) { rec[14 + 2 * mv + i] = st.vimages[(size_t)sid * mv + i]; rec[14 + 3 * mv + i] = st.vcells[(size_t)sid * mv + i]; }
+    }
+}
+
+// removals of every rank's message (a patch may be listed by several ranks: the first warp to see it erases it)
+__global__ void k4_unpack_remove(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks) {
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int rk = 0; rk < nranks; ++rk) {
+        const int* msg = all + (size_t)rk * ml.words();
+        const int nrem = msg[1];
+        for (int r = gwarp; r < nrem; r += nwarps) {
+            const int id = msg[4 + r];
+            const int ni = st.nimg[id], nv = st.nvimg[id];
+            for (int i = lane; i < ni; i += 32) {
+                const int img = st.images[(size_t)id * st.maxv + i], c = st.cells[(size_t)id * st.maxv + i];
+                erase_from_cell(st, cell_global(sp, img, cell_x(c), cell_y(c)), id);
+            }
+            for (int i = lane; i < nv; i += 32) {
+                const int img = st.vimages[(size_t)id * st.maxv + i], c = st.vcells[(size_t)id * st.maxv + i];
+                erase_from_cell(st, cell_global(sp, img, cell_x(c), cell_y(c)), (int)((unsigned)id | SLOT_V));
+            }
+            __syncwarp();
+            if (lane == 0) st.state[id] = 0;
+        }
+    }
+}
+
+// one thread: final ids of every rank's records, rank-major; rec_base[rk] = first id of rank rk (or -1 beyond capacity)
+__global__ void k4_unpack_scan(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks, int* __restrict__ rec_base) {
+    const StoreDev& st = sp.st;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = st.counters[SC_N];
+    int b = st.counters[SC_BIRTH];
+    for (int rk = 0; rk < nranks; ++rk) {
+        const int* msg = all + (size_t)rk * ml.words();
+        if (msg[2]) atomicAdd(st.counters + SC_OVERFLOW, 1);
+        const int k = msg[0];
+        if (n + k <= st.cap) { rec_base[rk] = n; rec_base[nranks + rk] = b; n += k; b += k; }
+        else { rec_base[rk] = -1; rec_base[nranks + rk] = 0; atomicAdd(st.counters + SC_FULL, k); }
+    }
+    st.counters[SC_N] = n;
+    st.counters[SC_BIRTH] = b;
+}
+
+__global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks, const int* __restrict__ rec_base) {
+    const StoreDev& st = sp.st;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool deep = sp.cp.p.depth != 0;
+    for (int rk = 0; rk < nranks; ++rk) {
+        const int* msg = all + (size_t)rk * ml.words();
+        const int k = msg[0], base = rec_base[rk];
+        if (base < 0) continue;
+        for (int r = gwarp; r < k; r += nwarps) {
+            const int* rec = msg + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
+            const int fid = base + r, mv = st.maxv;
+            const int ni = rec[12], nv = rec[13];
+            if (lane == 0) {
+                st.coord[fid] = make_float4(__int_as_float(rec[0]), __int_as_float(rec[1]), __int_as_float(rec[2]), __int_as_float(rec[3]));
+                st.normal[fid] = make_float4(__int_as_float(rec[4]), __int_as_float(rec[5]), __int_as_float(rec[6]), __int_as_float(rec[7]));
+                st.scal[fid] = make_float4(__int_as_float(rec[8]), __int_as_float(rec[9]), __int_as_float(rec[10]), __int_as_float(rec[11]));
+                st.nimg[fid] = ni; st.nvimg[fid] = nv; st.state[fid] = 1; st.birth[fid] = (unsigned int)(rec_base[nranks + rk] + r);
+            }
+            for (int i = lane; i < ni; i += 32) { st.images[(size_t)fid * mv + i] = rec[14 + i]; st.cells[(size_t)fid * mv + i] = rec[14 + mv + i]; }
+            for (int i = lane; i < nv; i += 32) { st.vimages[(size_t)fid * mv + i] = rec[14 + 2 * mv + i]; st.vcells[(size_t)fid * mv + i] = rec[14 + 3 * mv + i]; }
+            __syncwarp();
+            warp_register_patch(sp, fid, deep, deep, lane);
+            __syncwarp();
+        }
+    }
+}
+
+// order-independent digest of the live store (replica consistency checks): sum over patches of a hash of coord, ncc and lists
+__global__ void k_store_checksum(const StoreDev st, int n, unsigned long long* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || st.state[q] != 1) return;
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned int v) { h ^= v; h *= 1099511628211ull; };
+    const float4 c = st.coord[q], m = st.normal[q], s = st.scal[q];
+    mix(__float_as_uint(c.x)); mix(__float_as_uint(c.y)); mix(__float_as_uint(c.z));
+    mix(__float_as_uint(m.x)); mix(__float_as_uint(m.y)); mix(__float_as_uint(m.z));
+    mix(__float_as_uint(s.x)); mix(__float_as_uint(s.y));
+    const int ni = st.nimg[q], nv = st.nvimg[q];
+    for (int i = 0; i < ni; ++i) { mix((unsigned)st.images[(size_t)q * st.maxv + i]); mix((unsigned)st.cells[(size_t)q * st.maxv + i]); }
+    mix(0xffffffffu);
+    for (int i = 0; i < nv; ++i) { mix((unsigned)st.vimages[(size_t)q * st.maxv + i]); mix((unsigned)st.vcells[(size_t)q * st.maxv + i]); }
+    atomicAdd(out, h);
+    atomicAdd(out + 1, 1ull);
 }
 
 }  // namespace pmk

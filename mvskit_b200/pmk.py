@@ -335,6 +335,15 @@ class Context:
         _chk(lib().pmk_filter(self.h, _p(c)))
         return [int(v) for v in c]
 
+    # -- multi-GPU --------------------------------------------------------------------------------------------
+    def comm_init(self, rank: int, nranks: int, unique_id: Optional[bytes]):
+        _chk(lib().pmk_comm_init(self.h, rank, nranks, unique_id))
+
+    def store_checksum(self):
+        out = np.zeros(2, np.uint64)
+        _chk(lib().pmk_store_checksum(self.h, _p(out)))
+        return int(out[0]), int(out[1])
+
     # -- plumbing ------------------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> DeviceBuffer:
         return DeviceBuffer(self, nbytes)
@@ -374,3 +383,15 @@ def exported_symbols():
     hdr = os.path.join(HERE, "..", "include", "pmk.h")
     txt = open(hdr).read()
     return sorted(set(re.findall(r"\b(pmk_[a-z0-9_]+)\s*\(", txt)))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _chk(lib().pmk_comm_unique_id(buf))
+    return buf.raw
+
+
+def band_rows(gheight: int, rank: int, nranks: int):
+    lo, hi = C.c_int(), C.c_int()
+    _chk(lib().pmk_band_rows(gheight, rank, nranks, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
