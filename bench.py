@@ -391,7 +391,10 @@ def main():
         }
         if world == 1 and args.pipeline_iters > 0:
             # BASELINE metric (2): patches alive after the last Filter::run / wall time of init -> propagate x ITER -> filter
-            pipe = run_pipeline(ctx, scene, args.pipeline_iters)
+            try:
+                pipe = run_pipeline(ctx, scene, args.pipeline_iters)
+            except Exception as exc:                      # the headline line must not be lost to the second metric
+                pipe = {"error": str(exc)}
             pipe["config"] = f"config{args.config} scale {args.scale:g}: {scene.nviews} views, seeds every 4th cell, sweep_group {args.sweep_group or scene.nviews}"
             out["pipeline"] = pipe
         if world == 1 and not args.no_cpu_baseline:

@@ -49,6 +49,8 @@ def build(force: bool = False, verbose: bool = False, fast: bool = False) -> str
           ["-Xlinker", "--version-script=" + os.path.join(CSRC, "pmk_exports.map")]
     if fast:
         cmd.insert(1, "-DPMK_WS_ONLY=7")
+    for flag in os.environ.get("PMK_NVCC_FLAGS", "").split():
+        cmd.insert(1, flag)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

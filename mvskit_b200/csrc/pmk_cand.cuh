@@ -55,8 +55,11 @@ __device__ __forceinline__ double uniform_pm1(uint32_t v) { return ((double)(v >
 // Optim::getTex + Optim::normalize for (X, N, px, py) in `view` (optim.cpp:790-844, 917-940).  Every lane of the
 // group holds the same arguments.  On return: t = this lane's lattice column, centred (tex - mean) and masked;
 // inv_msd = 1 / sqrt(ssd / (3 n)) (1 when ssd == 0).  Returns the pyramid level sampled or -1 (getTex == -1).
+#ifndef PMK_GRAB_INLINE
+#define PMK_GRAB_INLINE __noinline__     // one copy of the texture grab: the sweep kernel is I-cache bound with it inlined 15 times
+#endif
 template <int WS, int GW>
-__device__ __forceinline__ int group_grab(const Params& p, int view, V4 X, V4 N, V4 px, V4 py, int col, float cmask,
+__device__ PMK_GRAB_INLINE int group_grab(const Params& p, int view, V4 X, V4 N, V4 px, V4 py, int col, float cmask,
                                           float t[WS][3], float& inv_msd, unsigned gm = 0xffffffffu) {
     constexpr int NSAMP = WS * WS;
     constexpr float INV_NSAMP = 1.0f / (float)NSAMP, INV_3NSAMP = 1.0f / (float)(3 * NSAMP);

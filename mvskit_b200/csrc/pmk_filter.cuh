@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k8_neighbor(const StoreParams
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
     const Overlay none{-1, nullptr, 0, nullptr, 0};
-    int* nb = sp.nb_scratch + (size_t)gwarp * 2 * NB_CAP;
+    int* nb = sp.nb_scratch + (size_t)gwarp * NB_STRIDE;
     for (int q = gwarp; q < n; q += gridDim.x * CAND_WARPS) {
         if (st.state[q] != 1) { if (lane == 0) { flags[q] = 0; if (nn_out) nn_out[q] = 0; if (res_out) res_out[q] = 0.0f; } continue; }
         const PGeo me = load_geo(st, q);

@@ -197,27 +197,21 @@ __device__ __forceinline__ bool overlay_removed(const Overlay& ov, int id) {
     return false;
 }
 
-// max over the m_pgrids entries q of cell c of (q.ncc - thr) subject to `front` (pdepth < bdepth, vimages only) and !isNeighbor
-__device__ __forceinline__ float warp_cell_pressure(const StoreParams& sp, const PGeo& me, int img, int c, bool need_front, float pdepth, const Overlay& ov, int lane) {
+// max over the m_pgrids entries q of cell c of (q.ncc - thr) subject to `front` (pdepth < bdepth, vimages only) and !isNeighbor;
+// one LANE walks the whole cell (the warp spreads over the patch's registrations)
+__device__ __forceinline__ float lane_cell_pressure(const StoreParams& sp, const PGeo& me, int img, int c, bool need_front, float pdepth, const Overlay& ov) {
     const StoreDev& st = sp.st;
     const Params& p = sp.cp.p;
     float mp = 0.0f;
     const bool local = (c == ov.cell);
     const int n = local ? ov.n : min(st.ccount[c], st.cell_cap);
-    for (int base = 0; base < n; base += 32) {
-        const int s = base + lane;
-        if (s < n) {
-            const int e = local ? ov.ids[s] : st.cslots[(size_t)c * st.cell_cap + s];
-            if (e != SLOT_TOMB && e >= 0 && (local || !overlay_removed(ov, e))) {
-                const PGeo q = load_geo(st, e);
-                bool consider = true;
-                if (need_front) consider = pdepth < dot4(ld4(p.views[img].oaxis), q.X);       // Camera::computeDepth (camera.cpp:339-346)
-                if (consider && !is_neighbor(sp, me, q, sp.neighbor_threshold1)) mp = max_std(mp, xsub(st.scal[e].x, p.ncc_threshold));
-            }
-        }
+    for (int s = 0; s < n; ++s) {
+        const int e = local ? ov.ids[s] : st.cslots[(size_t)c * st.cell_cap + s];
+        if (e == SLOT_TOMB || e < 0 || (!local && overlay_removed(ov, e))) continue;
+        const PGeo q = load_geo(st, e);
+        if (need_front && !(pdepth < dot4(ld4(p.views[img].oaxis), q.X))) continue;            // Camera::computeDepth (camera.cpp:339-346)
+        if (!is_neighbor(sp, me, q, sp.neighbor_threshold1)) mp = max_std(mp, xsub(st.scal[e].x, p.ncc_threshold));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mp = fmaxf(mp, __shfl_xor_sync(0xffffffffu, mp, o));
     return mp;
 }
 
@@ -225,22 +219,47 @@ __device__ __forceinline__ float warp_cell_pressure(const StoreParams& sp, const
 __device__ __forceinline__ float warp_compute_gain(const StoreParams& sp, const PGeo& me, float ncc, const PatchLists& pl, const Overlay& ov, int lane) {
     const Params& p = sp.cp.p;
     float gain = xmul(max_std(0.0f, xsub(ncc, p.ncc_threshold)), (float)pl.nimg);              // score2 (patch.cpp:27-29)
-    for (int i = 0; i < pl.nimg; ++i) {
-        const int img = pl.images[i], c = pl.cells[i];
-        const float mp = warp_cell_pressure(sp, me, img, cell_global(sp, img, cell_x(c), cell_y(c)), false, 0.0f, ov, lane);
-        gain = xsub(gain, mp);
-    }
-    for (int i = 0; i < pl.nvimg; ++i) {
-        const int img = pl.vimages[i], c = pl.vcells[i];
-        const float pdepth = dot4(ld4(p.views[img].oaxis), me.X);
-        const float mp = warp_cell_pressure(sp, me, img, cell_global(sp, img, cell_x(c), cell_y(c)), true, pdepth, ov, lane);
-        gain = xsub(gain, mp);
+    const int tot = pl.nimg + pl.nvimg;
+    for (int base = 0; base < tot; base += 32) {
+        const int i = base + lane;
+        float mp = 0.0f;
+        if (i < tot) {
+            const bool isv = i >= pl.nimg;
+            const int img = isv ? pl.vimages[i - pl.nimg] : pl.images[i], c = isv ? pl.vcells[i - pl.nimg] : pl.cells[i];
+            const float pdepth = isv ? dot4(ld4(p.views[img].oaxis), me.X) : 0.0f;
+            mp = lane_cell_pressure(sp, me, img, cell_global(sp, img, cell_x(c), cell_y(c)), isv, pdepth, ov);
+        }
+        const int m = min(32, tot - base);
+        for (int k = 0; k < m; ++k) gain = xsub(gain, __shfl_sync(0xffffffffu, mp, k));          // in list order, like the reference
     }
     return gain;
 }
 
 // ---- PatchManager::findNeighbors (patch_manager.cpp:671-728): unique patches of the +-margin cells of every view of m_images
-// (m_pgrids and m_vpgrids) that pass isNeighborRadius.  Ids go to `out` (first-occurrence order); returns the count. ----------------
+// (m_pgrids and m_vpgrids) that pass isNeighborRadius.  Ids go to `out` in ascending order; returns the count.
+// Per view the (2 margin + 1)^2 cells are flattened into one slot range spread over the lanes; uniqueness (sort + unique by
+// pointer in the reference) comes from a warp-private open-addressing table of (call token, id) words in global scratch.
+constexpr int NB_HASH = 8192;          // table entries per warp (power of two, >= 2 * NB_CAP)
+constexpr int NB_STRIDE = 2 * NB_CAP + 2 * NB_HASH + 4;   // ints of findNeighbors scratch per warp
+
+__device__ __forceinline__ bool nb_insert(unsigned long long* table, unsigned int token, int id) {
+    unsigned int h = ((unsigned int)id * 2654435761u) >> 19;                  // 13 bits
+    const unsigned long long mine = ((unsigned long long)token << 32) | (unsigned int)id;
+    for (int probe = 0; probe < NB_HASH; ++probe) {
+        const unsigned long long cur = __ldcg(table + h);                    // L2: the table is written with atomics
+        if ((unsigned int)(cur >> 32) == token) {
+            if ((unsigned int)cur == (unsigned int)id) return false;
+        } else {
+            const unsigned long long old = atomicCAS(table + h, cur, mine);
+            if (old == cur) return true;
+            if (old == mine) return false;
+            continue;                                                          // another lane claimed the slot: look at it again
+        }
+        h = (h + 1) & (NB_HASH - 1);
+    }
+    return false;
+}
+
 __device__ __forceinline__ int warp_find_neighbors(const StoreParams& sp, const PGeo& me, const PatchLists& pl, float scale, int margin,
                                                    const Overlay& ov, int* out, int lane) {
     const StoreDev& st = sp.st;
@@ -262,57 +281,62 @@ __device__ __forceinline__ int warp_find_neighbors(const StoreParams& sp, const 
     const float radius = __double2float_rn(__dmul_rn(1.5 * (double)margin, (double)rad0));
     const float unit = xmul(xdiv(usum, (float)pl.nimg), (float)p.csize);
     const float thr = xmul(sp.neighbor_threshold, scale);
-    int nraw = 0;
-    const int side = 2 * margin + 1;
+    // scratch of this warp: [0, NB_CAP) list, [NB_CAP, 2 NB_CAP) sort buffer, then the table and its call counter
+    unsigned long long* table = reinterpret_cast<unsigned long long*>(out + 2 * NB_CAP);
+    unsigned int* tokp = reinterpret_cast<unsigned int*>(table + NB_HASH);
+    unsigned int token = 0;
+    if (lane == 0) { token = *tokp + 1; if (token == 0) token = 1; *tokp = token; }
+    token = __shfl_sync(0xffffffffu, token, 0);
+    int nuni = 0;
+    bool overflow = false;
+    const int side = 2 * margin + 1, ncell = side * side;           // <= 25 cells, one per lane
     for (int i = 0; i < pl.nimg; ++i) {
         const int img = pl.images[i];
         const ViewConst& vc = p.views[img];
         const int ix = cell_x(pl.cells[i]), iy = cell_y(pl.cells[i]);
-        for (int w = 0; w < side * side; ++w) {
-            const int yt = iy + w / side - margin, xt = ix + w % side - margin;
-            if (yt < 0 || vc.gh <= yt || xt < 0 || vc.gw <= xt) continue;
-            const int c = cell_global(sp, img, xt, yt);
-            const int n = min(st.ccount[c], st.cell_cap);
-            const bool local = (c == ov.cell);
-            const int ntot = local ? n + ov.n : n;        // the overlay supplies the m_pgrids entries, the slots the m_vpgrids ones
-            for (int base = 0; base < ntot; base += 32) {
-                const int s = base + lane;
-                int id = -1;
-                if (s < n) {
-                    const int e = st.cslots[(size_t)c * st.cell_cap + s];
-                    if (e != SLOT_TOMB && (e & 0x7fffffff) != SLOT_TOMB) {
+        int myc = -1, myn = 0, mynslot = 0;
+        if (lane < ncell) {
+            const int yt = iy + lane / side - margin, xt = ix + lane % side - margin;
+            if (!(yt < 0 || vc.gh <= yt || xt < 0 || vc.gw <= xt)) {
+                myc = cell_global(sp, img, xt, yt);
+                mynslot = min(st.ccount[myc], st.cell_cap);
+                myn = mynslot + (myc == ov.cell ? ov.n : 0);       // the overlay supplies the m_pgrids entries, the slots the m_vpgrids ones
+            }
+        }
+        int incl = myn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int base = 0; base < total; base += 32) {
+            const int f = base + lane;
+            int c = -1, slot = 0, nslot = 0;
+            for (int j = 0; j < ncell; ++j) {
+                const int pj = __shfl_sync(0xffffffffu, incl, j), nj = __shfl_sync(0xffffffffu, myn, j);
+                const int cj = __shfl_sync(0xffffffffu, myc, j), sj = __shfl_sync(0xffffffffu, mynslot, j);
+                if (c < 0 && f < pj && nj > 0 && f < total) { c = cj; slot = f - (pj - nj); nslot = sj; }
+            }
+            int id = -1;
+            if (c >= 0) {
+                if (slot < nslot) {
+                    const int e = st.cslots[(size_t)c * st.cell_cap + slot];
+                    if ((e & 0x7fffffff) != SLOT_TOMB) {
                         const bool isv = e < 0;
                         const int q = e & 0x7fffffff;
-                        if (!(local && !isv) && !overlay_removed(ov, q)) id = q;
+                        if (!(c == ov.cell && !isv) && !overlay_removed(ov, q)) id = q;
                     }
-                } else if (s < ntot) id = ov.ids[s - n];
-                bool hit = false;
-                if (id >= 0) hit = is_neighbor_radius(sp, me, load_geo(st, id), unit, thr, radius) != 0;
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (hit) { const int pos = nraw + __popc(m & ((1u << lane) - 1u)); if (pos < NB_CAP) out[pos] = id; }
-                nraw += __popc(m);
+                } else id = ov.ids[slot - nslot];
             }
+            bool hit = false;
+            if (id >= 0) hit = is_neighbor_radius(sp, me, load_geo(st, id), unit, thr, radius) != 0;
+            if (hit) hit = nb_insert(table, token, id);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) { const int pos = nuni + __popc(m & ((1u << lane) - 1u)); if (pos < NB_CAP) out[pos] = id; }
+            nuni += __popc(m);
         }
     }
     __syncwarp();
-    if (nraw > NB_CAP) { if (lane == 0) atomicAdd(st.counters + SC_NBOVER, 1); nraw = NB_CAP; }
-    // sort + unique (by pointer in the reference; any total order gives the same set): keep first occurrences
-    int nuni = 0;
-    for (int base = 0; base < nraw; base += 32) {
-        const int k = base + lane;
-        bool first = false;
-        int id = 0;
-        if (k < nraw) {
-            id = out[k];
-            first = true;
-            for (int j = 0; j < k; ++j) if (out[j] == id) { first = false; break; }
-        }
-        __syncwarp();                                  // every lane has read out[0..k) before the compaction overwrites a prefix
-        const unsigned m = __ballot_sync(0xffffffffu, first);
-        if (first) out[nuni + __popc(m & ((1u << lane) - 1u))] = id;   // nuni + rank <= k
-        nuni += __popc(m);
-        __syncwarp();
-    }
+    if (nuni > NB_CAP) { overflow = true; nuni = NB_CAP; }
+    if (overflow && lane == 0) atomicAdd(st.counters + SC_NBOVER, 1);
     // ascending id order: the quadric fit sums over the neighbours, and replicated stores (multi-GPU) must sum in one order
     int* tmp = out + NB_CAP;
     for (int k = lane; k < nuni; k += 32) {

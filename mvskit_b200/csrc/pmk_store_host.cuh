@@ -119,7 +119,8 @@ int store_init(pmk_ctx* ctx) {
         return rc;
     CandParams cp;
     if ((rc = cand_params(ctx, cp, 0))) return rc;                       // sizes cand_grid and the pairwise scratch
-    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * 2 * NB_CAP))) return rc;
+    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * NB_STRIDE))) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->nb_scratch, 0, (size_t)ctx->cand_grid * CAND_WARPS * NB_STRIDE * sizeof(int), ctx->stream));
     s->gather_bytes = (size_t)d.cap * d.maxv * sizeof(int);
     s->gather_bytes = std::max(s->gather_bytes, (size_t)d.cap * sizeof(float4));
     CUDA_TRY(cudaMalloc(&s->gather_tmp, s->gather_bytes));
@@ -392,7 +393,7 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     if (sa.ntasks > 0) { k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, sa); ctx->launches++; }
     if (s->nranks <= 1) {
         k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
-        k4_apply_scan<<<1, 32, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
+        k4_apply_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
         k4_apply_add<<<std::max(1, std::min(ctx->sm_count * 2, sa.ntasks)), 128, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
         ctx->launches += 3;
     } else {

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k4_sweep(const StoreParams sp
                         tmp = gain;
                         if (gain < 0.0f) r = -1;
                         else {
-                            int* nb = sp.nb_scratch + (size_t)gwarp * 2 * NB_CAP;
+                            int* nb = sp.nb_scratch + (size_t)gwarp * NB_STRIDE;
                             const int nn = warp_find_neighbors(sp, me, pl, 4.0f, 2, ov, nb, lane);
                             if (6 < nn && warp_filter_quad(sp, me, pl, nb, nn, nullptr, lane)) r = -1;
                         }
@@ -372,31 +372,60 @@ __device__ __forceinline__ void warp_register_patch(const StoreParams& sp, int i
     }
 }
 
-// one block: exclusive scan of the staged-and-alive counts -> final ids; bumps SC_N / SC_BIRTH.  final_id[task * NEW_MAX + j] = id or -1
-__global__ void k4_apply_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, int* __restrict__ final_id) {
+// one block: exclusive scan of the staged-and-alive counts -> final ids (task order); bumps SC_N / SC_BIRTH.
+// final_id[task * NEW_MAX + j] = id or -1.  Launched with 1024 threads; thread t owns tasks t, t + 1024, ...
+__global__ void __launch_bounds__(1024) k4_apply_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, int* __restrict__ final_id) {
     const StoreDev& st = sp.st;
-    __shared__ int s_base;
-    if (threadIdx.x == 0) {
-        int n = st.counters[SC_N];
-        unsigned int b = (unsigned int)st.counters[SC_BIRTH];
-        for (int t = 0; t < ntasks; ++t) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const int n0 = st.counters[SC_N];
+    const int b0 = st.counters[SC_BIRTH];
+    for (int base = 0; base < ntasks; base += 1024) {
+        const int t = base + tid;
+        int cnt = 0;
+        if (t < ntasks) {
+            const int k = task_new[t];
+            for (int j = 0; j < k; ++j) cnt += st.state[st.cap + t * NEW_MAX + j] == 1 ? 1 : 0;
+        }
+        int incl = cnt;                                     // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+            s_warp[lane] = w;                               // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        int excl = carry + (wid > 0 ? s_warp[wid - 1] : 0) + incl - cnt;
+        if (t < ntasks) {
             const int k = task_new[t];
             for (int j = 0; j < k; ++j) {
                 const int sid = st.cap + t * NEW_MAX + j;
                 int fid = -1;
                 if (st.state[sid] == 1) {
-                    if (n < st.cap) { fid = n++; st.birth[sid] = b++; }
+                    if (n0 + excl < st.cap) { fid = n0 + excl; st.birth[sid] = (unsigned int)(b0 + excl); }
                     else atomicAdd(st.counters + SC_FULL, 1);
+                    ++excl;
                 }
                 final_id[t * NEW_MAX + j] = fid;
             }
         }
-        st.counters[SC_N] = n;
-        st.counters[SC_BIRTH] = (int)b;
-        s_base = n;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
     }
-    __syncthreads();
-    (void)s_base;
+    if (tid == 0) {
+        const int total = s_carry;
+        st.counters[SC_N] = min(st.cap, n0 + total);
+        st.counters[SC_BIRTH] = b0 + total;
+    }
 }
 
 // copy every staged, surviving patch to its final slot and register it (one warp per staged entry)
