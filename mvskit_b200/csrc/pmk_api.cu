@@ -81,6 +81,8 @@ struct pmk_ctx {
     pmk_config cfg;
     pmk_store* store = nullptr;             // device patch store (pmk_store_host.cuh), created on first use
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;        // copy streams of the chunked host-buffer NCC call
+    std::vector<cudaEvent_t> ev_in, ev_k;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     Params params;
@@ -177,7 +179,7 @@ int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, cons
                 void* incc, void* ncc, void* levels) {
     static const int minb = getenv("PMK_K1_MINB") ? atoi(getenv("PMK_K1_MINB")) : 4;   // tuning knob: CTAs/SM the kernel is compiled for
 #ifdef PMK_WS_ONLY
-    if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+    if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
     (void)minb;
 #else
     switch (ctx->cfg.wsize) {
@@ -312,6 +314,8 @@ int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
     ctx->cfg = *cfg;
     CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     ctx->h_views.resize(cfg->nviews);
@@ -348,6 +352,9 @@ void pmk_destroy(pmk_ctx* ctx) {
     cudaFree(ctx->d_views);
     cudaFree(ctx->d_counters);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_k) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->stream);
     delete ctx->store;
     delete ctx;
@@ -539,17 +546,38 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
         (rc = ensure(ctx, ctx->s_nviews, N * 4)) || (rc = ensure(ctx, ctx->s_incc, N * 4)) || (rc = ensure(ctx, ctx->s_ncc, N * 4)) ||
         (rc = ensure(ctx, ctx->s_levels, N * tau * 4)))
         return rc;
+    // Three-stage pipeline over chunks of the batch: H2D on s_in, K1 on the context stream, D2H on s_out, chained by events, so
+    // the PCIe copies of one chunk overlap the kernel of another (host buffers should be pinned for the copies to be asynchronous).
     cudaStream_t st = ctx->stream;
-    CUDA_TRY(cudaMemcpyAsync(ctx->s_coord.p, coord4, N * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->s_normal.p, normal4, N * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->s_views.p, views, N * stride * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->s_nviews.p, nviews, N * 4, cudaMemcpyHostToDevice, st));
-    rc = pmk_ncc_eval_dev(ctx, n, ctx->s_coord.p, ctx->s_normal.p, ctx->s_views.p, ctx->s_nviews.p, stride, ctx->s_incc.p,
-                          ncc_out ? ctx->s_ncc.p : nullptr, levels_out ? ctx->s_levels.p : nullptr);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(incc_out, ctx->s_incc.p, N * 4, cudaMemcpyDeviceToHost, st));
-    if (ncc_out) CUDA_TRY(cudaMemcpyAsync(ncc_out, ctx->s_ncc.p, N * 4, cudaMemcpyDeviceToHost, st));
-    if (levels_out) CUDA_TRY(cudaMemcpyAsync(levels_out, ctx->s_levels.p, N * tau * 4, cudaMemcpyDeviceToHost, st));
+    const size_t chunk = 1 << 17;
+    const int nchunks = (int)((N + chunk - 1) / chunk);
+    while ((int)ctx->ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ctx->ev_in.push_back(a); ctx->ev_k.push_back(b);
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev1, st));                      // the copies must not overtake earlier work on the context stream
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev1, 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t o = (size_t)c * chunk, m = std::min(chunk, N - o);
+        CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_coord.p + o * 16, coord4 + o * 4, m * 16, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_normal.p + o * 16, normal4 + o * 4, m * 16, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_views.p + o * stride * 4, views + o * stride, m * stride * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_nviews.p + o * 4, nviews + o, m * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
+        rc = pmk_ncc_eval_dev(ctx, (int)m, (char*)ctx->s_coord.p + o * 16, (char*)ctx->s_normal.p + o * 16, (char*)ctx->s_views.p + o * stride * 4,
+                              (char*)ctx->s_nviews.p + o * 4, stride, (char*)ctx->s_incc.p + o * 4, ncc_out ? (char*)ctx->s_ncc.p + o * 4 : nullptr,
+                              levels_out ? (char*)ctx->s_levels.p + o * tau * 4 : nullptr);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev_k[c], st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(incc_out + o, (char*)ctx->s_incc.p + o * 4, m * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (ncc_out) CUDA_TRY(cudaMemcpyAsync(ncc_out + o, (char*)ctx->s_ncc.p + o * 4, m * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (levels_out) CUDA_TRY(cudaMemcpyAsync(levels_out + o * tau, (char*)ctx->s_levels.p + o * tau * 4, m * tau * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PMK_OK;
 }

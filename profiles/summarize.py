@@ -50,7 +50,10 @@ def main():
             if len(r) <= iE:
                 continue
             m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[iS])
-            ops[m.group(2).split(".")[0] if m else "?"] += float(r[iE] or 0)
+            try:
+                ops[m.group(2).split(".")[0] if m else "?"] += float(r[iE] or 0)
+            except ValueError:          # a second kernel's header row inside the same csv
+                continue
         tot = sum(ops.values())
         print(f"== SASS: {len(data)} static instructions, {tot:.0f} executed warp-instructions")
         for op, c in ops.most_common(16):
