@@ -214,13 +214,14 @@ def run_pipeline(ctx, scene, iters: int, seed: int = 0x5EED0001):
     ctx.store_clear()
     ctx.store_add(coord, normal, scal, images, nimg)
     ctx.set_depth(1)
-    evals, t_prop, t_filt, counts = 0, 0.0, 0.0, None
+    evals, calls, t_prop, t_filt, counts = 0, 0, 0.0, 0.0, None
     for it in range(iters):
         t = time.perf_counter()
         st = ctx.propagate(it, seed)
         ctx.sync()
         t_prop += time.perf_counter() - t
         evals += st["evals"]
+        calls += st["calls"]
         t = time.perf_counter()
         counts = ctx.filter()
         ctx.sync()
@@ -229,8 +230,36 @@ def run_pipeline(ctx, scene, iters: int, seed: int = 0x5EED0001):
     n = ctx.store_count()
     dt = time.perf_counter() - t0
     return {"patches": n, "seconds": dt, "patches_per_sec": n / dt, "seeds": int(len(coord)), "iters": iters, "propagate_seconds": t_prop,
+            "propagate_patch_calls": int(calls), "propagate_patch_calls_per_sec": calls / max(t_prop, 1e-9),
             "filter_seconds": t_filt, "sweep_ncc_evals": int(evals), "sweep_ncc_evals_per_sec": evals / max(t_prop, 1e-9),
             "last_filter_counts": counts, "gpu_launches": ctx.launch_count() - l0}
+
+
+def cpu_reference_sweep_calls_per_sec(scene, config, scale, budget_s: float = 15.0):
+    """The reference's own Propagate::propagatePatch (oracle/_ref/libpmref.so), driven dest cell by dest cell over the first
+    anti-diagonals of view 0 from the same seeds, for `budget_s` seconds on one core: propagatePatch calls per second."""
+    from oracle import pyoracle
+    from mvskit_b200 import synth
+    if not os.path.exists(pyoracle.REF_SO):
+        return None
+    global _REF
+    if _REF is None:
+        _ref_init(ensure_scene_dir(scene, config, scale))
+    ref = _REF
+    coord, normal, scal, images, nimg = synth.seed_arrays(scene)
+    ref.clear_patches()
+    ref.set_depth(0)
+    ref.add_patches(coord, normal, scal, images, nimg)
+    ref.set_depth(1)
+    ref.refine_seed(0x5EED0001)
+    gw, gh = ref.grid_dims(0)
+    calls, d, t0 = 0, 12, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and d < gw + gh - 1:
+        calls += ref.propagate_diag(0, d, 1, 0)
+        d += 1
+    dt = time.perf_counter() - t0
+    return {"value": calls / dt, "unit": "propagatePatch calls/s", "cores": 1, "kind": "reference",
+            "sample": f"{calls} calls: anti-diagonals 12..{d - 1} of view 0, iteration 0, same seeds, {dt:.1f} s"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -357,6 +386,29 @@ def main():
     barrier()
     clocks = sampler.stop(t_wall0, time.time())
 
+    # BASELINE metric (2) on N > 1 GPUs: the same scene, dest-cell rows split into bands, step mutations all-gathered (NCCL)
+    pipe_mg = None
+    if dist and args.pipeline_iters > 0:
+        import torch
+        from mvskit_b200 import dist as pdist
+        try:
+            pdist.init_comm(ctx, dist, device=torch.device("cuda", local_rank))
+            barrier()
+            pipe_mg = run_pipeline(ctx, scene, args.pipeline_iters)
+            barrier()
+            digest = ctx.store_checksum()
+            allsum = [None] * world
+            dist.all_gather_object(allsum, digest)
+            secs = torch.tensor([pipe_mg["seconds"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+            pipe_mg["seconds"] = float(secs[0])
+            pipe_mg["patches_per_sec"] = pipe_mg["patches"] / pipe_mg["seconds"]
+            pipe_mg["replicas_identical"] = all(x == allsum[0] for x in allsum)
+            pipe_mg["config"] = (f"config{args.config} scale {args.scale:g}: {scene.nviews} views, {world} GPUs (row bands, replicated store, "
+                                 f"ncclAllGather of step mutations), sweep_group {args.sweep_group or scene.nviews}")
+        except Exception as exc:
+            pipe_mg = {"error": str(exc)}
+
     total_ms, total_e2e = float(sum(ms_steps)), float(sum(e2e_ms))
     if dist:
         import torch
@@ -389,6 +441,8 @@ def main():
                          "note": "not HBM-bound: the pyramid stays L2/L1 resident; binding units per ncu (profiles/): L1TEX data pipe ~71%, issue slots ~74%", "peak_source": peak_src,
                          "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0)},
         }
+        if pipe_mg is not None:
+            out["pipeline"] = pipe_mg
         if world == 1 and args.pipeline_iters > 0:
             # BASELINE metric (2): patches alive after the last Filter::run / wall time of init -> propagate x ITER -> filter
             try:
@@ -396,6 +450,11 @@ def main():
             except Exception as exc:                      # the headline line must not be lost to the second metric
                 pipe = {"error": str(exc)}
             pipe["config"] = f"config{args.config} scale {args.scale:g}: {scene.nviews} views, seeds every 4th cell, sweep_group {args.sweep_group or scene.nviews}"
+            if "error" not in pipe and not args.no_cpu_baseline:
+                try:
+                    pipe["cpu_baseline"] = cpu_reference_sweep_calls_per_sec(scene, args.config, args.scale)
+                except Exception as exc:
+                    pipe["cpu_baseline"] = {"error": str(exc)}
             out["pipeline"] = pipe
         if world == 1 and not args.no_cpu_baseline:
             v, kind = cpu_reference_evals_per_sec(scene, args.config, args.scale, hyp, 1, min(args.cpu_sample, N))

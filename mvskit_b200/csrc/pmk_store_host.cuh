@@ -387,8 +387,9 @@ template <int WS>
 int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     pmk_store* s = ctx->store;
     cudaStream_t st = ctx->stream;
-    const size_t smem = CAND_WARPS * (sizeof(WarpScratch) + sizeof(SweepScratch));
-    const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + CAND_WARPS - 1) / CAND_WARPS));
+    const size_t smem = CAND_WARPS * (sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellShared));
+    const int cpc = CAND_WARPS / sa.wpc;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + cpc - 1) / cpc));
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
     if (sa.ntasks > 0) { k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, sa); ctx->launches++; }
     if (s->nranks <= 1) {
@@ -449,6 +450,14 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
         sa.g_off[sa.ngroup] = sa.ntasks;
         if (sa.ntasks <= 0 && s->nranks <= 1) continue;
         if (sa.ntasks > s->max_tasks) return fail(PMK_ERR_CAPACITY, "pmk: sweep step exceeds the staging capacity");
+        // warps per dest cell: a step ends with its slowest cell, so narrow steps put 4 (or 2) warps on each cell (speculative tries,
+        // in-order commit); wide steps already fill the machine with one warp per cell
+        {
+            static const int forced = getenv("PMK_SWEEP_WPC") ? atoi(getenv("PMK_SWEEP_WPC")) : 0;
+            const int resident = ctx->sm_count * PMK_SWEEP_MINB * CAND_WARPS;        // warps in flight
+            sa.wpc = sa.ntasks * 4 <= resident ? 4 : (sa.ntasks * 2 <= resident ? 2 : 1);
+            if (forced == 1 || forced == 2 || forced == 4) sa.wpc = forced;
+        }
         WS_DISPATCH(ctx->cfg.wsize, { if ((rc = launch_sweep<WS>(ctx, sp, sa))) return rc; });
     }
     s->canonical = false;

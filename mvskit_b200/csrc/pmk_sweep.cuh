@@ -28,6 +28,7 @@ struct SweepArgs {
     int ngroup, ntasks, inc;
     int g_img[GROUP_MAX], g_diag[GROUP_MAX], g_xlo[GROUP_MAX], g_off[GROUP_MAX + 1];
     int iter;                              // Propagate::run(iter)
+    int wpc;                               // warps cooperating on one dest cell: 1, 2 or 4 (CAND_WARPS / wpc cells per CTA)
     int jitter_mode;                       // 0: the reference's four constant draws (propagate.cpp:139-141), 1: Philox per try
     float jitter[4];
     int* rem_list;                         // patches removed this step (SC_REM counts them)
@@ -35,11 +36,8 @@ struct SweepArgs {
     unsigned long long* stats;             // SweepStat
 };
 
-struct SweepScratch {
-    int l_id[LIST_MAX];
-    float l_ncc[LIST_MAX];
-    int src_id[SRC_MAX];
-    int removed[LIST_MAX + NEW_MAX];
+struct SweepScratch {                  // per warp
+    int l_snap[LIST_MAX];              // snapshot of the dest cell's list the try was evaluated against
     int vimg[CAND_MAXV];
     int vcell[CAND_MAXV];
     int cells[CAND_MAXV];
@@ -103,23 +101,85 @@ __device__ __forceinline__ float warp_compute_ncc(const Params& p, WarpScratch& 
     return xsub(1.0f, unrobustincc(incc));
 }
 
+// ---- one dest cell per CTA: the tries run speculatively on the CTA's warps and commit in order ------------------------------
+// The tries of a dest cell (call c, try k) depend on each other only through the cell's list: whether it still has room, and
+// otherwise which patch is the worst.  Each warp claims the next try, snapshots the list (seqlock), evaluates the try against
+// that snapshot, waits for its turn (commit_ptr == try index), and commits if the snapshot's assumptions still hold -- the
+// branch (room / full), the worst patch when full; the store-reading tail (stage B) is redone when the list changed at all.
+// Otherwise it re-evaluates, now against the final state since it holds the turn.  The outcome is the sequential one.
+struct CellShared {
+    int l_id[LIST_MAX];
+    float l_ncc[LIST_MAX];
+    int src_id[SRC_MAX];
+    int removed[LIST_MAX + NEW_MAX];
+    int nl, nrem, nnew, nsrc;
+    int version;                 // seqlock: odd while a commit is in progress
+    int next_try, commit_ptr;
+};
+
+struct TrySnap {
+    int ver, np, w, nrem;
+    float wncc;
+};
+
+__device__ __forceinline__ int ld_shared_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// consistent copy of the dest-cell list into warp-private scratch
+__device__ __forceinline__ TrySnap take_snapshot(const CellShared& cs, int* my_id, int maxp, int lane) {
+    TrySnap sn;
+    while (true) {
+        const int v0 = ld_shared_volatile(&cs.version);
+        if (v0 & 1) { __nanosleep(50); continue; }
+        const int np = ld_shared_volatile(&cs.nl);
+        for (int i = lane; i < min(np, LIST_MAX); i += 32) my_id[i] = ld_shared_volatile(&cs.l_id[i]);
+        sn.np = np;
+        sn.w = np >= maxp ? ld_shared_volatile(&cs.l_id[maxp - 1]) : -1;
+        sn.wncc = np >= maxp ? __int_as_float(ld_shared_volatile(reinterpret_cast<const int*>(&cs.l_ncc[maxp - 1]))) : 0.0f;
+        sn.nrem = ld_shared_volatile(&cs.nrem);
+        __syncwarp();
+        const int v1 = ld_shared_volatile(&cs.version);
+        sn.ver = v0;
+        if (v0 == v1) break;
+    }
+    return sn;
+}
+
+enum TryOutcome { TRY_GEN_NULL = 0, TRY_LOSE, TRY_FAIL0, TRY_FAIL1, TRY_ACCEPT };
+
+struct Cand {                    // a candidate after stage A (its image list is in ws.images)
+    V4 X, N;
+    int nv, nvv;
+    float ncc, dscale, ascale, tmp;
+};
+
+#ifndef PMK_SWEEP_MINB
+#define PMK_SWEEP_MINB 2
+#endif
 template <int WS>
-__global__ void __launch_bounds__(CAND_WARPS * 32) k4_sweep(const StoreParams sp, const SweepArgs sa) {
+__global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(const StoreParams sp, const SweepArgs sa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch& ws = warp_scratch(smem_raw);
     SweepScratch& ss = reinterpret_cast<SweepScratch*>(smem_raw + CAND_WARPS * sizeof(WarpScratch))[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, cta_warp = threadIdx.x >> 5;
+    const int wpc = sa.wpc, cpc = CAND_WARPS / wpc;                   // warps per cell, cells per CTA
+    const int cell_slot = cta_warp / wpc, warp = cta_warp % wpc;      // `warp` = rank among the warps of this dest cell
+    CellShared& cs = reinterpret_cast<CellShared*>(smem_raw + CAND_WARPS * (sizeof(WarpScratch) + sizeof(SweepScratch)))[cell_slot];
     const CandParams& cp = sp.cp;
     const Params& p = cp.p;
     const StoreDev& st = sp.st;
-    const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    const int gwarp = blockIdx.x * CAND_WARPS + cta_warp;
+    // barrier over the warps of this cell only (the cells of a CTA run different numbers of tasks)
+    auto cell_sync = [&]() {
+        if (wpc == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + cell_slot), "r"(wpc * 32) : "memory");
+    };
     const int inc = sa.inc;
     const int maxp = sp.max_patches_cell;
-    unsigned long long stat[SS_COUNT];
+    unsigned int stat[SS_COUNT];
 #pragma unroll
     for (int i = 0; i < SS_COUNT; ++i) stat[i] = 0;
 
-    for (int task = gwarp; task < sa.ntasks; task += gridDim.x * CAND_WARPS) {
+    for (int task = blockIdx.x * cpc + cell_slot; task < sa.ntasks; task += gridDim.x * cpc) {
         int g = 0;
         while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
         const int img = sa.g_img[g];
@@ -127,186 +187,248 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k4_sweep(const StoreParams sp
         const int gw = vimgc.gw, gh = vimgc.gh;
         const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
         const int cD = st.cell_base[img] + y * gw + x;
-        int nrem = 0, nnew = 0;
-        // ---- D's list: sortPatches + trim (propagate.cpp:123-134) ----
-        int nl = warp_load_cell(sp, cD, ss.l_id, ss.l_ncc, lane);
-        for (int i = 0; i < nl; ++i) {
-            if (ss.l_ncc[i] < 0.0f) {                                   // sortPatches recomputes a negative m_ncc (patch_manager.cpp:411-415)
-                const int e = ss.l_id[i];
-                const int nv = min(st.nimg[e], CAND_MAXV);
-                for (int k = lane; k < nv; k += 32) ws.images[k] = st.images[(size_t)e * st.maxv + k];
-                __syncwarp();
-                const float v = warp_compute_ncc<WS>(p, ws, f4v(st.coord[e]), f4v(st.normal[e]), nv, lane);
-                if (lane == 0) { ss.l_ncc[i] = v; st.scal[e].x = v; }
-                __syncwarp();
+        // ================= preamble (warp 0): D's list, trim, sources =================
+        if (warp == 0) {
+            int nrem = 0;
+            // ---- D's list: sortPatches + trim (propagate.cpp:123-134) ----
+            int nl = warp_load_cell(sp, cD, cs.l_id, cs.l_ncc, lane);
+            for (int i = 0; i < nl; ++i) {
+                if (cs.l_ncc[i] < 0.0f) {                                   // sortPatches recomputes a negative m_ncc (patch_manager.cpp:411-415)
+                    const int e = cs.l_id[i];
+                    const int nv = min(st.nimg[e], CAND_MAXV);
+                    for (int k = lane; k < nv; k += 32) ws.images[k] = st.images[(size_t)e * st.maxv + k];
+                    __syncwarp();
+                    const float v = warp_compute_ncc<WS>(p, ws, f4v(st.coord[e]), f4v(st.normal[e]), nv, lane);
+                    if (lane == 0) { cs.l_ncc[i] = v; st.scal[e].x = v; }
+                    __syncwarp();
+                }
             }
-        }
-        if (lane == 0) swap_sort_desc(ss.l_id, ss.l_ncc, nl);
-        __syncwarp();
-        if (nl > maxp) {
-            for (int i = maxp + lane; i < nl; i += 32) ss.removed[nrem + i - maxp] = ss.l_id[i];
-            stat[SS_TRIMMED] += nl - maxp;
-            nrem += nl - maxp; nl = maxp;
-        }
-        __syncwarp();
-        // ---- sources: (x, y - inc) first, then (x - inc, y); each cell's sorted top-maxp, reference view == img ----
-        int nsrc = 0;
-        for (int side = 0; side < 2; ++side) {
-            const int sx = side == 0 ? x : x - inc, sy = side == 0 ? y - inc : y;
-            if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
-            int* tid = ss.vimg; float* tncc = reinterpret_cast<float*>(ss.vcell);       // scratch, free until postProcess
-            int m = warp_load_cell(sp, st.cell_base[img] + sy * gw + sx, tid, tncc, lane);
-            if (lane == 0) swap_sort_desc(tid, tncc, m);
+            if (lane == 0) swap_sort_desc(cs.l_id, cs.l_ncc, nl);
             __syncwarp();
-            m = min(m, maxp);
-            for (int i = 0; i < m && nsrc < SRC_MAX; ++i) {
-                const int e = tid[i];
-                if (st.images[(size_t)e * st.maxv] == img) { if (lane == 0) ss.src_id[nsrc] = e; ++nsrc; }
+            if (nl > maxp) {
+                for (int i = maxp + lane; i < nl; i += 32) cs.removed[nrem + i - maxp] = cs.l_id[i];
+                stat[SS_TRIMMED] += nl - maxp;
+                nrem += nl - maxp; nl = maxp;
             }
             __syncwarp();
+            // ---- sources: (x, y - inc) first, then (x - inc, y); each cell's sorted top-maxp, reference view == img ----
+            int nsrc = 0;
+            for (int side = 0; side < 2; ++side) {
+                const int sx = side == 0 ? x : x - inc, sy = side == 0 ? y - inc : y;
+                if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
+                int* tid = ss.vimg; float* tncc = reinterpret_cast<float*>(ss.vcell);       // scratch, free until stage B
+                int m = warp_load_cell(sp, st.cell_base[img] + sy * gw + sx, tid, tncc, lane);
+                if (lane == 0) swap_sort_desc(tid, tncc, m);
+                __syncwarp();
+                m = min(m, maxp);
+                for (int i = 0; i < m && nsrc < SRC_MAX; ++i) {
+                    const int e = tid[i];
+                    if (st.images[(size_t)e * st.maxv] == img) { if (lane == 0) cs.src_id[nsrc] = e; ++nsrc; }
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { cs.nl = nl; cs.nrem = nrem; cs.nnew = 0; cs.nsrc = nsrc; cs.version = 0; cs.next_try = 0; cs.commit_ptr = 0; }
         }
-        // ---- the propagatePatch calls (propagate.cpp:122-218) ----
-        for (int call = 0; call < nsrc; ++call) {
-            const int src = ss.src_id[call];
+        cell_sync();
+        const int ntries = 2 * cs.nsrc;                                                    // MAX_NUM_OF_PROPAG tries per call
+        // ================= the propagatePatch tries (propagate.cpp:122-218), speculative, committed in order =================
+        while (true) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&cs.next_try, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= ntries) break;
+            const int call = t >> 1, k = t & 1;
+            const int src = cs.src_id[call];
             const V4 sX = f4v(st.coord[src]), sN = f4v(st.normal[src]);
             const int sref = st.images[(size_t)src * st.maxv];
             const int snv = min(st.nimg[src], CAND_MAXV);
             // one PMR1 stream per call: (iter, view, dest cell, call ordinal)
             const uint64_t stream = ((uint64_t)(unsigned)sa.iter << 56) ^ ((uint64_t)(unsigned)img << 40) ^ ((uint64_t)(unsigned)(y * gw + x) << 8) ^ (uint64_t)call;
-            stat[SS_CALLS] += 1;
-            for (int k = 0; k < 2; ++k) {                                                   // MAX_NUM_OF_PROPAG
-                stat[SS_TRIES] += 1;
-                const int np = nl;
-                V3 ic;
-                float wncc = 0.0f;
-                if (np < maxp) {
-                    float jx = sa.jitter[2 * k], jy = sa.jitter[2 * k + 1];
-                    if (sa.jitter_mode == 1) {
-                        uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), 0x4a495454u, (uint32_t)k};
-                        philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
-                        jx = (float)(0.5 * uniform_pm1(ctr[0])); jy = (float)(0.5 * uniform_pm1(ctr[1]));
-                    }
-                    const float cxf = (float)(p.csize * (2 * x + 1) - 1) / 2.0f, cyf = (float)(p.csize * (2 * y + 1) - 1) / 2.0f;
-                    ic = V3{xadd(cxf, xmul(jx, (float)p.csize)), xadd(cyf, xmul(jy, (float)p.csize)), xadd(1.0f, 0.0f)};
-                } else {
-                    const int w = ss.l_id[maxp - 1];
-                    wncc = ss.l_ncc[maxp - 1];
-                    ic = project(vimgc.P, f4v(st.coord[w]));
-                }
-                // ---- generatePatch (propagate.cpp:220-237) ----
-                const ViewConst& vr = p.views[sref];
-                const float depth = dot4(ld4(vr.oaxis), sX);
-                const float b0 = xsub(xmul(depth, ic.x), vr.P[3]), b1 = xsub(xmul(depth, ic.y), vr.P[7]), b2 = xsub(xmul(depth, ic.z), vr.P[11]);
-                V4 X, N = sN;                                                              // Camera::unproject (camera.cpp:329-337)
-                X.x = xadd(xadd(xmul(vr.Minv[0], b0), xmul(vr.Minv[1], b1)), xmul(vr.Minv[2], b2));
-                X.y = xadd(xadd(xmul(vr.Minv[4], b0), xmul(vr.Minv[5], b1)), xmul(vr.Minv[6], b2));
-                X.z = xadd(xadd(xmul(vr.Minv[8], b0), xmul(vr.Minv[9], b1)), xmul(vr.Minv[10], b2));
-                X.w = 1.0f;
-                int nv = 0;                                                                // setGridsImages (patch_manager.cpp:223-239)
-                for (int base = 0; base < snv; base += 32) {
-                    const int i = base + lane;
-                    bool keep = false;
-                    int v = 0;
-                    if (i < snv) {
-                        v = st.images[(size_t)src * st.maxv + i];
-                        const V3 q = project(p.views[v].P, X);
-                        const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
-                        keep = 0 <= ix && ix < p.views[v].gw && 0 <= iy && iy < p.views[v].gh;
-                    }
-                    const unsigned msk = __ballot_sync(0xffffffffu, keep);
-                    if (keep) ws.images[nv + __popc(msk & ((1u << lane) - 1u))] = v;
-                    nv += __popc(msk);
-                }
-                __syncwarp();
-                if (nv == 0) { stat[SS_GEN_NULL] += 1; continue; }
-                float ncc = warp_compute_ncc<WS>(p, ws, X, N, nv, lane);
-                ncc = __shfl_sync(0xffffffffu, ncc, 0);
-                stat[SS_EVALS] += 1;
-                if (np >= maxp && ncc < wncc) { stat[SS_NCC_LOSE] += 1; continue; }
-                // ---- patch optimisation (propagate.cpp:176-193) ----
-                float dscale, ascale;
-                if (warp_pre_process<WS>(cp, ws, X, N, nv, dscale, ascale, lane) == -1) { stat[SS_FAIL0] += 1; continue; }
-                ncc = warp_refine<WS>(cp, ws, X, N, nv, dscale, stream, nullptr, lane);
-                ncc = __shfl_sync(0xffffffffu, ncc, 0);
-                X = V4{__shfl_sync(0xffffffffu, X.x, 0), __shfl_sync(0xffffffffu, X.y, 0), __shfl_sync(0xffffffffu, X.z, 0), __shfl_sync(0xffffffffu, X.w, 0)};
-                N = V4{__shfl_sync(0xffffffffu, N.x, 0), __shfl_sync(0xffffffffu, N.y, 0), __shfl_sync(0xffffffffu, N.z, 0), 0.0f};
-                stat[SS_EVALS] += PMR1_EVALS + 1;
-                int r = warp_post_process<WS>(cp, ws, X, N, nv, gwarp, lane);
-                int nvv = 0;
-                float tmp = 0.0f;
-                if (r == 0) {
-                    for (int i = lane; i < nv; i += 32) {                                  // setGrids (optim.cpp:285)
-                        const V3 q = project(p.views[ws.images[i]].P, X);
-                        ss.cells[i] = pack_cell(cell_of(q.x, p.csize), cell_of(q.y, p.csize));
+            Cand cd;
+            cd.nv = 0; cd.nvv = 0; cd.ncc = 0.f; cd.dscale = 0.f; cd.ascale = 0.f; cd.tmp = 0.f;
+            cd.X = V4{0.f, 0.f, 0.f, 1.f}; cd.N = sN;
+            int outcome = TRY_GEN_NULL;
+            bool have_turn = false;
+            TrySnap sn;
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                sn = take_snapshot(cs, ss.l_snap, maxp, lane);
+                // ---------------- stage A: everything up to postProcess's store-independent part ----------------
+                {
+                    V3 ic;
+                    if (sn.np < maxp) {
+                        float jx = sa.jitter[2 * k], jy = sa.jitter[2 * k + 1];
+                        if (sa.jitter_mode == 1) {
+                            uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), 0x4a495454u, (uint32_t)k};
+                            philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
+                            jx = (float)(0.5 * uniform_pm1(ctr[0])); jy = (float)(0.5 * uniform_pm1(ctr[1]));
+                        }
+                        const float cxf = (float)(p.csize * (2 * x + 1) - 1) / 2.0f, cyf = (float)(p.csize * (2 * y + 1) - 1) / 2.0f;
+                        ic = V3{xadd(cxf, xmul(jx, (float)p.csize)), xadd(cyf, xmul(jy, (float)p.csize)), xadd(1.0f, 0.0f)};
+                    } else ic = project(vimgc.P, f4v(st.coord[sn.w]));
+                    // ---- generatePatch (propagate.cpp:220-237) ----
+                    const ViewConst& vr = p.views[sref];
+                    const float depth = dot4(ld4(vr.oaxis), sX);
+                    const float b0 = xsub(xmul(depth, ic.x), vr.P[3]), b1 = xsub(xmul(depth, ic.y), vr.P[7]), b2 = xsub(xmul(depth, ic.z), vr.P[11]);
+                    V4 X, N = sN;                                                              // Camera::unproject (camera.cpp:329-337)
+                    X.x = xadd(xadd(xmul(vr.Minv[0], b0), xmul(vr.Minv[1], b1)), xmul(vr.Minv[2], b2));
+                    X.y = xadd(xadd(xmul(vr.Minv[4], b0), xmul(vr.Minv[5], b1)), xmul(vr.Minv[6], b2));
+                    X.z = xadd(xadd(xmul(vr.Minv[8], b0), xmul(vr.Minv[9], b1)), xmul(vr.Minv[10], b2));
+                    X.w = 1.0f;
+                    int nv = 0;                                                                // setGridsImages (patch_manager.cpp:223-239)
+                    for (int base = 0; base < snv; base += 32) {
+                        const int i = base + lane;
+                        bool keep = false;
+                        int v = 0;
+                        if (i < snv) {
+                            v = st.images[(size_t)src * st.maxv + i];
+                            const V3 q = project(p.views[v].P, X);
+                            const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
+                            keep = 0 <= ix && ix < p.views[v].gw && 0 <= iy && iy < p.views[v].gh;
+                        }
+                        const unsigned msk = __ballot_sync(0xffffffffu, keep);
+                        if (keep) ws.images[nv + __popc(msk & ((1u << lane) - 1u))] = v;
+                        nv += __popc(msk);
                     }
                     __syncwarp();
-                    tmp = xmul(max_std(0.0f, xsub(ncc, p.ncc_threshold)), (float)nv);      // m_tmp = score2 (optim.cpp:288)
-                    if (p.depth) nvv = warp_set_vimages(sp, ws, X, N, ws.images, nv, ss.vimg, ss.vcell, 0, lane);   // :290-292
-                    if (2 <= p.depth) {                                                    // Optim::check (optim.cpp:300-323)
-                        PGeo me; me.X = X; me.N = N; me.dscale = dscale; me.ref = ws.images[0];
-                        const PatchLists pl{ws.images, ss.cells, nv, ss.vimg, ss.vcell, nvv};
-                        const Overlay ov{cD, ss.l_id, nl, ss.removed, nrem};
-                        const float gain = warp_compute_gain(sp, me, ncc, pl, ov, lane);
-                        tmp = gain;
-                        if (gain < 0.0f) r = -1;
+                    outcome = TRY_GEN_NULL;
+                    if (nv > 0) {
+                        float ncc = warp_compute_ncc<WS>(p, ws, X, N, nv, lane);
+                        ncc = __shfl_sync(0xffffffffu, ncc, 0);
+                        if (sn.np >= maxp && ncc < sn.wncc) outcome = TRY_LOSE;
                         else {
-                            int* nb = sp.nb_scratch + (size_t)gwarp * NB_STRIDE;
-                            const int nn = warp_find_neighbors(sp, me, pl, 4.0f, 2, ov, nb, lane);
-                            if (6 < nn && warp_filter_quad(sp, me, pl, nb, nn, nullptr, lane)) r = -1;
+                            // ---- patch optimisation (propagate.cpp:176-193) ----
+                            float dscale, ascale;
+                            if (warp_pre_process<WS>(cp, ws, X, N, nv, dscale, ascale, lane) == -1) outcome = TRY_FAIL0;
+                            else {
+                                ncc = warp_refine<WS>(cp, ws, X, N, nv, dscale, stream, nullptr, lane);
+                                ncc = __shfl_sync(0xffffffffu, ncc, 0);
+                                X = V4{__shfl_sync(0xffffffffu, X.x, 0), __shfl_sync(0xffffffffu, X.y, 0), __shfl_sync(0xffffffffu, X.z, 0), __shfl_sync(0xffffffffu, X.w, 0)};
+                                N = V4{__shfl_sync(0xffffffffu, N.x, 0), __shfl_sync(0xffffffffu, N.y, 0), __shfl_sync(0xffffffffu, N.z, 0), 0.0f};
+                                const int r = warp_post_process<WS>(cp, ws, X, N, nv, gwarp, lane);
+                                outcome = r == 0 ? TRY_ACCEPT : TRY_FAIL1;
+                                cd.X = X; cd.N = N; cd.nv = nv; cd.ncc = ncc; cd.dscale = dscale; cd.ascale = ascale;
+                                if (r == 0) {
+                                    for (int i = lane; i < nv; i += 32) {                      // setGrids (optim.cpp:285)
+                                        const V3 q = project(p.views[ws.images[i]].P, X);
+                                        ss.cells[i] = pack_cell(cell_of(q.x, p.csize), cell_of(q.y, p.csize));
+                                    }
+                                    __syncwarp();
+                                }
+                            }
                         }
                     }
                 }
-                if (r == -1) { stat[SS_FAIL1] += 1; continue; }
+                bool post_ok = outcome == TRY_ACCEPT;
+                // ---------------- stage B (needs the list): setVImagesVGrids, check (optim.cpp:288-296) ----------------
+                bool stage_b_done = false;
+                while (true) {
+                    if (post_ok && !stage_b_done) {
+                        outcome = TRY_ACCEPT;
+                        cd.tmp = xmul(max_std(0.0f, xsub(cd.ncc, p.ncc_threshold)), (float)cd.nv);      // m_tmp = score2
+                        cd.nvv = 0;
+                        if (p.depth) cd.nvv = warp_set_vimages(sp, ws, cd.X, cd.N, ws.images, cd.nv, ss.vimg, ss.vcell, 0, lane);
+                        if (2 <= p.depth) {                                                    // Optim::check (optim.cpp:300-323)
+                            PGeo me; me.X = cd.X; me.N = cd.N; me.dscale = cd.dscale; me.ref = ws.images[0];
+                            const PatchLists pl{ws.images, ss.cells, cd.nv, ss.vimg, ss.vcell, cd.nvv};
+                            const Overlay ov{cD, ss.l_snap, min(sn.np, LIST_MAX), cs.removed, sn.nrem};
+                            const float gain = warp_compute_gain(sp, me, cd.ncc, pl, ov, lane);
+                            cd.tmp = gain;
+                            if (gain < 0.0f) outcome = TRY_FAIL1;
+                            else {
+                                int* nb = sp.nb_scratch + (size_t)gwarp * NB_STRIDE;
+                                const int nn = warp_find_neighbors(sp, me, pl, 4.0f, 2, ov, nb, lane);
+                                if (6 < nn && warp_filter_quad(sp, me, pl, nb, nn, nullptr, lane)) outcome = TRY_FAIL1;
+                            }
+                        }
+                        stage_b_done = true;
+                    }
+                    if (have_turn) break;
+                    // ---------------- wait for this try's turn ----------------
+                    while (ld_shared_volatile(&cs.commit_ptr) != t) __nanosleep(100);
+                    have_turn = true;
+                    __syncwarp();
+                    if (ld_shared_volatile(&cs.version) == sn.ver) break;                    // nothing committed since the snapshot
+                    // the list changed: are the snapshot's assumptions still true?
+                    const int np_now = ld_shared_volatile(&cs.nl);
+                    const bool same_branch = (sn.np < maxp) == (np_now < maxp);
+                    const bool same_worst = np_now < maxp || ld_shared_volatile(&cs.l_id[maxp - 1]) == sn.w;
+                    if (!(same_branch && same_worst)) { stage_b_done = false; post_ok = false; outcome = -1; break; }   // redo stage A
+                    sn = take_snapshot(cs, ss.l_snap, maxp, lane);                            // stage A stands; stage B reads the list
+                    if (post_ok && p.depth >= 2) stage_b_done = false; else break;
+                }
+                if (outcome >= 0) break;
+            }
+            // ================= commit (this warp holds the turn) =================
+            stat[SS_CALLS] += (k == 0) ? 1 : 0;
+            stat[SS_TRIES] += 1;
+            if (outcome != TRY_GEN_NULL) stat[SS_EVALS] += 1;
+            if (outcome == TRY_FAIL1 || outcome == TRY_ACCEPT) stat[SS_EVALS] += PMR1_EVALS + 1;
+            if (outcome == TRY_GEN_NULL) stat[SS_GEN_NULL] += 1;
+            else if (outcome == TRY_LOSE) stat[SS_NCC_LOSE] += 1;
+            else if (outcome == TRY_FAIL0) stat[SS_FAIL0] += 1;
+            else if (outcome == TRY_FAIL1) stat[SS_FAIL1] += 1;
+            else {
                 // ---- removePatch(worst) / addPatch(new) (propagate.cpp:195-207); grid updates are staged ----
-                if (np == maxp) {
-                    const int w = ss.l_id[maxp - 1];
-                    if (w >= st.cap) { if (lane == 0) st.state[w] = 0; }                   // staged this step: never reaches the grids
-                    else { if (lane == 0) ss.removed[nrem] = w; ++nrem; }
+                int nl = cs.nl;
+                if (lane == 0) { cs.version = sn.ver + 1; }
+                __threadfence_block();
+                if (nl == maxp) {
+                    const int w = cs.l_id[maxp - 1];
+                    if (w >= st.cap) { if (lane == 0) st.state[w] = 0; }                       // staged this step: never reaches the grids
+                    else if (lane == 0) { cs.removed[cs.nrem] = w; cs.nrem = cs.nrem + 1; }
                     --nl;
                     stat[SS_REPLACED] += 1;
                 } else stat[SS_ADDED] += 1;
                 __syncwarp();
-                const int sid = st.cap + task * NEW_MAX + nnew;
-                ++nnew;
+                const int sid = st.cap + task * NEW_MAX + cs.nnew;
+                __syncwarp();
                 if (lane == 0) {
-                    st.coord[sid] = v4f(X); st.normal[sid] = v4f(N);
-                    st.scal[sid] = make_float4(ncc, dscale, ascale, tmp);
-                    st.nimg[sid] = nv; st.nvimg[sid] = nvv; st.state[sid] = 1;
+                    cs.nnew = cs.nnew + 1;
+                    st.coord[sid] = v4f(cd.X); st.normal[sid] = v4f(cd.N);
+                    st.scal[sid] = make_float4(cd.ncc, cd.dscale, cd.ascale, cd.tmp);
+                    st.nimg[sid] = cd.nv; st.nvimg[sid] = cd.nvv; st.state[sid] = 1;
                     st.birth[sid] = 0xffffffffu;
                 }
                 bool inD = false;
-                for (int i = lane; i < nv; i += 32) {
+                for (int i = lane; i < cd.nv; i += 32) {
                     st.images[(size_t)sid * st.maxv + i] = ws.images[i];
                     st.cells[(size_t)sid * st.maxv + i] = ss.cells[i];
                     if (ws.images[i] == img && cell_x(ss.cells[i]) == x && cell_y(ss.cells[i]) == y) inD = true;
                 }
-                for (int i = lane; i < nvv; i += 32) {
+                for (int i = lane; i < cd.nvv; i += 32) {
                     st.vimages[(size_t)sid * st.maxv + i] = ss.vimg[i];
                     st.vcells[(size_t)sid * st.maxv + i] = ss.vcell[i];
                 }
                 inD = __any_sync(0xffffffffu, inD);
-                if (inD) {
-                    if (lane == 0) { ss.l_id[nl] = sid; ss.l_ncc[nl] = ncc; }
-                    ++nl;
-                    __syncwarp();
-                    if (lane == 0) swap_sort_desc(ss.l_id, ss.l_ncc, nl);
+                if (lane == 0) {
+                    if (inD) { cs.l_id[nl] = sid; cs.l_ncc[nl] = cd.ncc; ++nl; swap_sort_desc(cs.l_id, cs.l_ncc, nl); }
+                    cs.nl = nl;
+                    __threadfence_block();
+                    cs.version = sn.ver + 2;
                 }
                 __syncwarp();
             }
+            __threadfence_block();
+            if (lane == 0) cs.commit_ptr = t + 1;
+            __syncwarp();
         }
+        cell_sync();
         // ---- hand the step's mutations to k4_apply ----
-        if (lane == 0) sa.task_new[task] = nnew;
-        if (nrem > 0) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(st.counters + SC_REM, nrem);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (int i = lane; i < nrem; i += 32) sa.rem_list[base + i] = ss.removed[i];
+        if (warp == 0) {
+            const int nrem = cs.nrem;
+            if (lane == 0) sa.task_new[task] = cs.nnew;
+            if (nrem > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(st.counters + SC_REM, nrem);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int i = lane; i < nrem; i += 32) sa.rem_list[base + i] = cs.removed[i];
+            }
         }
-        __syncwarp();
+        cell_sync();
     }
     if (lane == 0)
 #pragma unroll
-        for (int i = 0; i < SS_COUNT; ++i) if (stat[i]) atomicAdd(sa.stats + i, stat[i]);
+        for (int i = 0; i < SS_COUNT; ++i) if (stat[i]) atomicAdd(sa.stats + i, (unsigned long long)stat[i]);
 }
 
 // ---- apply: removals ---------------------------------------------------------------------------------------------------------------
