@@ -43,6 +43,18 @@ def env_int(name, default):
         return default
 
 
+def load_traffic(n_per_launch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        per_hyp = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["hypotheses_per_launch"]
+        return per_hyp * n_per_launch, t["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -435,7 +447,9 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches_timed),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c.nbytes + n.nbytes + vw.nbytes + nv.nbytes),
                     "d2h_bytes_per_step": int(2 * N * 4), "ms_per_step": total_e2e / args.steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(N)[0],
+                         "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": load_traffic(N)[1],
+                         "algorithmic_bytes_per_launch": algo_bytes * N,
                          "kernel": "k1_ncc<7,4>", "algorithmic_bytes_per_eval": algo_bytes, "valid_views_per_eval": valid_views,
                          "layout_bytes_per_eval": layout_bytes, "achieved_layout": per_gpu * layout_bytes / 1e9, "frac_layout": per_gpu * layout_bytes / 1e9 / peak,
                          "note": "not HBM-bound: the pyramid stays L2/L1 resident; binding units per ncu (profiles/): L1TEX data pipe ~71%, issue slots ~74%", "peak_source": peak_src,
