@@ -81,7 +81,8 @@ struct pmk_ctx {
     pmk_config cfg;
     pmk_store* store = nullptr;             // device patch store (pmk_store_host.cuh), created on first use
     cudaStream_t stream = nullptr;
-    cudaStream_t s_in = nullptr, s_out = nullptr;        // copy streams of the chunked host-buffer NCC call
+    cudaStream_t s_in = nullptr, s_out = nullptr;        // copy streams of the chunked host-buffer NCC call (s_in doubles as the sweep's second stream)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
@@ -223,7 +224,7 @@ int cand_params(pmk_ctx* ctx, CandParams& cp, uint64_t seed) {
     const int ws = ctx->cfg.wsize, texw = ws * ws * 3 + 4;
     if (!ctx->cand_grid) {
         ctx->cand_grid = ctx->sm_count * 4;
-        const size_t warps = (size_t)ctx->cand_grid * CAND_WARPS;
+        const size_t warps = (size_t)ctx->cand_grid * CAND_WARPS * 2;   // x2: the sweep runs two kernels side by side (heavy / light dest cells)
         CUDA_TRY(cudaMalloc((void**)&ctx->tex_scratch, warps * ctx->cfg.nviews * texw * sizeof(float)));
         CUDA_TRY(cudaMalloc((void**)&ctx->mat_scratch, warps * ctx->cfg.nviews * ctx->cfg.nviews * sizeof(float)));
         ctx->owned.push_back(ctx->tex_scratch);
@@ -316,6 +317,8 @@ int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     ctx->h_views.resize(cfg->nviews);
@@ -351,7 +354,7 @@ void pmk_destroy(pmk_ctx* ctx) {
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     cudaFree(ctx->d_views);
     cudaFree(ctx->d_counters);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_k) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);

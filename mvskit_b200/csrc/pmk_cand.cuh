@@ -151,8 +151,11 @@ __device__ __forceinline__ void encode(const CandParams& cp, const RefineCtx& rc
 
 // ---- Optim::cost_func (optim.cpp:401-468) by one evaluator group -------------------------------------------------------------
 // views/sz: m_indexes (first min(tau, n) entries are used).  Returns the cost as the reference's double.
+#ifndef PMK_COST_INLINE
+#define PMK_COST_INLINE __forceinline__
+#endif
 template <int WS, int GW>
-__device__ __forceinline__ double group_cost(const CandParams& cp, const RefineCtx& rc, const double x[3], const int* views, int nimages,
+__device__ PMK_COST_INLINE double group_cost(const CandParams& cp, const RefineCtx& rc, const double x[3], const int* views, int nimages,
                                              int col, float cmask, unsigned gm) {
     const Params& p = cp.p;
     V4 coord, normal, px, py;
@@ -216,8 +219,11 @@ __device__ __forceinline__ void compute_weights(const Params& p, V4 X, V4 N, con
 }
 
 // ---- Optim::setINCCs 1-vs-all (optim.cpp:708-746): inccs[i] for images[0..n), views spread over the groups -------------------
+#ifndef PMK_INCCS_INLINE
+#define PMK_INCCS_INLINE __forceinline__
+#endif
 template <int WS, int GW>
-__device__ __forceinline__ void warp_set_inccs(const Params& p, V4 X, V4 N, const int* views, int n, int robust, float* inccs,
+__device__ PMK_INCCS_INLINE void warp_set_inccs(const Params& p, V4 X, V4 N, const int* views, int n, int robust, float* inccs,
                                                int lane) {
     constexpr int G = 32 / GW;
     const int grp = lane / GW, col = lane % GW;

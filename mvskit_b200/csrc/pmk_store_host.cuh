@@ -22,7 +22,7 @@ struct pmk_store {
     int* cell_base_d = nullptr;
     std::vector<int> cell_base;         // host copy
     // scratch
-    int* rem_list = nullptr; int* task_new = nullptr; int* final_id = nullptr;
+    int* rem_list = nullptr; int* task_new = nullptr; int* final_id = nullptr; int* order = nullptr;
     unsigned long long* stats = nullptr;
     unsigned long long* keys = nullptr; unsigned long long* keys2 = nullptr;
     int* vals = nullptr; int* vals2 = nullptr;
@@ -112,15 +112,15 @@ int store_init(pmk_ctx* ctx) {
         return rc;
     d.cell_base = s->cell_base_d;
     CUDA_TRY(cudaMemcpyAsync(s->cell_base_d, s->cell_base.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = dalloc(ctx, &s->rem_list, d.cap)) || (rc = dalloc(ctx, &s->task_new, s->max_tasks)) || (rc = dalloc(ctx, &s->final_id, d.stage_cap)) ||
+    if ((rc = dalloc(ctx, &s->rem_list, d.cap)) || (rc = dalloc(ctx, &s->task_new, s->max_tasks)) || (rc = dalloc(ctx, &s->order, s->max_tasks + 1)) || (rc = dalloc(ctx, &s->final_id, d.stage_cap)) ||
         (rc = dalloc(ctx, &s->stats, SS_COUNT)) || (rc = dalloc(ctx, &s->keys, d.cap)) || (rc = dalloc(ctx, &s->keys2, d.cap)) ||
         (rc = dalloc(ctx, &s->vals, d.cap)) || (rc = dalloc(ctx, &s->vals2, d.cap)) || (rc = dalloc(ctx, &s->f_tmp, d.cap)) ||
         (rc = dalloc(ctx, &s->i_tmp, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp2, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp3, d.cap + 1)) || (rc = dalloc(ctx, &s->small, 16)))
         return rc;
     CandParams cp;
     if ((rc = cand_params(ctx, cp, 0))) return rc;                       // sizes cand_grid and the pairwise scratch
-    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * NB_STRIDE))) return rc;
-    CUDA_TRY(cudaMemsetAsync(s->nb_scratch, 0, (size_t)ctx->cand_grid * CAND_WARPS * NB_STRIDE * sizeof(int), ctx->stream));
+    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * 2 * NB_STRIDE))) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->nb_scratch, 0, (size_t)ctx->cand_grid * CAND_WARPS * 2 * NB_STRIDE * sizeof(int), ctx->stream));
     s->gather_bytes = (size_t)d.cap * d.maxv * sizeof(int);
     s->gather_bytes = std::max(s->gather_bytes, (size_t)d.cap * sizeof(float4));
     CUDA_TRY(cudaMalloc(&s->gather_tmp, s->gather_bytes));
@@ -391,7 +391,30 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     const int cpc = CAND_WARPS / sa.wpc;
     const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + cpc - 1) / cpc));
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
-    if (sa.ntasks > 0) { k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, sa); ctx->launches++; }
+    if (sa.ntasks > 0) {
+        SweepArgs a = sa;
+        a.heavy_slot = s->max_tasks;
+        a.wslot_base = 0;
+        k4_plan<<<1, 1024, 0, st>>>(sp, a, s->order);
+        ctx->launches++;
+        if (a.wpc > 1 || sa.split == 0) {                 // narrow step (or splitting disabled): one launch
+            a.range_sel = 0;
+            k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, a);
+            ctx->launches++;
+        } else {
+            // wide step: the dest cells with many tries (they end the step) get four warps each on the context stream, the rest
+            // one warp each on a second stream; both read the same snapshot and stage into disjoint slots
+            CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_fork, 0));
+            a.range_sel = 1; a.wpc = 4;
+            k4_sweep<WS><<<std::max(1, std::min(ctx->cand_grid, sa.ntasks)), CAND_WARPS * 32, smem, st>>>(sp, a);
+            a.range_sel = 2; a.wpc = 1; a.wslot_base = ctx->cand_grid * CAND_WARPS;
+            k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, ctx->s_in>>>(sp, a);
+            CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+            ctx->launches += 2;
+        }
+    }
     if (s->nranks <= 1) {
         k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
         k4_apply_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
@@ -429,7 +452,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     sa.inc = inc; sa.iter = iter;
     sa.jitter_mode = ctx->cfg.jitter_mode;
     for (int i = 0; i < 4; ++i) sa.jitter[i] = s->jitter[i];
-    sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats;
+    sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order;
     int max_steps = 0;
     for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
     for (int k = step_first; k < step_first + step_count && k < max_steps; ++k) {
@@ -457,6 +480,8 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
             const int resident = ctx->sm_count * PMK_SWEEP_MINB * CAND_WARPS;        // warps in flight
             sa.wpc = sa.ntasks * 4 <= resident ? 4 : (sa.ntasks * 2 <= resident ? 2 : 1);
             if (forced == 1 || forced == 2 || forced == 4) sa.wpc = forced;
+            static const int nosplit = getenv("PMK_SWEEP_NOSPLIT") ? 1 : 0;
+            sa.split = nosplit ? 0 : 1;
         }
         WS_DISPATCH(ctx->cfg.wsize, { if ((rc = launch_sweep<WS>(ctx, sp, sa))) return rc; });
     }

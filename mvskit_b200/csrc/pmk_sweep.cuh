@@ -33,6 +33,11 @@ struct SweepArgs {
     float jitter[4];
     int* rem_list;                         // patches removed this step (SC_REM counts them)
     int* task_new;                         // [max_tasks] staged entries used by each task
+    const int* order;                      // [ntasks] task ids, most expensive first (k4_plan); order[max_tasks] = number of heavy tasks
+    int heavy_slot;                        // index of that count inside `order`
+    int range_sel;                         // 0: every task, 1: the heavy prefix, 2: the light rest
+    int wslot_base;                        // first per-warp scratch slot of this launch
+    int split;                             // host: run heavy / light cells as two concurrent launches on wide steps
     unsigned long long* stats;             // SweepStat
 };
 
@@ -167,7 +172,9 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
     const CandParams& cp = sp.cp;
     const Params& p = cp.p;
     const StoreDev& st = sp.st;
-    const int gwarp = blockIdx.x * CAND_WARPS + cta_warp;
+    const int gwarp = sa.wslot_base + blockIdx.x * CAND_WARPS + cta_warp;
+    const int nheavy = sa.range_sel ? sa.order[sa.heavy_slot] : 0;
+    const int t_first = sa.range_sel == 2 ? nheavy : 0, t_last = sa.range_sel == 1 ? nheavy : sa.ntasks;
     // barrier over the warps of this cell only (the cells of a CTA run different numbers of tasks)
     auto cell_sync = [&]() {
         if (wpc == 1) __syncwarp();
@@ -179,7 +186,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
 #pragma unroll
     for (int i = 0; i < SS_COUNT; ++i) stat[i] = 0;
 
-    for (int task = blockIdx.x * cpc + cell_slot; task < sa.ntasks; task += gridDim.x * cpc) {
+    for (int tslot = t_first + blockIdx.x * cpc + cell_slot; tslot < t_last; tslot += gridDim.x * cpc) {
+        const int task = sa.order[tslot];
         int g = 0;
         while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
         const int img = sa.g_img[g];
@@ -429,6 +437,91 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
     if (lane == 0)
 #pragma unroll
         for (int i = 0; i < SS_COUNT; ++i) if (stat[i]) atomicAdd(sa.stats + i, (unsigned long long)stat[i]);
+}
+
+// ---- longest-first schedule of a step ---------------------------------------------------------------------------------------
+// A step ends with its slowest dest cell, so the cells are started in decreasing order of a cost estimate: the number of
+// propagatePatch calls aimed at the cell (patches of its two source cells whose reference view is the swept view), doubled
+// while the cell still has room (every try then runs the full optimisation instead of first having to beat the worst patch).
+// One block; counting sort on the estimate.  The order only changes WHEN a cell runs, never what it computes.
+constexpr int HEAVY_EST = 8;           // dest cells with at least this many estimated tries get four warps
+
+__global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const SweepArgs sa, int* __restrict__ order) {
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    constexpr int NBIN = 2 * SRC_MAX + 2;
+    __shared__ int hist[NBIN], offs[NBIN];
+    for (int i = threadIdx.x; i < NBIN; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int maxp = sp.max_patches_cell;
+    for (int base = 0; base < sa.ntasks; base += blockDim.x) {
+        const int task = base + threadIdx.x;
+        int est = 0;
+        if (task < sa.ntasks) {
+            int g = 0;
+            while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+            const int img = sa.g_img[g];
+            const int gw = p.views[img].gw, gh = p.views[img].gh;
+            const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
+            int nsrc = 0;
+            for (int side = 0; side < 2; ++side) {
+                const int sx = side == 0 ? x : x - sa.inc, sy = side == 0 ? y - sa.inc : y;
+                if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
+                const int c = st.cell_base[img] + sy * gw + sx;
+                const int n = min(st.ccount[c], st.cell_cap);
+                int k = 0;
+                for (int s2 = 0; s2 < n; ++s2) {
+                    const int e = st.cslots[(size_t)c * st.cell_cap + s2];
+                    if (e == SLOT_TOMB || e < 0) continue;
+                    if (st.images[(size_t)e * st.maxv] == img) ++k;
+                }
+                nsrc += min(k, maxp);
+            }
+            const int cD = st.cell_base[img] + y * gw + x;
+            int nd = 0;
+            const int n = min(st.ccount[cD], st.cell_cap);
+            for (int s2 = 0; s2 < n; ++s2) { const int e = st.cslots[(size_t)cD * st.cell_cap + s2]; if (e != SLOT_TOMB && e >= 0) ++nd; }
+            est = min(NBIN - 1, nsrc * (nd < maxp ? 2 : 1));
+            atomicAdd(&hist[est], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0, heavy = 0;
+        for (int b = NBIN - 1; b >= 0; --b) { offs[b] = acc; acc += hist[b]; if (b >= HEAVY_EST) heavy = acc; }
+        order[sa.heavy_slot] = heavy;
+    }
+    __syncthreads();
+    for (int base = 0; base < sa.ntasks; base += blockDim.x) {
+        const int task = base + threadIdx.x;
+        if (task >= sa.ntasks) continue;
+        // recompute the estimate (cheaper than keeping it: tasks can exceed the block size)
+        int g = 0;
+        while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+        const int img = sa.g_img[g];
+        const int gw = p.views[img].gw, gh = p.views[img].gh;
+        const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
+        int nsrc = 0;
+        for (int side = 0; side < 2; ++side) {
+            const int sx = side == 0 ? x : x - sa.inc, sy = side == 0 ? y - sa.inc : y;
+            if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
+            const int c = st.cell_base[img] + sy * gw + sx;
+            const int n = min(st.ccount[c], st.cell_cap);
+            int k = 0;
+            for (int s2 = 0; s2 < n; ++s2) {
+                const int e = st.cslots[(size_t)c * st.cell_cap + s2];
+                if (e == SLOT_TOMB || e < 0) continue;
+                if (st.images[(size_t)e * st.maxv] == img) ++k;
+            }
+            nsrc += min(k, maxp);
+        }
+        const int cD = st.cell_base[img] + y * gw + x;
+        int nd = 0;
+        const int n = min(st.ccount[cD], st.cell_cap);
+        for (int s2 = 0; s2 < n; ++s2) { const int e = st.cslots[(size_t)cD * st.cell_cap + s2]; if (e != SLOT_TOMB && e >= 0) ++nd; }
+        const int est = min(NBIN - 1, nsrc * (nd < maxp ? 2 : 1));
+        order[atomicAdd(&offs[est], 1)] = task;
+    }
 }
 
 // ---- apply: removals ---------------------------------------------------------------------------------------------------------------
