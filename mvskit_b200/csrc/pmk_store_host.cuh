@@ -482,6 +482,8 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
             if (forced == 1 || forced == 2 || forced == 4) sa.wpc = forced;
             static const int nosplit = getenv("PMK_SWEEP_NOSPLIT") ? 1 : 0;
             sa.split = nosplit ? 0 : 1;
+            static const int heavy_est = getenv("PMK_HEAVY_EST") ? atoi(getenv("PMK_HEAVY_EST")) : 16;
+            sa.heavy_est = heavy_est;
         }
         WS_DISPATCH(ctx->cfg.wsize, { if ((rc = launch_sweep<WS>(ctx, sp, sa))) return rc; });
     }

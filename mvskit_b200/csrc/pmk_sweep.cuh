@@ -38,6 +38,7 @@ struct SweepArgs {
     int range_sel;                         // 0: every task, 1: the heavy prefix, 2: the light rest
     int wslot_base;                        // first per-warp scratch slot of this launch
     int split;                             // host: run heavy / light cells as two concurrent launches on wide steps
+    int heavy_est;                         // dest cells with at least this many estimated full-cost tries count as heavy
     unsigned long long* stats;             // SweepStat
 };
 
@@ -444,7 +445,6 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
 // propagatePatch calls aimed at the cell (patches of its two source cells whose reference view is the swept view), doubled
 // while the cell still has room (every try then runs the full optimisation instead of first having to beat the worst patch).
 // One block; counting sort on the estimate.  The order only changes WHEN a cell runs, never what it computes.
-constexpr int HEAVY_EST = 8;           // dest cells with at least this many estimated tries get four warps
 
 __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const SweepArgs sa, int* __restrict__ order) {
     const StoreDev& st = sp.st;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const Swee
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0, heavy = 0;
-        for (int b = NBIN - 1; b >= 0; --b) { offs[b] = acc; acc += hist[b]; if (b >= HEAVY_EST) heavy = acc; }
+        for (int b = NBIN - 1; b >= 0; --b) { offs[b] = acc; acc += hist[b]; if (b >= sa.heavy_est) heavy = acc; }
         order[sa.heavy_slot] = heavy;
     }
     __syncthreads();
