@@ -1,0 +1,69 @@
+"""BASELINE.json configs[1] at FULL size (47 views 640x480): size-independent properties of the store after one
+propagate + filter pass -- invariants every surviving patch must satisfy, consistency of the stored cells with a fresh
+projection, determinism of the whole pass, and agreement of K1 with the store's own m_ncc bookkeeping."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+@pytest.fixture(scope="module")
+def full_scene():
+    import bench
+    return bench.get_scene(2, 1.0)
+
+
+def _run(scene, seeds):
+    from mvskit_b200 import pmk
+    ctx = pmk.Context(nviews=scene.nviews, sweep_group=scene.nviews)
+    ctx.set_scene(scene.P, scene.images)
+    ctx.set_depth(0); ctx.store_clear(); ctx.store_add(*seeds); ctx.set_depth(1)
+    st = ctx.propagate(0, 0x5EED0001)
+    d_prop = ctx.store_checksum()
+    counts = ctx.filter()
+    d_filt = ctx.store_checksum()
+    return ctx, st, counts, d_prop, d_filt
+
+
+def test_full_size_pass_invariants_and_determinism(full_scene):
+    from mvskit_b200 import synth
+    scene = full_scene
+    seeds = synth.seed_arrays(scene)
+    ctx, st, counts, d_prop, d_filt = _run(scene, seeds)
+    g = ctx.store_get()
+    assert g.n == counts[5] == d_filt[1] and g.n > 10 * len(seeds[0])
+    assert st["tries"] == 2 * st["calls"]
+    assert st["added"] + st["replaced"] + st["fail0"] + st["fail1"] + st["ncc_lose"] + st["gen_null"] == st["tries"]
+    # every survivor: enough views, reference view first and inside its grid, no duplicate views, finite geometry, unit-ish normal
+    assert (g.nimages >= 3).all()
+    assert np.isfinite(g.coord).all() and np.isfinite(g.normal).all() and (g.coord[:, 3] == 1).all() and (g.normal[:, 3] == 0).all()
+    assert np.abs(np.linalg.norm(g.normal[:, :3], axis=1) - 1).max() < 1e-3
+    gw, gh = ctx.grid_dims(0)
+    for i in range(0, g.n, 997):
+        k = g.nimages[i]
+        assert len(set(g.images[i, :k].tolist())) == k
+        assert (g.grids[i, :k, 0] >= 0).all() and (g.grids[i, :k, 0] < gw).all() and (g.grids[i, :k, 1] >= 0).all() and (g.grids[i, :k, 1] < gh).all()
+        both = set(g.images[i, :k].tolist()) & set(g.vimages[i, :g.nvimages[i]].tolist())
+        assert not both                                                    # m_vimages never repeats m_images (patch_manager.cpp:267-301)
+    # stored cells == setGrids of the stored coordinate, for the reference view of every patch
+    pr = ctx.probe(g.images[:, 0].copy(), g.coord)
+    assert np.array_equal(pr["cell"], g.grids[:, 0])
+    # the sphere is where the patches are: on-sphere survivors sit within 2.5e-3 of the scene scale of r = 1
+    r = np.linalg.norm(g.coord[:, :3], axis=1)
+    on = np.abs(r - 1.0) < 0.05
+    assert on.mean() > 0.4 and np.quantile(np.abs(r[on] - 1.0) / scene.scene_scale, 0.9) < 2.5e-3
+    ctx.close()
+    # determinism: a second context, same seeds and seed value -> the same store after propagate and after filter
+    ctx2, st2, counts2, d_prop2, d_filt2 = _run(scene, seeds)
+    assert (d_prop2, d_filt2, counts2) == (d_prop, d_filt, counts) and st2 == st
+    # Filter::run on an already filtered store only removes what the lower depth-map occupancy newly exposes: a small fraction
+    again = ctx2.filter()
+    assert again[0] == counts[5] and again[5] >= 0.9 * again[0]
+    ctx2.close()
