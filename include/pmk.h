@@ -53,7 +53,7 @@ typedef struct pmk_config {
     float max_angle_threshold;  /* Option::m_maxAngleThreshold, radians                            */
     float quad_threshold;       /* Option::m_quadThreshold                                         */
     int max_patches;            /* capacity of the device patch store; 0 = 4 per cell of all views */
-    int cell_capacity;          /* slots per grid cell (m_pgrids + m_vpgrids entries); 0 = 96, at most 128 */
+    int cell_capacity;          /* slots per grid cell (m_pgrids + m_vpgrids entries); 0 = max(96, 4 * nviews) capped at 1024 */
     int jitter_mode;            /* 0: the reference's pixel jitter (propagate.cpp:139-141 re-seeds its engine on every
                                    call, so it is the same four draws each time); 1: Philox4x32 per (iter, view, cell, call, try) */
     int sweep_group;            /* views whose wavefronts advance together in Propagate::run: 1 = one view after the other like

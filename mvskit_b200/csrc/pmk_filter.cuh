@@ -276,16 +276,34 @@ __global__ void k_store_add(const StoreParams sp, int first, int n, unsigned int
     for (int k = gwarp; k < n; k += nwarps) {
         const int q = first + k;
         const V4 X = f4v(st.coord[q]);
-        const int ni = st.nimg[q];
-        for (int i = lane; i < ni; i += 32) {
-            const V3 ic = project(p.views[st.images[(size_t)q * st.maxv + i]].P, X);
-            st.cells[(size_t)q * st.maxv + i] = pack_cell(cell_of(ic.x, p.csize), cell_of(ic.y, p.csize));
+        // setGrids (patch_manager.cpp:241-249).  The reference then indexes m_pgrids with whatever cell comes out; a view whose
+        // projection falls outside its grid would be an out-of-bounds write there, so such views are dropped from the list the way
+        // setGridsImages does (patch_manager.cpp:223-239), keeping the order of the rest.
+        int ni = 0;
+        const int ni0 = min(st.nimg[q], st.maxv);
+        for (int base = 0; base < ni0; base += 32) {
+            const int i = base + lane;
+            bool keep = false;
+            int v = 0, cell = 0;
+            if (i < ni0) {
+                v = st.images[(size_t)q * st.maxv + i];
+                const V3 ic = project(p.views[v].P, X);
+                const int ix = cell_of(ic.x, p.csize), iy = cell_of(ic.y, p.csize);
+                keep = 0 <= ix && ix < p.views[v].gw && 0 <= iy && iy < p.views[v].gh;
+                cell = pack_cell(ix, iy);
+            }
+            const unsigned msk = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) { const int pos = ni + __popc(msk & ((1u << lane) - 1u)); st.images[(size_t)q * st.maxv + pos] = v; st.cells[(size_t)q * st.maxv + pos] = cell; }
+            ni += __popc(msk);
+            __syncwarp();
         }
+        if (lane == 0) st.nimg[q] = ni;
         if (lane == 0) {
             float4 sc = st.scal[q];
             sc.w = xmul(max_std(0.0f, xsub(sc.x, p.ncc_threshold)), (float)ni);
             st.scal[q] = sc;
-            st.nvimg[q] = 0; st.state[q] = 1; st.birth[q] = birth0 + (unsigned int)k;
+            st.nvimg[q] = 0; st.state[q] = ni > 0 ? 1 : 0; st.birth[q] = birth0 + (unsigned int)k;
         }
         __syncwarp();
         const bool deep = p.depth != 0;

@@ -23,7 +23,6 @@ namespace pmk {
 
 constexpr int SLOT_TOMB = 0x7fffffff;
 constexpr unsigned SLOT_V = 0x80000000u;
-constexpr int LIST_MAX = 128;          // longest dest-cell list the sweep keeps in shared memory (>= cell capacity)
 constexpr int NEW_MAX = 32;            // new patches one dest cell can stage in one wavefront step (2 per call, 16 calls)
 constexpr int SRC_MAX = 32;            // source patches feeding one dest cell (two cells of <= MAX_NUM_OF_PATCHES)
 constexpr int NB_CAP = 4096;           // findNeighbors scratch per warp (2 * NB_CAP ints: list + sort buffer)

@@ -86,29 +86,37 @@ int store_init(pmk_ctx* ctx) {
     StoreDev& d = s->d;
     d.total_cells = s->cell_base[nv];
     d.maxv = nv;
-    d.cell_cap = ctx->cfg.cell_capacity > 0 ? ctx->cfg.cell_capacity : 96;
-    if (d.cell_cap > LIST_MAX) return fail(PMK_ERR_ARG, "pmk: cell_capacity exceeds 128");
-    if (ctx->cfg.max_patches > 0) d.cap = ctx->cfg.max_patches;
-    else {
-        // one iteration creates up to ~1.5 patches per cell before Filter::run compacts the store; removed patches keep their
-        // slot until then.  Default: 4 per cell of all views, at most half of the free device memory.
-        size_t free_b = 0, total_b = 0;
-        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_patch = 3 * 16 + 4 * 4 + 4 * (size_t)nv * 4 + 48;
-        const size_t by_mem = free_b / 2 / per_patch;
-        d.cap = (int)std::min<size_t>(std::min<size_t>((size_t)4 * d.total_cells, by_mem), (size_t)0x3fffffff);
-    }
+    // a cell holds its m_pgrids entries (every view that matches the surface adds its patches until the cell's own sweep trims
+    // it) and its m_vpgrids entries (views that see the surface without matching it): both grow with the number of views
+    d.cell_cap = ctx->cfg.cell_capacity > 0 ? ctx->cfg.cell_capacity : std::min(1024, std::max(96, 4 * nv));
+    if (d.cell_cap > 1024) return fail(PMK_ERR_ARG, "pmk: cell_capacity exceeds 1024");
+    // grids first (their size is fixed by the views), then the patch arrays from what is left of the device memory
+    if ((rc = dalloc(ctx, &d.ccount, d.total_cells)) || (rc = dalloc(ctx, &d.cslots, (size_t)d.total_cells * d.cell_cap)) ||
+        (rc = dalloc(ctx, &d.dmap, d.total_cells)))
+        return rc;
     s->group = ctx->cfg.sweep_group <= 0 ? 1 : std::min(std::min(ctx->cfg.sweep_group, nv), (int)GROUP_MAX);
     s->max_tasks = max_diag * s->group;
     d.stage_cap = s->max_tasks * NEW_MAX;
+    const size_t per_patch = 3 * 16 + 4 * 4 + 4 * (size_t)nv * 4 + 64;          // store arrays + sort / scratch words per patch
+    if (ctx->cfg.max_patches > 0) d.cap = ctx->cfg.max_patches;
+    else {
+        // one iteration creates up to ~1.5 patches per cell before Filter::run compacts the store; removed patches keep their
+        // slot until then.  Default: 4 per cell of all views, within 70 % of the memory that is still free after the grids,
+        // the staging region and ~8 GB of per-warp scratch.
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t reserve = (size_t)d.stage_cap * per_patch + ((size_t)8 << 30);
+        const size_t usable = free_b > reserve ? (size_t)((free_b - reserve) * 0.7) : 0;
+        const size_t by_mem = usable / (per_patch + (size_t)nv * 4);             // + the gather buffer row
+        d.cap = (int)std::min<size_t>(std::min<size_t>((size_t)4 * d.total_cells, by_mem), (size_t)0x3fffffff);
+        if (d.cap < 1024) return fail(PMK_ERR_CUDA, "pmk: not enough device memory for the patch store");
+    }
     const size_t tot = (size_t)d.cap + d.stage_cap;
     if ((rc = dalloc(ctx, &d.coord, tot)) || (rc = dalloc(ctx, &d.normal, tot)) || (rc = dalloc(ctx, &d.scal, tot)) ||
         (rc = dalloc(ctx, &d.nimg, tot)) || (rc = dalloc(ctx, &d.nvimg, tot)) || (rc = dalloc(ctx, &d.state, tot)) || (rc = dalloc(ctx, &d.birth, tot)) ||
         (rc = dalloc(ctx, &d.images, tot * d.maxv)) || (rc = dalloc(ctx, &d.cells, tot * d.maxv)) ||
         (rc = dalloc(ctx, &d.vimages, tot * d.maxv)) || (rc = dalloc(ctx, &d.vcells, tot * d.maxv)) ||
-        (rc = dalloc(ctx, &d.counters, SC_COUNT)) || (rc = dalloc(ctx, &s->cell_base_d, nv + 1)) ||
-        (rc = dalloc(ctx, &d.ccount, d.total_cells)) || (rc = dalloc(ctx, &d.cslots, (size_t)d.total_cells * d.cell_cap)) ||
-        (rc = dalloc(ctx, &d.dmap, d.total_cells)))
+        (rc = dalloc(ctx, &d.counters, SC_COUNT)) || (rc = dalloc(ctx, &s->cell_base_d, nv + 1)))
         return rc;
     d.cell_base = s->cell_base_d;
     CUDA_TRY(cudaMemcpyAsync(s->cell_base_d, s->cell_base.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

@@ -21,6 +21,8 @@ namespace pmk {
 enum SweepStat { SS_CALLS = 0, SS_TRIES, SS_GEN_NULL, SS_NCC_LOSE, SS_FAIL0, SS_FAIL1, SS_ADDED, SS_REPLACED, SS_TRIMMED, SS_EVALS, SS_COUNT = 16 };
 
 constexpr int GROUP_MAX = 128;         // views whose wavefronts one step can carry
+constexpr int LKEEP = 40;              // entries of a cell list the sweep keeps (MAX_NUM_OF_PATCHES <= 32, plus slack)
+constexpr int REM_OVERLAY = 128;       // removals of a dest cell that the step's own check() calls can see
 
 struct SweepArgs {
     // dest cells of this step: for group member g, view g_img[g], cells (g_xlo[g] + t, g_diag[g] - g_xlo[g] - t),
@@ -43,7 +45,7 @@ struct SweepArgs {
 };
 
 struct SweepScratch {                  // per warp
-    int l_snap[LIST_MAX];              // snapshot of the dest cell's list the try was evaluated against
+    int l_snap[LKEEP];                 // snapshot of the dest cell's list the try was evaluated against
     int vimg[CAND_MAXV];
     int vcell[CAND_MAXV];
     int cells[CAND_MAXV];
@@ -56,31 +58,86 @@ __device__ __forceinline__ void swap_sort_desc(int* id, float* ncc, int n) {
             if (ncc[i] < ncc[j]) { const float t = ncc[i]; ncc[i] = ncc[j]; ncc[j] = t; const int u = id[i]; id[i] = id[j]; id[j] = u; }
 }
 
-// m_pgrids entries of global cell c in the reference's vector order (ascending creation), then sortPatches(desc).
-// Returns the count (clamped to LIST_MAX).  only_ref >= 0 keeps, after sorting and truncating to `keep`, the patches whose
-// reference image is only_ref (propagate.cpp:102).
-__device__ __forceinline__ int warp_load_cell(const StoreParams& sp, int c, int* id, float* ncc, int lane) {
+// sortPatches(desc) + "keep the first `keep`" (propagate.cpp:88-97,124-134) in one streaming pass over the m_pgrids entries
+// of global cell c: id[] / ncc[] / birth[] end up holding the `keep` best patches by (m_ncc descending, creation ascending),
+// in that order.  A cell can hold hundreds of entries (every view that sees the surface registers its patches there until the
+// cell's own sweep trims it), so nothing longer than `keep` is ever materialised.  TRIM: every other live entry is a patch
+// the reference removes (removePatch): the first REM_OVERLAY go to removed[] (visible to this cell's check() calls), the
+// rest straight to the step's removal list.  Returns the kept count; *ntrim counts the trimmed ones.
+template <bool TRIM>
+__device__ __forceinline__ int warp_load_cell_topk(const StoreParams& sp, int c, int keep, int* id, float* ncc, unsigned int* birth,
+                                                   int* removed, int* nremoved, int* rem_list, int* ntrim, int lane) {
     const StoreDev& st = sp.st;
     const int n = min(st.ccount[c], st.cell_cap);
-    int m = 0;
+    int m = 0, trimmed = 0, nrem = TRIM ? *nremoved : 0;
+    // short cells (the common case): the reference's own procedure, verbatim -- vector order (creation), its O(n^2) swap sort,
+    // then everything past `keep` is removed -- so ties in m_ncc resolve exactly as in the reference
+    int live = 0;
     for (int base = 0; base < n; base += 32) {
         const int s = base + lane;
         int e = SLOT_TOMB;
         if (s < n) e = st.cslots[(size_t)c * st.cell_cap + s];
         const bool ok = e != SLOT_TOMB && e >= 0 && st.state[e] == 1;
         const unsigned msk = __ballot_sync(0xffffffffu, ok);
-        if (ok) { const int pos = m + __popc(msk & ((1u << lane) - 1u)); if (pos < LIST_MAX) { id[pos] = e; ncc[pos] = st.scal[e].x; } }
-        m = min(LIST_MAX, m + __popc(msk));
+        if (ok) { const int pos = live + __popc(msk & ((1u << lane) - 1u)); if (pos < LKEEP) { id[pos] = e; ncc[pos] = st.scal[e].x; birth[pos] = st.birth[e]; } }
+        live += __popc(msk);
     }
     __syncwarp();
-    if (lane == 0) {
-        for (int i = 1; i < m; ++i) {                    // vector order = creation order
-            const int e = id[i]; const float v = ncc[i]; const unsigned b = st.birth[e];
-            int j = i - 1;
-            while (j >= 0 && st.birth[id[j]] > b) { id[j + 1] = id[j]; ncc[j + 1] = ncc[j]; --j; }
-            id[j + 1] = e; ncc[j + 1] = v;
+    if (live <= LKEEP) {
+        if (lane == 0) {
+            for (int i = 1; i < live; ++i) {                 // vector order = creation order
+                const int e = id[i]; const float v = ncc[i]; const unsigned int b = birth[i];
+                int j = i - 1;
+                while (j >= 0 && birth[j] > b) { id[j + 1] = id[j]; ncc[j + 1] = ncc[j]; birth[j + 1] = birth[j]; --j; }
+                id[j + 1] = e; ncc[j + 1] = v; birth[j + 1] = b;
+            }
+            swap_sort_desc(id, ncc, live);
+            if (TRIM) for (int i = keep; i < live; ++i) {
+                if (nrem < REM_OVERLAY) removed[nrem++] = id[i];
+                else rem_list[atomicAdd(st.counters + SC_REM, 1)] = id[i];
+                ++trimmed;
+            }
+        }
+        m = min(live, keep);
+        if (TRIM) { *nremoved = __shfl_sync(0xffffffffu, nrem, 0); *ntrim = __shfl_sync(0xffffffffu, trimmed, 0); }
+        __syncwarp();
+        return m;
+    }
+    // long cells: stream, keeping only the `keep` best by (m_ncc descending, creation ascending)
+    for (int base = 0; base < n; base += 32) {
+        const int s = base + lane;
+        int e = SLOT_TOMB;
+        if (s < n) e = st.cslots[(size_t)c * st.cell_cap + s];
+        const bool ok = e != SLOT_TOMB && e >= 0 && st.state[e] == 1;
+        const float v = ok ? st.scal[e].x : 0.0f;
+        const unsigned int b = ok ? st.birth[e] : 0u;
+        unsigned msk = __ballot_sync(0xffffffffu, ok);
+        while (msk) {
+            const int l = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const int el = __shfl_sync(0xffffffffu, e, l);
+            const float vl = __shfl_sync(0xffffffffu, v, l);
+            const unsigned int bl = __shfl_sync(0xffffffffu, b, l);
+            int out = -1;                                    // the entry that falls off the list, if any
+            if (lane == 0) {
+                int pos = m;                                 // insertion point: after every better entry
+                while (pos > 0 && (ncc[pos - 1] < vl || (ncc[pos - 1] == vl && birth[pos - 1] > bl))) --pos;
+                if (pos >= keep) out = el;
+                else {
+                    if (m == keep) { out = id[keep - 1]; } else ++m;
+                    for (int j = m - 1; j > pos; --j) { id[j] = id[j - 1]; ncc[j] = ncc[j - 1]; birth[j] = birth[j - 1]; }
+                    id[pos] = el; ncc[pos] = vl; birth[pos] = bl;
+                }
+                if (TRIM && out >= 0) {
+                    if (nrem < REM_OVERLAY) removed[nrem++] = out;
+                    else rem_list[atomicAdd(st.counters + SC_REM, 1)] = out;
+                    ++trimmed;
+                }
+            }
         }
     }
+    m = __shfl_sync(0xffffffffu, m, 0);
+    if (TRIM) { *nremoved = __shfl_sync(0xffffffffu, nrem, 0); *ntrim = __shfl_sync(0xffffffffu, trimmed, 0); }
     __syncwarp();
     return m;
 }
@@ -114,10 +171,11 @@ __device__ __forceinline__ float warp_compute_ncc(const Params& p, WarpScratch& 
 // branch (room / full), the worst patch when full; the store-reading tail (stage B) is redone when the list changed at all.
 // Otherwise it re-evaluates, now against the final state since it holds the turn.  The outcome is the sequential one.
 struct CellShared {
-    int l_id[LIST_MAX];
-    float l_ncc[LIST_MAX];
+    int l_id[LKEEP];
+    float l_ncc[LKEEP];
+    unsigned int l_birth[LKEEP];
     int src_id[SRC_MAX];
-    int removed[LIST_MAX + NEW_MAX];
+    int removed[REM_OVERLAY + NEW_MAX];
     int nl, nrem, nnew, nsrc;
     int version;                 // seqlock: odd while a commit is in progress
     int next_try, commit_ptr;
@@ -137,7 +195,7 @@ __device__ __forceinline__ TrySnap take_snapshot(const CellShared& cs, int* my_i
         const int v0 = ld_shared_volatile(&cs.version);
         if (v0 & 1) { __nanosleep(50); continue; }
         const int np = ld_shared_volatile(&cs.nl);
-        for (int i = lane; i < min(np, LIST_MAX); i += 32) my_id[i] = ld_shared_volatile(&cs.l_id[i]);
+        for (int i = lane; i < min(np, LKEEP); i += 32) my_id[i] = ld_shared_volatile(&cs.l_id[i]);
         sn.np = np;
         sn.w = np >= maxp ? ld_shared_volatile(&cs.l_id[maxp - 1]) : -1;
         sn.wncc = np >= maxp ? __int_as_float(ld_shared_volatile(reinterpret_cast<const int*>(&cs.l_ncc[maxp - 1]))) : 0.0f;
@@ -200,36 +258,38 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
         if (warp == 0) {
             int nrem = 0;
             // ---- D's list: sortPatches + trim (propagate.cpp:123-134) ----
-            int nl = warp_load_cell(sp, cD, cs.l_id, cs.l_ncc, lane);
-            for (int i = 0; i < nl; ++i) {
-                if (cs.l_ncc[i] < 0.0f) {                                   // sortPatches recomputes a negative m_ncc (patch_manager.cpp:411-415)
-                    const int e = cs.l_id[i];
-                    const int nv = min(st.nimg[e], CAND_MAXV);
-                    for (int k = lane; k < nv; k += 32) ws.images[k] = st.images[(size_t)e * st.maxv + k];
-                    __syncwarp();
-                    const float v = warp_compute_ncc<WS>(p, ws, f4v(st.coord[e]), f4v(st.normal[e]), nv, lane);
-                    if (lane == 0) { cs.l_ncc[i] = v; st.scal[e].x = v; }
-                    __syncwarp();
+            {   // sortPatches recomputes a negative m_ncc first (patch_manager.cpp:411-415)
+                const int n = min(st.ccount[cD], st.cell_cap);
+                for (int base = 0; base < n; base += 32) {
+                    const int s2 = base + lane;
+                    int e = SLOT_TOMB;
+                    if (s2 < n) e = st.cslots[(size_t)cD * st.cell_cap + s2];
+                    const bool neg = e != SLOT_TOMB && e >= 0 && st.state[e] == 1 && st.scal[e].x < 0.0f;
+                    unsigned msk = __ballot_sync(0xffffffffu, neg);
+                    while (msk) {
+                        const int l = __ffs(msk) - 1;
+                        msk &= msk - 1;
+                        const int el = __shfl_sync(0xffffffffu, e, l);
+                        const int nv = min(st.nimg[el], CAND_MAXV);
+                        for (int k = lane; k < nv; k += 32) ws.images[k] = st.images[(size_t)el * st.maxv + k];
+                        __syncwarp();
+                        const float v = warp_compute_ncc<WS>(p, ws, f4v(st.coord[el]), f4v(st.normal[el]), nv, lane);
+                        if (lane == 0) st.scal[el].x = v;
+                        __syncwarp();
+                    }
                 }
             }
-            if (lane == 0) swap_sort_desc(cs.l_id, cs.l_ncc, nl);
-            __syncwarp();
-            if (nl > maxp) {
-                for (int i = maxp + lane; i < nl; i += 32) cs.removed[nrem + i - maxp] = cs.l_id[i];
-                stat[SS_TRIMMED] += nl - maxp;
-                nrem += nl - maxp; nl = maxp;
-            }
-            __syncwarp();
+            int ntrim = 0;
+            const int nl = warp_load_cell_topk<true>(sp, cD, maxp, cs.l_id, cs.l_ncc, cs.l_birth, cs.removed, &nrem, sa.rem_list, &ntrim, lane);
+            stat[SS_TRIMMED] += ntrim;
             // ---- sources: (x, y - inc) first, then (x - inc, y); each cell's sorted top-maxp, reference view == img ----
             int nsrc = 0;
             for (int side = 0; side < 2; ++side) {
                 const int sx = side == 0 ? x : x - inc, sy = side == 0 ? y - inc : y;
                 if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
                 int* tid = ss.vimg; float* tncc = reinterpret_cast<float*>(ss.vcell);       // scratch, free until stage B
-                int m = warp_load_cell(sp, st.cell_base[img] + sy * gw + sx, tid, tncc, lane);
-                if (lane == 0) swap_sort_desc(tid, tncc, m);
-                __syncwarp();
-                m = min(m, maxp);
+                unsigned int* tbirth = reinterpret_cast<unsigned int*>(ss.cells);
+                const int m = warp_load_cell_topk<false>(sp, st.cell_base[img] + sy * gw + sx, maxp, tid, tncc, tbirth, nullptr, nullptr, nullptr, nullptr, lane);
                 for (int i = 0; i < m && nsrc < SRC_MAX; ++i) {
                     const int e = tid[i];
                     if (st.images[(size_t)e * st.maxv] == img) { if (lane == 0) cs.src_id[nsrc] = e; ++nsrc; }
@@ -339,7 +399,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                         if (2 <= p.depth) {                                                    // Optim::check (optim.cpp:300-323)
                             PGeo me; me.X = cd.X; me.N = cd.N; me.dscale = cd.dscale; me.ref = ws.images[0];
                             const PatchLists pl{ws.images, ss.cells, cd.nv, ss.vimg, ss.vcell, cd.nvv};
-                            const Overlay ov{cD, ss.l_snap, min(sn.np, LIST_MAX), cs.removed, sn.nrem};
+                            const Overlay ov{cD, ss.l_snap, min(sn.np, LKEEP), cs.removed, sn.nrem};
                             const float gain = warp_compute_gain(sp, me, cd.ncc, pl, ov, lane);
                             cd.tmp = gain;
                             if (gain < 0.0f) outcome = TRY_FAIL1;

@@ -12,6 +12,26 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvskit_b200 import pmk, synth  # noqa: E402
 
 
+def _render_worker(args):
+    config, scale, nviews, views = args
+    sc = synth.make_scene(config, scale=scale, nviews=nviews)
+    sc.render(views=views)
+    return [(v, sc.images[v]) for v in views]
+
+
+def render_parallel(scene, config, scale, nviews, procs):
+    """scene.render() spread over `procs` processes (every view renders independently and deterministically)."""
+    import multiprocessing as mp
+    V = scene.nviews
+    jobs = [(config, scale, nviews, list(range(i, V, procs))) for i in range(procs)]
+    scene.images = [None] * V
+    with mp.get_context("spawn").Pool(procs) as pool:
+        for part in pool.map(_render_worker, jobs):
+            for v, im in part:
+                scene.images[v] = im
+    return scene
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=1)
@@ -20,11 +40,18 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--group", type=int, default=1)
     ap.add_argument("--cell-capacity", type=int, default=0)
+    ap.add_argument("--procs", type=int, default=1, help="processes rendering the synthetic views")
+    ap.add_argument("--seed-stride", type=int, default=4, help="one seed every this many cells")
     a = ap.parse_args()
-    scene = synth.make_scene(a.config, scale=a.scale, nviews=a.nviews).render()
+    t0 = time.time()
+    scene = synth.make_scene(a.config, scale=a.scale, nviews=a.nviews)
+    scene = render_parallel(scene, a.config, a.scale, a.nviews, a.procs) if a.procs > 1 else scene.render()
+    print(f"rendered {scene.nviews} views {scene.width}x{scene.height} in {time.time() - t0:.1f} s", flush=True)
     ctx = pmk.Context(nviews=scene.nviews, sweep_group=a.group, cell_capacity=a.cell_capacity)
     ctx.set_scene(scene.P, scene.images)
-    coord, normal, scal, images, nimg = synth.seed_arrays(scene)
+    t0 = time.time()
+    coord, normal, scal, images, nimg = synth.seed_arrays(scene, stride=a.seed_stride)
+    print(f"{len(coord)} seeds in {time.time() - t0:.1f} s", flush=True)
     ctx.set_depth(0); ctx.store_clear(); ctx.store_add(coord, normal, scal, images, nimg); ctx.set_depth(1)
     print("seeds", len(coord), "views", scene.nviews, "grid", ctx.grid_dims(0), "group", a.group, flush=True)
     T0 = time.time()
