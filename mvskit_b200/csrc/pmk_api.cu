@@ -1145,10 +1145,16 @@ int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128) {
     s->nccl_comm = comm;
     s->ml.rem_cap = 16384;
     s->ml.rec_cap = std::max(1024, std::min(16384, s->max_tasks * 4));
-    s->ml.rec_words = 14 + 4 * s->d.maxv;
+    s->ml.rec_words = 16 + 4 * s->d.maxv;
     if ((rc = dalloc(ctx, &s->msg, s->ml.words())) || (rc = dalloc(ctx, &s->all_msgs, s->ml.words() * nranks)) ||
-        (rc = dalloc(ctx, &s->pack_ids, s->ml.rec_cap)) || (rc = dalloc(ctx, &s->rec_base, 2 * nranks)))
+        (rc = dalloc(ctx, &s->pack_ids, s->ml.rec_cap)) || (rc = dalloc(ctx, &s->rec_base, 2 * nranks + 4)))
         return rc;
+    const size_t nrec = (size_t)nranks * s->ml.rec_cap;
+    if ((rc = dalloc(ctx, &s->mg_keys, nrec)) || (rc = dalloc(ctx, &s->mg_keys2, nrec)) || (rc = dalloc(ctx, &s->mg_vals, nrec)) || (rc = dalloc(ctx, &s->mg_vals2, nrec)))
+        return rc;
+    cub::DeviceRadixSort::SortPairs(nullptr, s->mg_cub_bytes, s->mg_keys, s->mg_keys2, s->mg_vals, s->mg_vals2, (int)nrec, 0, 64, ctx->stream);
+    CUDA_TRY(cudaMalloc(&s->mg_cub, s->mg_cub_bytes));
+    ctx->owned.push_back(s->mg_cub);
     return PMK_OK;
 }
 

@@ -336,7 +336,8 @@ __device__ __forceinline__ int warp_find_neighbors(const StoreParams& sp, const 
     __syncwarp();
     if (nuni > NB_CAP) { overflow = true; nuni = NB_CAP; }
     if (overflow && lane == 0) atomicAdd(st.counters + SC_NBOVER, 1);
-    // ascending id order: the quadric fit sums over the neighbours, and replicated stores (multi-GPU) must sum in one order
+    // ascending id order (ids follow creation order, identical on every replica and for every number of GPUs): the quadric fit
+    // sums over the neighbours and must do so in one order everywhere
     int* tmp = out + NB_CAP;
     for (int k = lane; k < nuni; k += 32) {
         const int id = out[k];

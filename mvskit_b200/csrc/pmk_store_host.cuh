@@ -36,6 +36,8 @@ struct pmk_store {
     void* nccl_comm = nullptr;
     pmk::MsgLayout ml = {0, 0, 0};
     int* msg = nullptr; int* all_msgs = nullptr; int* pack_ids = nullptr; int* rec_base = nullptr;
+    unsigned long long* mg_keys = nullptr; unsigned long long* mg_keys2 = nullptr; int* mg_vals = nullptr; int* mg_vals2 = nullptr;
+    void* mg_cub = nullptr; size_t mg_cub_bytes = 0;
     bool canonical = false;             // patch ids are the reference's m_ppatches indices (collect order, no holes)
 };
 
@@ -433,13 +435,16 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
         NcclApi* api = nccl_api();
         if (!api || !s->nccl_comm) return fail(PMK_ERR_STATE, "pmk: multi-GPU sweep without a communicator (pmk_comm_init)");
         k4_pack_scan<<<1, 32, 0, st>>>(sp, s->task_new, sa.ntasks, s->rem_list, s->ml, s->msg, s->pack_ids);
-        k4_pack_copy<<<ctx->sm_count, 128, 0, st>>>(sp, s->ml, s->msg, s->pack_ids);
+        k4_pack_copy<<<ctx->sm_count, 128, 0, st>>>(sp, sa, s->ml, s->msg, s->pack_ids);
         const ncclResult_t nr = api->AllGather(s->msg, s->all_msgs, s->ml.words(), ncclInt32, (ncclComm_t)s->nccl_comm, st);
         if (nr != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nr) : "error"));
         k4_unpack_remove<<<ctx->sm_count, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks);
+        const int nrec = s->nranks * s->ml.rec_cap;
+        k4_unpack_keys<<<(nrec + 255) / 256, 256, 0, st>>>(s->ml, s->all_msgs, s->nranks, s->mg_keys, s->mg_vals);
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->mg_cub, s->mg_cub_bytes, s->mg_keys, s->mg_keys2, s->mg_vals, s->mg_vals2, nrec, 0, 64, st));
         k4_unpack_scan<<<1, 32, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, s->rec_base);
-        k4_unpack_add<<<ctx->sm_count * 2, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, s->rec_base);
-        ctx->launches += 5;
+        k4_unpack_add<<<ctx->sm_count * 2, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, s->rec_base, s->mg_vals2);
+        ctx->launches += 7;
     }
     CUDA_TRY(cudaGetLastError());
     return PMK_OK;
@@ -465,6 +470,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
     for (int k = step_first; k < step_first + step_count && k < max_steps; ++k) {
         sa.ngroup = 0; sa.ntasks = 0;
+        int gtasks = 0;
         for (int g = 0; g < nimg; ++g) {
             const ViewConst& vc = ctx->h_views[img_first + g];
             const int gw = vc.gw, gh = vc.gh, ndiag = gw + gh - 1;
@@ -472,10 +478,14 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
             const int d = inc > 0 ? k : ndiag - 1 - k;
             // rows of this rank's band
             const int ylo = (int)((long long)gh * s->rank / s->nranks), yhi = (int)((long long)gh * (s->rank + 1) / s->nranks);
-            const int xlo = std::max(std::max(0, d - gh + 1), d - yhi + 1), xhi = std::min(std::min(gw - 1, d), d - ylo);
+            const int gxlo = std::max(0, d - gh + 1), gxhi = std::min(gw - 1, d);             // the whole anti-diagonal
+            const int xlo = std::max(gxlo, d - yhi + 1), xhi = std::min(gxhi, d - ylo);       // this rank's band of it
+            const int goff = gtasks;
+            gtasks += gxhi - gxlo + 1;
             if (xhi < xlo) continue;
             const int m = sa.ngroup++;
             sa.g_img[m] = img_first + g; sa.g_diag[m] = d; sa.g_xlo[m] = xlo; sa.g_off[m] = sa.ntasks;
+            sa.g_gxlo[m] = gxlo; sa.g_goff[m] = goff;
             sa.ntasks += xhi - xlo + 1;
         }
         sa.g_off[sa.ngroup] = sa.ntasks;

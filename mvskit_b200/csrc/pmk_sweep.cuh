@@ -29,6 +29,8 @@ struct SweepArgs {
     // t in [0, g_off[g + 1] - g_off[g]); task index = g_off[g] + t
     int ngroup, ntasks, inc;
     int g_img[GROUP_MAX], g_diag[GROUP_MAX], g_xlo[GROUP_MAX], g_off[GROUP_MAX + 1];
+    // the same enumeration without the row-band restriction (multi-GPU: ids and creation numbers follow THIS order on every rank)
+    int g_gxlo[GROUP_MAX], g_goff[GROUP_MAX];
     int iter;                              // Propagate::run(iter)
     int wpc;                               // warps cooperating on one dest cell: 1, 2 or 4 (CAND_WARPS / wpc cells per CTA)
     int jitter_mode;                       // 0: the reference's four constant draws (propagate.cpp:139-141), 1: Philox per try
@@ -734,8 +736,11 @@ __global__ void k4_apply_add(const StoreParams sp, const int* __restrict__ task_
 // Multi-GPU: the store is replicated, the dest cells of a step are partitioned by row band, and the step's mutations
 // (new patches, removals) travel between the ranks as one fixed-layout message per rank (ncclAllGather over NVLink).
 // Every rank then applies ALL messages in rank order, so ids, creation numbers and grids stay identical everywhere.
-//   message = int hdr[4] {n_new, n_rem, overflow, 0} | int rem[rem_cap] | rec[rec_cap][14 + 4 * maxv]
-//   record  = coord4, normal4, scal4 (as int bits), nimg, nvimg, images[maxv], cells[maxv], vimages[maxv], vcells[maxv]
+//   message = int hdr[4] {n_new, n_rem, overflow, 0} | int rem[rem_cap] | rec[rec_cap][16 + 4 * maxv]
+//   record  = coord4, normal4, scal4 (as int bits), nimg, nvimg, global task index, slot in the task,
+//             images[maxv], cells[maxv], vimages[maxv], vcells[maxv]
+// Final ids and creation numbers are assigned in (global task, slot) order -- the order the single-GPU scan uses -- so an
+// N-GPU run produces the single-GPU store bit for bit.
 // =====================================================================================================================
 namespace pmk {
 
@@ -764,7 +769,7 @@ __global__ void k4_pack_scan(const StoreParams sp, const int* __restrict__ task_
     for (int i = 0; i < nrem; ++i) msg[4 + i] = rem_list[i];
 }
 
-__global__ void k4_pack_copy(const StoreParams sp, MsgLayout ml, int* __restrict__ msg, const int* __restrict__ pack_ids) {
+__global__ void k4_pack_copy(const StoreParams sp, const SweepArgs sa, MsgLayout ml, int* __restrict__ msg, const int* __restrict__ pack_ids) {
     const StoreDev& st = sp.st;
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -778,10 +783,15 @@ __global__ void k4_pack_copy(const StoreParams sp, MsgLayout ml, int* __restrict
             rec[4] = __float_as_int(m.x); rec[5] = __float_as_int(m.y); rec[6] = __float_as_int(m.z); rec[7] = __float_as_int(m.w);
             rec[8] = __float_as_int(s.x); rec[9] = __float_as_int(s.y); rec[10] = __float_as_int(s.z); rec[11] = __float_as_int(s.w);
             rec[12] = st.nimg[sid]; rec[13] = st.nvimg[sid];
+            const int task = (sid - st.cap) / NEW_MAX;
+            int g = 0;
+            while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+            rec[14] = sa.g_goff[g] + (sa.g_xlo[g] + (task - sa.g_off[g]) - sa.g_gxlo[g]);
+            rec[15] = (sid - st.cap) % NEW_MAX;
         }
         const int ni = st.nimg[sid], nv = st.nvimg[sid], mv = st.maxv;
-        for (int i = lane; i < ni; i += 32) { rec[14 + i] = st.images[(size_t)sid * mv + i]; rec[14 + mv + i] = st.cells[(size_t)sid * mv + i]; }
-        for (int i = lane; i < nv; i += 32) { rec[14 + 2 * mv + i] = st.vimages[(size_t)sid * mv + i]; rec[14 + 3 * mv + i] = st.vcells[(size_t)sid * mv + i]; }
+        for (int i = lane; i < ni; i += 32) { rec[16 + i] = st.images[(size_t)sid * mv + i]; rec[16 + mv + i] = st.cells[(size_t)sid * mv + i]; }
+        for (int i = lane; i < nv; i += 32) { rec[16 + 2 * mv + i] = st.vimages[(size_t)sid * mv + i]; rec[16 + 3 * mv + i] = st.vcells[(size_t)sid * mv + i]; }
     }
 }
 
@@ -810,48 +820,64 @@ __global__ void k4_unpack_remove(const StoreParams sp, MsgLayout ml, const int* 
     }
 }
 
-// one thread: final ids of every rank's records, rank-major; rec_base[rk] = first id of rank rk (or -1 beyond capacity)
+// sort keys of every rank's records: (global task, slot); unused tail = ~0.  One thread per record slot.
+__global__ void k4_unpack_keys(MsgLayout ml, const int* __restrict__ all, int nranks, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nranks * ml.rec_cap) return;
+    const int rk = i / ml.rec_cap, r = i % ml.rec_cap;
+    const int* msg = all + (size_t)rk * ml.words();
+    unsigned long long k = ~0ull;
+    if (r < msg[0]) {
+        const int* rec = msg + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
+        k = (unsigned long long)(unsigned int)rec[14] * NEW_MAX + (unsigned int)rec[15];
+    }
+    keys[i] = k;
+    vals[i] = i;
+}
+
+// one thread: how many records there are in all, capacity check, counters
 __global__ void k4_unpack_scan(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks, int* __restrict__ rec_base) {
     const StoreDev& st = sp.st;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int n = st.counters[SC_N];
-    int b = st.counters[SC_BIRTH];
+    int total = 0;
     for (int rk = 0; rk < nranks; ++rk) {
         const int* msg = all + (size_t)rk * ml.words();
         if (msg[2]) atomicAdd(st.counters + SC_OVERFLOW, 1);
-        const int k = msg[0];
-        if (n + k <= st.cap) { rec_base[rk] = n; rec_base[nranks + rk] = b; n += k; b += k; }
-        else { rec_base[rk] = -1; rec_base[nranks + rk] = 0; atomicAdd(st.counters + SC_FULL, k); }
+        total += msg[0];
     }
-    st.counters[SC_N] = n;
-    st.counters[SC_BIRTH] = b;
+    const int n = st.counters[SC_N], b = st.counters[SC_BIRTH];
+    int take = total;
+    if (n + total > st.cap) { take = max(0, st.cap - n); atomicAdd(st.counters + SC_FULL, total - take); }
+    rec_base[0] = n; rec_base[1] = b; rec_base[2] = take;
+    st.counters[SC_N] = n + take;
+    st.counters[SC_BIRTH] = b + total;
 }
 
-__global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks, const int* __restrict__ rec_base) {
+// record at sorted position pos gets id n0 + pos and creation number b0 + pos (one warp per record)
+__global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks, const int* __restrict__ rec_base,
+                              const int* __restrict__ sorted_vals) {
     const StoreDev& st = sp.st;
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const bool deep = sp.cp.p.depth != 0;
-    for (int rk = 0; rk < nranks; ++rk) {
-        const int* msg = all + (size_t)rk * ml.words();
-        const int k = msg[0], base = rec_base[rk];
-        if (base < 0) continue;
-        for (int r = gwarp; r < k; r += nwarps) {
-            const int* rec = msg + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
-            const int fid = base + r, mv = st.maxv;
-            const int ni = rec[12], nv = rec[13];
-            if (lane == 0) {
-                st.coord[fid] = make_float4(__int_as_float(rec[0]), __int_as_float(rec[1]), __int_as_float(rec[2]), __int_as_float(rec[3]));
-                st.normal[fid] = make_float4(__int_as_float(rec[4]), __int_as_float(rec[5]), __int_as_float(rec[6]), __int_as_float(rec[7]));
-                st.scal[fid] = make_float4(__int_as_float(rec[8]), __int_as_float(rec[9]), __int_as_float(rec[10]), __int_as_float(rec[11]));
-                st.nimg[fid] = ni; st.nvimg[fid] = nv; st.state[fid] = 1; st.birth[fid] = (unsigned int)(rec_base[nranks + rk] + r);
-            }
-            for (int i = lane; i < ni; i += 32) { st.images[(size_t)fid * mv + i] = rec[14 + i]; st.cells[(size_t)fid * mv + i] = rec[14 + mv + i]; }
-            for (int i = lane; i < nv; i += 32) { st.vimages[(size_t)fid * mv + i] = rec[14 + 2 * mv + i]; st.vcells[(size_t)fid * mv + i] = rec[14 + 3 * mv + i]; }
-            __syncwarp();
-            warp_register_patch(sp, fid, deep, deep, lane);
-            __syncwarp();
+    const int n0 = rec_base[0], b0 = rec_base[1], take = rec_base[2];
+    for (int pos = gwarp; pos < take; pos += nwarps) {
+        const int i = sorted_vals[pos];
+        const int rk = i / ml.rec_cap, r = i % ml.rec_cap;
+        const int* rec = all + (size_t)rk * ml.words() + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
+        const int fid = n0 + pos, mv = st.maxv;
+        const int ni = rec[12], nv = rec[13];
+        if (lane == 0) {
+            st.coord[fid] = make_float4(__int_as_float(rec[0]), __int_as_float(rec[1]), __int_as_float(rec[2]), __int_as_float(rec[3]));
+            st.normal[fid] = make_float4(__int_as_float(rec[4]), __int_as_float(rec[5]), __int_as_float(rec[6]), __int_as_float(rec[7]));
+            st.scal[fid] = make_float4(__int_as_float(rec[8]), __int_as_float(rec[9]), __int_as_float(rec[10]), __int_as_float(rec[11]));
+            st.nimg[fid] = ni; st.nvimg[fid] = nv; st.state[fid] = 1; st.birth[fid] = (unsigned int)(b0 + pos);
         }
+        for (int k = lane; k < ni; k += 32) { st.images[(size_t)fid * mv + k] = rec[16 + k]; st.cells[(size_t)fid * mv + k] = rec[16 + mv + k]; }
+        for (int k = lane; k < nv; k += 32) { st.vimages[(size_t)fid * mv + k] = rec[16 + 2 * mv + k]; st.vcells[(size_t)fid * mv + k] = rec[16 + 3 * mv + k]; }
+        __syncwarp();
+        warp_register_patch(sp, fid, deep, deep, lane);
+        __syncwarp();
     }
 }
 

@@ -12,6 +12,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from mvskit_b200 import dist as pdist, pmk, synth  # noqa: E402
 
 
@@ -37,6 +38,8 @@ def main():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--procs", type=int, default=1)
+    ap.add_argument("--seed-stride", type=int, default=4)
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -44,8 +47,19 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    scene = synth.make_scene(a.config, scale=a.scale, nviews=a.nviews).render()
-    seeds = synth.seed_arrays(scene)
+    # rank 0 renders (in parallel processes) and caches; the other ranks load the cache
+    import tempfile
+    from run_pipeline import render_parallel
+    cache = os.path.join(tempfile.gettempdir(), f"pmk_mg_scene_c{a.config}_s{a.scale:g}_v{a.nviews}.npy")
+    scene = synth.make_scene(a.config, scale=a.scale, nviews=a.nviews)
+    if rank == 0 and not os.path.exists(cache):
+        render_parallel(scene, a.config, a.scale, a.nviews, a.procs) if a.procs > 1 else scene.render()
+        np.save(cache + ".tmp.npy", np.stack(scene.images))
+        os.replace(cache + ".tmp.npy", cache)
+    dist.barrier()
+    arr = np.load(cache)
+    scene.images = [arr[v] for v in range(arr.shape[0])]
+    seeds = synth.seed_arrays(scene, stride=a.seed_stride)
     group = a.group or scene.nviews
     ctx = pmk.Context(nviews=scene.nviews, device=local, sweep_group=group)
     ctx.set_scene(scene.P, scene.images)
