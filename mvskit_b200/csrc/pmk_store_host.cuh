@@ -23,7 +23,7 @@ struct pmk_store {
     std::vector<int> cell_base;         // host copy
     // scratch
     int* rem_list = nullptr; int* task_new = nullptr; int* final_id = nullptr; int* order = nullptr;
-    unsigned long long* stats = nullptr;
+    unsigned long long* stats = nullptr; unsigned long long* step_max = nullptr;
     unsigned long long* keys = nullptr; unsigned long long* keys2 = nullptr;
     int* vals = nullptr; int* vals2 = nullptr;
     void* cub_tmp = nullptr; size_t cub_bytes = 0;
@@ -123,7 +123,7 @@ int store_init(pmk_ctx* ctx) {
     d.cell_base = s->cell_base_d;
     CUDA_TRY(cudaMemcpyAsync(s->cell_base_d, s->cell_base.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = dalloc(ctx, &s->rem_list, d.cap)) || (rc = dalloc(ctx, &s->task_new, s->max_tasks)) || (rc = dalloc(ctx, &s->order, s->max_tasks + 1)) || (rc = dalloc(ctx, &s->final_id, d.stage_cap)) ||
-        (rc = dalloc(ctx, &s->stats, SS_COUNT)) || (rc = dalloc(ctx, &s->keys, d.cap)) || (rc = dalloc(ctx, &s->keys2, d.cap)) ||
+        (rc = dalloc(ctx, &s->stats, SS_COUNT)) || (rc = dalloc(ctx, &s->step_max, 4)) || (rc = dalloc(ctx, &s->keys, d.cap)) || (rc = dalloc(ctx, &s->keys2, d.cap)) ||
         (rc = dalloc(ctx, &s->vals, d.cap)) || (rc = dalloc(ctx, &s->vals2, d.cap)) || (rc = dalloc(ctx, &s->f_tmp, d.cap)) ||
         (rc = dalloc(ctx, &s->i_tmp, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp2, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp3, d.cap + 1)) || (rc = dalloc(ctx, &s->small, 16)))
         return rc;
@@ -401,6 +401,7 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     const int cpc = CAND_WARPS / sa.wpc;
     const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + cpc - 1) / cpc));
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(s->step_max, 0, sizeof(unsigned long long), st));
     if (sa.ntasks > 0) {
         SweepArgs a = sa;
         a.heavy_slot = s->max_tasks;
@@ -425,6 +426,7 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
             ctx->launches += 2;
         }
     }
+    k_fold_step<<<1, 1, 0, st>>>(s->stats, s->step_max);
     if (s->nranks <= 1) {
         k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
         k4_apply_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
@@ -465,7 +467,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     sa.inc = inc; sa.iter = iter;
     sa.jitter_mode = ctx->cfg.jitter_mode;
     for (int i = 0; i < 4; ++i) sa.jitter[i] = s->jitter[i];
-    sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order;
+    sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order; sa.step_max = s->step_max;
     int max_steps = 0;
     for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
     for (int k = step_first; k < step_first + step_count && k < max_steps; ++k) {

@@ -18,7 +18,8 @@
 
 namespace pmk {
 
-enum SweepStat { SS_CALLS = 0, SS_TRIES, SS_GEN_NULL, SS_NCC_LOSE, SS_FAIL0, SS_FAIL1, SS_ADDED, SS_REPLACED, SS_TRIMMED, SS_EVALS, SS_COUNT = 16 };
+enum SweepStat { SS_CALLS = 0, SS_TRIES, SS_GEN_NULL, SS_NCC_LOSE, SS_FAIL0, SS_FAIL1, SS_ADDED, SS_REPLACED, SS_TRIMMED, SS_EVALS,
+                 SS_CELL_NS, SS_STEP_MAX_NS, SS_STEPS, SS_COUNT = 16 };   // ..., summed dest-cell time, summed per-step slowest cell, steps
 
 constexpr int GROUP_MAX = 128;         // views whose wavefronts one step can carry
 constexpr int LKEEP = 40;              // entries of a cell list the sweep keeps (MAX_NUM_OF_PATCHES <= 32, plus slack)
@@ -44,6 +45,7 @@ struct SweepArgs {
     int split;                             // host: run heavy / light cells as two concurrent launches on wide steps
     int heavy_est;                         // dest cells with at least this many estimated full-cost tries count as heavy
     unsigned long long* stats;             // SweepStat
+    unsigned long long* step_max;          // slowest dest cell of this step, ns (one word per step, zeroed by the host)
 };
 
 struct SweepScratch {                  // per warp
@@ -256,6 +258,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
         const int gw = vimgc.gw, gh = vimgc.gh;
         const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
         const int cD = st.cell_base[img] + y * gw + x;
+        unsigned long long t_begin = 0;
+        if (warp == 0 && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
         // ================= preamble (warp 0): D's list, trim, sources =================
         if (warp == 0) {
             int nrem = 0;
@@ -494,6 +498,12 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                 base = __shfl_sync(0xffffffffu, base, 0);
                 for (int i = lane; i < nrem; i += 32) sa.rem_list[base + i] = cs.removed[i];
             }
+            if (lane == 0) {
+                unsigned long long t_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+                atomicAdd(sa.stats + SS_CELL_NS, t_end - t_begin);
+                atomicMax(sa.step_max, t_end - t_begin);
+            }
         }
         cell_sync();
     }
@@ -584,6 +594,11 @@ __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const Swee
         const int est = min(NBIN - 1, nsrc * (nd < maxp ? 2 : 1));
         order[atomicAdd(&offs[est], 1)] = task;
     }
+}
+
+__global__ void k_fold_step(unsigned long long* stats, const unsigned long long* step_max) {
+    stats[SS_STEP_MAX_NS] += *step_max;
+    stats[SS_STEPS] += 1;
 }
 
 // ---- apply: removals ---------------------------------------------------------------------------------------------------------------

@@ -68,7 +68,7 @@ def main():
             r = np.linalg.norm(g.coord[:, :3], axis=1)
             on_sphere = np.abs(r - 1.0) < 0.05
             q = (float(on_sphere.mean()), np.quantile(np.abs(r[on_sphere] - 1.0) / scene.scene_scale, [0.5, 0.9]))
-        print(f"iter {it}: propagate {t1:.2f}s -> {nprop} patches, {st['evals'] / t1 / 1e6:.1f} M evals/s, stats {st}; filter {t2:.3f}s {c}; "
+        print(f"iter {it}: propagate {t1:.2f}s -> {nprop} patches, {st['evals'] / t1 / 1e6:.1f} M evals/s, slowest-cell sum {st["step_max_ns"] / 1e9:.2f}s of {st["steps"]} steps, cell time {st["cell_ns"] / 1e9:.1f}s, stats {st}; filter {t2:.3f}s {c}; "
               f"quality {q}; launches {ctx.launch_count()}", flush=True)
     dt = time.time() - T0
     print(f"total {dt:.2f} s; {g.n} patches; {g.n / dt:.0f} patches/s")
