@@ -62,7 +62,9 @@ def test_full_size_pass_invariants_and_determinism(full_scene):
     ctx.close()
     # determinism: a second context, same seeds and seed value -> the same store after propagate and after filter
     ctx2, st2, counts2, d_prop2, d_filt2 = _run(scene, seeds)
-    assert (d_prop2, d_filt2, counts2) == (d_prop, d_filt, counts) and st2 == st
+    timing = ("cell_ns", "step_max_ns")
+    assert (d_prop2, d_filt2, counts2) == (d_prop, d_filt, counts)
+    assert {k: v for k, v in st2.items() if k not in timing} == {k: v for k, v in st.items() if k not in timing}
     # Filter::run on an already filtered store only removes what the lower depth-map occupancy newly exposes: a small fraction
     again = ctx2.filter()
     assert again[0] == counts[5] and again[5] >= 0.9 * again[0]
