@@ -504,6 +504,10 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
             sa.split = nosplit ? 0 : 1;
             static const int heavy_est = getenv("PMK_HEAVY_EST") ? atoi(getenv("PMK_HEAVY_EST")) : 16;
             sa.heavy_est = heavy_est;
+            static const int coop = getenv("PMK_SWEEP_COOP") ? atoi(getenv("PMK_SWEEP_COOP")) : 2;
+            sa.coop = coop;
+            static const int room_weight = getenv("PMK_ROOM_WEIGHT") ? atoi(getenv("PMK_ROOM_WEIGHT")) : 2;
+            sa.room_weight = room_weight;
         }
         WS_DISPATCH(ctx->cfg.wsize, { if ((rc = launch_sweep<WS>(ctx, sp, sa))) return rc; });
     }

@@ -19,7 +19,7 @@
 namespace pmk {
 
 enum SweepStat { SS_CALLS = 0, SS_TRIES, SS_GEN_NULL, SS_NCC_LOSE, SS_FAIL0, SS_FAIL1, SS_ADDED, SS_REPLACED, SS_TRIMMED, SS_EVALS,
-                 SS_CELL_NS, SS_STEP_MAX_NS, SS_STEPS, SS_COUNT = 16 };   // ..., summed dest-cell time, summed per-step slowest cell, steps
+                 SS_CELL_NS, SS_STEP_MAX_NS, SS_STEPS, SS_COOP_CELLS, SS_COOP_REFINES, SS_COUNT = 16 };   // ..., summed dest-cell time, summed per-step slowest cell, steps
 
 constexpr int GROUP_MAX = 128;         // views whose wavefronts one step can carry
 constexpr int LKEEP = 40;              // entries of a cell list the sweep keeps (MAX_NUM_OF_PATCHES <= 32, plus slack)
@@ -44,6 +44,8 @@ struct SweepArgs {
     int wslot_base;                        // first per-warp scratch slot of this launch
     int split;                             // host: run heavy / light cells as two concurrent launches on wide steps
     int heavy_est;                         // dest cells with at least this many estimated full-cost tries count as heavy
+    int coop;                              // 1: full cells, 2: every cell with four warps refines one candidate with all of them (coop_refine)
+    int room_weight;                       // cost weight of a try into a cell that still has room (k4_plan)
     unsigned long long* stats;             // SweepStat
     unsigned long long* step_max;          // slowest dest cell of this step, ns (one word per step, zeroed by the host)
 };
@@ -183,6 +185,14 @@ struct CellShared {
     int nl, nrem, nnew, nsrc;
     int version;                 // seqlock: odd while a commit is in progress
     int next_try, commit_ptr;
+    // cooperative refinement (all warps of the cell work on ONE candidate): command, context and per-candidate results
+    int coop, cmd;
+    float rs_center[4], rs_ray[4], rs_x[4], rs_n[4];
+    float rs_dscale;
+    int rs_nv, rs_warp;          // rs_warp: CTA warp whose WarpScratch holds the image list
+    unsigned long long rs_stream;
+    double res_cost[PMR1_CANDS];
+    double res_x[PMR1_CANDS][3];
 };
 
 struct TrySnap {
@@ -219,6 +229,129 @@ struct Cand {                    // a candidate after stage A (its image list is
     int nv, nvv;
     float ncc, dscale, ascale, tmp;
 };
+
+// ---- Optim::refinePatch by ALL warps of a dest cell --------------------------------------------------------------------------
+// Same schedule, same arithmetic and therefore the same result as warp_refine, but the 8 candidates of a PMR1 level are spread
+// over the 16 evaluator groups of four warps: one candidate per pair of groups, the pair splitting the non-reference views
+// (both grab the reference texture).  The per-view terms travel to one lane and are summed there in view order, exactly as
+// Optim::cost_func does, so the cost is bit-identical to the single-warp evaluation.  A level costs 1 + 3 texture grabs of
+// latency instead of 2 x 6.  Every participating warp calls this with the same arguments (read from the cell's shared block).
+template <int WS, typename Sync>
+__device__ __forceinline__ float coop_refine(const CandParams& cp, CellShared& cs, const int* images, float* weights, V4& X, V4& N, int nv,
+                                             float dscale, uint64_t stream, int cell_warp, int nwarps, int lane, Sync& cell_sync) {
+    constexpr int GW = WS <= 8 ? 8 : 16;
+    constexpr int G = 32 / GW;
+    const Params& p = cp.p;
+    const int grp = lane / GW, col = lane % GW;
+    const float cmask = col < WS ? 1.0f : 0.0f;
+    const unsigned gm = group_mask<GW>(lane);
+    const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
+    const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
+    RefineCtx rc;
+    rc.center = X;
+    rc.ref = images[0];
+    rc.ray = sub4(X, ld4(p.views[rc.ref].center));
+    rc.ray = div4(rc.ray, norm4(rc.ray));
+    rc.dscale = dscale;
+    if (cell_warp == 0) compute_weights(p, X, N, images, nv, weights, lane);      // m_weights of the UNREFINED patch (optim.cpp:490)
+    double best[3];
+    encode(cp, rc, X, N, best);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) best[i] = fmax(fmin(best[i], ub[i]), lb[i]);
+    double fbest = group_cost<WS, GW>(cp, rc, best, images, nv, col, cmask, gm);  // every group: the same value
+    __syncwarp();
+    const int tg = nwarps * G;                         // evaluator groups of the cell
+    const int halves = tg >= 2 * PMR1_CANDS ? 2 : 1;   // groups per candidate
+    const int gidx = cell_warp * G + grp;              // this group's index in the cell
+    const int sz = min(p.tau, nv);
+    const int minimum = min(p.min_image_num, sz);
+    const int n_o = sz - 1;                            // non-reference views
+    const int h0 = halves == 2 ? n_o / 2 : n_o;        // views [1, 1 + h0) go to half 0, the rest to half 1
+    const unsigned pairmask = halves == 2 ? (GW == 8 ? (0xffffu << (16 * (lane / 16))) : 0xffffffffu) : gm;
+    double r[3] = {4.0, 4.0, 4.0};
+#pragma unroll 1
+    for (int level = 0; level < PMR1_LEVELS; ++level) {
+#pragma unroll 1
+        for (int cb = 0; cb < PMR1_CANDS; cb += tg / halves) {
+            const int cnd = cb + gidx / halves, half = gidx % halves;
+            const bool live = cnd < PMR1_CANDS;
+            uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)level, (uint32_t)cnd};
+            philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
+            double xc[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) xc[i] = fmax(fmin(__dadd_rn(best[i], __dmul_rn(r[i], uniform_pm1(ctr[i]))), ub[i]), lb[i]);
+            // Optim::cost_func, this group's share of the views
+            V4 coord, normal, px, py;
+            decode(cp, rc, xc, coord, normal);
+            get_paxes(p.views[rc.ref], coord, normal, p.level_scale, px, py);
+            float t0[WS][3], t[WS][3];
+            float inv0, inv;
+            const bool ref_ok = group_grab<WS, GW>(p, images[0], coord, normal, px, py, col, cmask, t0, inv0, gm) >= 0;
+            const int i_first = half == 0 ? 1 : 1 + h0, i_last = half == 0 ? 1 + h0 : sz;
+            float val[PMK_MAX_TAU];
+#pragma unroll
+            for (int k = 0; k < PMK_MAX_TAU; ++k) val[k] = 0.0f;
+            int okmask = 0;
+#pragma unroll 1
+            for (int i = i_first; i < i_last; ++i) {
+                if (group_grab<WS, GW>(p, images[i], coord, normal, px, py, col, cmask, t, inv, gm) < 0) continue;
+                const float d = group_dot<WS, GW>(t0, inv0, t, inv, gm);
+                const float v = robustincc(__double2float_rn(1.0 - (double)d));
+                const int k = i - i_first;
+#pragma unroll
+                for (int kk = 0; kk < PMK_MAX_TAU; ++kk) if (kk == k) val[kk] = v;
+                okmask |= 1 << k;
+            }
+            // the second half hands its terms to the first (lanes GW apart)
+            float oval[PMK_MAX_TAU];
+#pragma unroll
+            for (int k = 0; k < PMK_MAX_TAU; ++k) oval[k] = 0.0f;
+            int ookmask = 0;
+            if (halves == 2) {
+#pragma unroll
+                for (int k = 0; k < PMK_MAX_TAU / 2; ++k) oval[k] = __shfl_xor_sync(pairmask, val[k], GW);
+                ookmask = __shfl_xor_sync(pairmask, okmask, GW);
+            }
+            if (live && half == 0 && col == 0) {
+                double fc = 2.0;
+                if (ref_ok) {
+                    double ans = 0.0;
+                    int denom = 0;
+#pragma unroll
+                    for (int k = 0; k < PMK_MAX_TAU; ++k) if (k < h0 && ((okmask >> k) & 1)) { ans += (double)val[k]; ++denom; }
+                    if (halves == 2) {
+#pragma unroll
+                        for (int k = 0; k < PMK_MAX_TAU / 2; ++k) if (k < n_o - h0 && ((ookmask >> k) & 1)) { ans += (double)oval[k]; ++denom; }
+                    }
+                    fc = denom < minimum - 1 ? 2.0 : ans / (double)denom;
+                }
+                cs.res_cost[cnd] = fc;
+                cs.res_x[cnd][0] = xc[0]; cs.res_x[cnd][1] = xc[1]; cs.res_x[cnd][2] = xc[2];
+            }
+        }
+        cell_sync();
+        // argmin over the level's candidates in index order, lowest index on ties (strict <), as the sequential loop does
+        double fwin = cs.res_cost[0];
+        int cwin = 0;
+        for (int c = 1; c < PMR1_CANDS; ++c) { const double fc = cs.res_cost[c]; if (fc < fwin) { fwin = fc; cwin = c; } }
+        if (fwin < fbest) { fbest = fwin; best[0] = cs.res_x[cwin][0]; best[1] = cs.res_x[cwin][1]; best[2] = cs.res_x[cwin][2]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = __dmul_rn(r[i], 0.6);
+        cell_sync();
+    }
+    // optim.cpp:534-541: decode, normal.w = 0, ncc = 1.0 - unrobustincc(computeINCC(...)) with the stale weights (the caller's warp)
+    V4 Xf, Nf;
+    decode(cp, rc, best, Xf, Nf);
+    float ncc = 0.0f;
+    if (cell_warp == 0) {
+        const float incc = group_incc<WS, GW>(p, Xf, Nf, images, nv, weights, col, cmask, gm);
+        ncc = __double2float_rn(1.0 - (double)unrobustincc(incc));
+    }
+    __syncwarp();
+    X = Xf;
+    N = V4{Nf.x, Nf.y, Nf.z, 0.0f};
+    return ncc;
+}
 
 #ifndef PMK_SWEEP_MINB
 #define PMK_SWEEP_MINB 2
@@ -302,12 +435,29 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                 }
                 __syncwarp();
             }
-            if (lane == 0) { cs.nl = nl; cs.nrem = nrem; cs.nnew = 0; cs.nsrc = nsrc; cs.version = 0; cs.next_try = 0; cs.commit_ptr = 0; }
+            if (lane == 0) {
+                cs.nl = nl; cs.nrem = nrem; cs.nnew = 0; cs.nsrc = nsrc; cs.version = 0; cs.next_try = 0; cs.commit_ptr = 0;
+                // a full cell's tries form a serial chain (each replacement moves the next try): all warps refine ONE candidate
+                cs.coop = (sa.coop && wpc == CAND_WARPS && (sa.coop == 2 || nl >= maxp)) ? 1 : 0;
+                cs.cmd = 0;
+            }
         }
         cell_sync();
         const int ntries = 2 * cs.nsrc;                                                    // MAX_NUM_OF_PROPAG tries per call
+        const bool coop = cs.coop != 0;
+        if (coop && warp == 0) stat[SS_COOP_CELLS] += 1;
+        if (coop && warp != 0) {
+            // helper warps of a cooperative cell: join every refinement the cell's first warp announces
+            while (true) {
+                cell_sync();
+                if (cs.cmd == 2) break;
+                V4 hX{cs.rs_x[0], cs.rs_x[1], cs.rs_x[2], cs.rs_x[3]}, hN{cs.rs_n[0], cs.rs_n[1], cs.rs_n[2], cs.rs_n[3]};
+                const WarpScratch& mws = reinterpret_cast<const WarpScratch*>(smem_raw)[cs.rs_warp];
+                coop_refine<WS>(cp, cs, mws.images, nullptr, hX, hN, cs.rs_nv, cs.rs_dscale, cs.rs_stream, warp, wpc, lane, cell_sync);
+            }
+        }
         // ================= the propagatePatch tries (propagate.cpp:122-218), speculative, committed in order =================
-        while (true) {
+        while (!(coop && warp != 0)) {
             int t = 0;
             if (lane == 0) t = atomicAdd(&cs.next_try, 1);
             t = __shfl_sync(0xffffffffu, t, 0);
@@ -375,6 +525,16 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                             float dscale, ascale;
                             if (warp_pre_process<WS>(cp, ws, X, N, nv, dscale, ascale, lane) == -1) outcome = TRY_FAIL0;
                             else {
+                                if (coop) {
+                                    if (lane == 0) {
+                                        cs.rs_x[0] = X.x; cs.rs_x[1] = X.y; cs.rs_x[2] = X.z; cs.rs_x[3] = X.w;
+                                        cs.rs_n[0] = N.x; cs.rs_n[1] = N.y; cs.rs_n[2] = N.z; cs.rs_n[3] = N.w;
+                                        cs.rs_dscale = dscale; cs.rs_nv = nv; cs.rs_warp = cta_warp; cs.rs_stream = stream; cs.cmd = 1;
+                                    }
+                                    cell_sync();
+                                    stat[SS_COOP_REFINES] += 1;
+                                    ncc = coop_refine<WS>(cp, cs, ws.images, ws.units, X, N, nv, dscale, stream, 0, wpc, lane, cell_sync);
+                                } else
                                 ncc = warp_refine<WS>(cp, ws, X, N, nv, dscale, stream, nullptr, lane);
                                 ncc = __shfl_sync(0xffffffffu, ncc, 0);
                                 X = V4{__shfl_sync(0xffffffffu, X.x, 0), __shfl_sync(0xffffffffu, X.y, 0), __shfl_sync(0xffffffffu, X.z, 0), __shfl_sync(0xffffffffu, X.w, 0)};
@@ -487,6 +647,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
             if (lane == 0) cs.commit_ptr = t + 1;
             __syncwarp();
         }
+        if (coop && warp == 0) { if (lane == 0) cs.cmd = 2; cell_sync(); }
         cell_sync();
         // ---- hand the step's mutations to k4_apply ----
         if (warp == 0) {
@@ -514,14 +675,15 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
 
 // ---- longest-first schedule of a step ---------------------------------------------------------------------------------------
 // A step ends with its slowest dest cell, so the cells are started in decreasing order of a cost estimate: the number of
-// propagatePatch calls aimed at the cell (patches of its two source cells whose reference view is the swept view), doubled
-// while the cell still has room (every try then runs the full optimisation instead of first having to beat the worst patch).
+// propagatePatch calls aimed at the cell (patches of its two source cells whose reference view is the swept view), times
+// `room_weight` while the cell still has room (every try then runs the full optimisation instead of first having to beat the
+// worst patch's NCC, which most tries fail).
 // One block; counting sort on the estimate.  The order only changes WHEN a cell runs, never what it computes.
 
 __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const SweepArgs sa, int* __restrict__ order) {
     const StoreDev& st = sp.st;
     const Params& p = sp.cp.p;
-    constexpr int NBIN = 2 * SRC_MAX + 2;
+    constexpr int NBIN = 8 * SRC_MAX + 2;
     __shared__ int hist[NBIN], offs[NBIN];
     for (int i = threadIdx.x; i < NBIN; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -553,7 +715,7 @@ __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const Swee
             int nd = 0;
             const int n = min(st.ccount[cD], st.cell_cap);
             for (int s2 = 0; s2 < n; ++s2) { const int e = st.cslots[(size_t)cD * st.cell_cap + s2]; if (e != SLOT_TOMB && e >= 0) ++nd; }
-            est = min(NBIN - 1, nsrc * (nd < maxp ? 2 : 1));
+            est = min(NBIN - 1, nsrc * (nd < maxp ? sa.room_weight : 1));
             atomicAdd(&hist[est], 1);
         }
     }
@@ -591,7 +753,7 @@ __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const Swee
         int nd = 0;
         const int n = min(st.ccount[cD], st.cell_cap);
         for (int s2 = 0; s2 < n; ++s2) { const int e = st.cslots[(size_t)cD * st.cell_cap + s2]; if (e != SLOT_TOMB && e >= 0) ++nd; }
-        const int est = min(NBIN - 1, nsrc * (nd < maxp ? 2 : 1));
+        const int est = min(NBIN - 1, nsrc * (nd < maxp ? sa.room_weight : 1));
         order[atomicAdd(&offs[est], 1)] = task;
     }
 }

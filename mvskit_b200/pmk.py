@@ -304,7 +304,7 @@ class Context:
         _chk(lib().pmk_store_colors(self.h, n, _p(out)))
         return out
 
-    SWEEP_STATS = ("calls", "tries", "gen_null", "ncc_lose", "fail0", "fail1", "added", "replaced", "trimmed", "evals", "cell_ns", "step_max_ns", "steps")
+    SWEEP_STATS = ("calls", "tries", "gen_null", "ncc_lose", "fail0", "fail1", "added", "replaced", "trimmed", "evals", "cell_ns", "step_max_ns", "steps", "coop_cells", "coop_refines")
 
     def propagate(self, it: int, seed: int) -> dict:
         """Propagate::run(iter)."""
