@@ -10,6 +10,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nvjpeg.h>
+
 #include "pmk_filter.cuh"
 
 using namespace pmk;
@@ -363,8 +366,8 @@ void pmk_destroy(pmk_ctx* ctx) {
     delete ctx;
 }
 
-int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int width, int height) {
-    if (!ctx || !P || !rgb) return fail(PMK_ERR_ARG, "pmk_set_view: null argument");
+static int set_view_impl(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, bool on_device, int width, int height) {
+    if (!ctx || !P || (!rgb && !on_device)) return fail(PMK_ERR_ARG, "pmk_set_view: null argument");
     if (view < 0 || view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_set_view: view out of range");
     const int nlevels = ctx->cfg.level + 3, level = ctx->cfg.level;
     if (width < (16 << nlevels) / 2 || height < (16 << nlevels) / 2) return fail(PMK_ERR_ARG, "pmk_set_view: image too small for the pyramid");
@@ -423,8 +426,10 @@ int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int
     vc.gw = (vc.w[level] + ctx->cfg.csize - 1) / ctx->cfg.csize;
     vc.gh = (vc.h[level] + ctx->cfg.csize - 1) / ctx->cfg.csize;
     const size_t npix0 = (size_t)width * height;
-    { const int rc = ensure(ctx, ctx->s_misc[0], npix0 * 3); if (rc) return rc; }
-    CUDA_TRY(cudaMemcpyAsync(ctx->s_misc[0].p, rgb, npix0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+    if (!on_device) {
+        { const int rc = ensure(ctx, ctx->s_misc[0], npix0 * 3); if (rc) return rc; }
+        CUDA_TRY(cudaMemcpyAsync(ctx->s_misc[0].p, rgb, npix0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+    }
     for (int l = 0; l < nlevels; ++l) {
         void* d = nullptr;
         CUDA_TRY(cudaMalloc(&d, (size_t)vc.w[l] * vc.h[l] * sizeof(Texel)));
@@ -443,6 +448,72 @@ int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int
     ctx->view_set[view] = 1;
     ctx->views_dirty = true;
     return PMK_OK;
+}
+
+int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int width, int height) {
+    if (!rgb) return fail(PMK_ERR_ARG, "pmk_set_view: null argument");
+    return set_view_impl(ctx, view, P, rgb, false, width, height);
+}
+
+// ---- JPEG ingest: nvJPEG decodes straight into the staging buffer K0 reads (Image::readJpeg, image/image.cpp:827-879) ----------------
+namespace {
+struct NvjpegApi {
+    void* handle = nullptr;
+    nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t*) = nullptr;
+    nvjpegStatus_t (*Destroy)(nvjpegHandle_t) = nullptr;
+    nvjpegStatus_t (*JpegStateCreate)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
+    nvjpegStatus_t (*JpegStateDestroy)(nvjpegJpegState_t) = nullptr;
+    nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
+    nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t, nvjpegImage_t*, cudaStream_t) = nullptr;
+};
+NvjpegApi* nvjpeg_api() {
+    static NvjpegApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12", "/usr/local/cuda/lib64/libnvjpeg.so"};
+        for (const char* nm : names) { api.handle = dlopen(nm, RTLD_NOW); if (api.handle) break; }
+        if (api.handle) {
+            api.CreateSimple = (decltype(api.CreateSimple))dlsym(api.handle, "nvjpegCreateSimple");
+            api.Destroy = (decltype(api.Destroy))dlsym(api.handle, "nvjpegDestroy");
+            api.JpegStateCreate = (decltype(api.JpegStateCreate))dlsym(api.handle, "nvjpegJpegStateCreate");
+            api.JpegStateDestroy = (decltype(api.JpegStateDestroy))dlsym(api.handle, "nvjpegJpegStateDestroy");
+            api.GetImageInfo = (decltype(api.GetImageInfo))dlsym(api.handle, "nvjpegGetImageInfo");
+            api.Decode = (decltype(api.Decode))dlsym(api.handle, "nvjpegDecode");
+        }
+    }
+    return (api.handle && api.CreateSimple && api.Destroy && api.JpegStateCreate && api.JpegStateDestroy && api.GetImageInfo && api.Decode) ? &api : nullptr;
+}
+}  // namespace
+
+int pmk_set_view_jpeg(pmk_ctx* ctx, int view, const float* P, const uint8_t* jpeg, uint64_t nbytes, int* width_out, int* height_out) {
+    if (!ctx || !P || !jpeg || nbytes < 4) return fail(PMK_ERR_ARG, "pmk_set_view_jpeg: null argument");
+    if (jpeg[0] != 0xFF || jpeg[1] != 0xD8) return fail(PMK_ERR_ARG, "pmk_set_view_jpeg: not a JPEG stream (no SOI marker)");
+    NvjpegApi* api = nvjpeg_api();
+    if (!api) return fail(PMK_ERR_STATE, "pmk_set_view_jpeg: libnvjpeg.so.12 not found");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    nvjpegHandle_t h = nullptr;
+    nvjpegJpegState_t st = nullptr;
+    if (api->CreateSimple(&h) != NVJPEG_STATUS_SUCCESS) return fail(PMK_ERR_CUDA, "nvjpegCreateSimple failed");
+    int rc = PMK_OK, comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+    nvjpegChromaSubsampling_t sub;
+    do {
+        if (api->JpegStateCreate(h, &st) != NVJPEG_STATUS_SUCCESS) { rc = fail(PMK_ERR_CUDA, "nvjpegJpegStateCreate failed"); break; }
+        if (api->GetImageInfo(h, jpeg, (size_t)nbytes, &comps, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS) { rc = fail(PMK_ERR_ARG, "pmk_set_view_jpeg: cannot parse the JPEG header"); break; }
+        const int w = ws[0], hgt = hs[0];
+        if ((rc = ensure(ctx, ctx->s_misc[0], (size_t)w * hgt * 3))) break;
+        nvjpegImage_t out;
+        std::memset(&out, 0, sizeof(out));
+        out.channel[0] = (unsigned char*)ctx->s_misc[0].p;
+        out.pitch[0] = (size_t)w * 3;
+        if (api->Decode(h, st, jpeg, (size_t)nbytes, NVJPEG_OUTPUT_RGBI, &out, ctx->stream) != NVJPEG_STATUS_SUCCESS) { rc = fail(PMK_ERR_CUDA, "nvjpegDecode failed"); break; }
+        if (width_out) *width_out = w;
+        if (height_out) *height_out = hgt;
+        rc = set_view_impl(ctx, view, P, nullptr, true, w, hgt);      // synchronises the stream
+    } while (false);
+    if (st) api->JpegStateDestroy(st);
+    api->Destroy(h);
+    return rc;
 }
 
 int pmk_get_thresholds(pmk_ctx* ctx, pmk_thresholds* t) {

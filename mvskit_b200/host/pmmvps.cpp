@@ -176,8 +176,19 @@ void PhotoSet::init(PmMvps& pmmvps, const vector<int>& images, const string pref
             snprintf(iname, sizeof(iname), "%simage/%04d%04d.%s", prefix.c_str(), i, 0, ext[e]);
             ok = read_ppm(iname, rgb, w, h);
         }
-        if (!ok) die(string("Image not found or not a binary PPM payload (JPEG decode is outside this path): ") + iname);
-        chk(pmk_set_view(pmmvps.m_ctx, i, P, rgb.data(), w, h), "pmk_set_view");
+        if (ok) chk(pmk_set_view(pmmvps.m_ctx, i, P, rgb.data(), w, h), "pmk_set_view");
+        else {
+            // a real JPEG: decoded on the device (nvJPEG) where the reference calls CImg::load_jpeg (image.cpp:834-837)
+            snprintf(iname, sizeof(iname), "%simage/%04d%04d.jpg", prefix.c_str(), i, 0);
+            FILE* f = fopen(iname, "rb");
+            if (!f) die(string("Image not found: ") + iname);
+            vector<unsigned char> bytes;
+            unsigned char buf[65536];
+            size_t got;
+            while ((got = fread(buf, 1, sizeof(buf), f)) > 0) bytes.insert(bytes.end(), buf, buf + got);
+            fclose(f);
+            chk(pmk_set_view_jpeg(pmmvps.m_ctx, i, P, bytes.data(), bytes.size(), &w, &h), "pmk_set_view_jpeg");
+        }
         cerr << "*" << std::flush;
     }
     cerr << endl;

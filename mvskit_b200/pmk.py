@@ -137,6 +137,13 @@ class Context:
         assert rgb.ndim == 3 and rgb.shape[2] == 3
         _chk(lib().pmk_set_view(self.h, view, _p(P), _p(rgb), rgb.shape[1], rgb.shape[0]))
 
+    def set_view_jpeg(self, view: int, P: np.ndarray, jpeg: bytes):
+        P = np.ascontiguousarray(P, np.float32).reshape(12)
+        buf = np.frombuffer(jpeg, np.uint8)
+        w, h = C.c_int(), C.c_int()
+        _chk(lib().pmk_set_view_jpeg(self.h, view, _p(P), _p(buf), C.c_uint64(len(buf)), C.byref(w), C.byref(h)))
+        return w.value, h.value
+
     def set_scene(self, P: np.ndarray, images: Sequence[np.ndarray]):
         for v in range(self.nviews):
             self.set_view(v, P[v], images[v])
