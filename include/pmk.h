@@ -208,6 +208,10 @@ int pmk_store_checksum(pmk_ctx* ctx, uint64_t* out2);       /* {order-independen
 int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const float* normal4,
               float* project3, float* unit1, float* px4, float* py4, int* cell_ixy2, int* cell_ok);
 
+/* PmMvps::isNeighbor (pmmvps.cpp:117-147; hunit NULL: computed from the two reference views as in :117-121) and isNeighborRadius
+ * (:149-180; radius non-NULL) on n free-standing pairs.  A patch is 10 floats: coord4, normal4, m_dscale, (float)m_images[0]. */
+int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs10, const float* hunit, const float* radius, float threshold, int* out);
+
 /* Stream control / timing helpers for bench.py (no reference counterpart). */
 int pmk_sync(pmk_ctx* ctx);
 int pmk_device_alloc(pmk_ctx* ctx, uint64_t bytes, void** out);

@@ -1262,4 +1262,30 @@ int pmk_store_checksum(pmk_ctx* ctx, uint64_t* out2) {
     return PMK_OK;
 }
 
+int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs10, const float* hunit, const float* radius, float threshold, int* out) {
+    if (!ctx || !lhs10 || !rhs10 || !out) return fail(PMK_ERR_ARG, "pmk_probe_neighbor: null argument");
+    if (radius && !hunit) return fail(PMK_ERR_ARG, "pmk_probe_neighbor: radius needs hunit");
+    if (n <= 0) return PMK_OK;
+    for (int i = 0; i < n; ++i) {
+        const int lr = (int)lhs10[(size_t)i * 10 + 9], rr = (int)rhs10[(size_t)i * 10 + 9];
+        if (lr < 0 || lr >= ctx->cfg.nviews || rr < 0 || rr >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_neighbor: reference view out of range");
+    }
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    const size_t N = (size_t)n;
+    void *dl, *dr, *dh = nullptr, *dd = nullptr, *dout;
+    if ((rc = stage_in(ctx, 0, lhs10, N * 40, &dl)) || (rc = stage_in(ctx, 1, rhs10, N * 40, &dr)) || (rc = stage_in(ctx, 2, nullptr, N * 4, &dout))) return rc;
+    if (hunit && (rc = stage_in(ctx, 3, hunit, N * 4, &dh))) return rc;
+    if (radius && (rc = stage_in(ctx, 4, radius, N * 4, &dd))) return rc;
+    k_probe_neighbor<<<(n + 127) / 128, 128, 0, ctx->stream>>>(sp, n, (const float*)dl, (const float*)dr, (const float*)dh, (const float*)dd, threshold, (int*)dout);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
 }  // extern "C"

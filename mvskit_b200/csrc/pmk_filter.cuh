@@ -312,4 +312,18 @@ __global__ void k_store_add(const StoreParams sp, int first, int n, unsigned int
     }
 }
 
+// probe of PmMvps::isNeighbor / isNeighborRadius (pmmvps.cpp:117-180) on free-standing patch pairs; rec = coord4, normal4, dscale, ref
+__global__ void k_probe_neighbor(const StoreParams sp, int n, const float* __restrict__ lrec, const float* __restrict__ rrec,
+                                 const float* __restrict__ hunit, const float* __restrict__ radius, float thr, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PGeo l, r;
+    const float* a = lrec + (size_t)i * 10; const float* b = rrec + (size_t)i * 10;
+    l.X = V4{a[0], a[1], a[2], a[3]}; l.N = V4{a[4], a[5], a[6], a[7]}; l.dscale = a[8]; l.ref = (int)a[9];
+    r.X = V4{b[0], b[1], b[2], b[3]}; r.N = V4{b[4], b[5], b[6], b[7]}; r.dscale = b[8]; r.ref = (int)b[9];
+    if (radius) out[i] = is_neighbor_radius(sp, l, r, hunit[i], thr, radius[i]);
+    else if (hunit) out[i] = is_neighbor_h(sp, l, r, hunit[i], thr);
+    else out[i] = is_neighbor(sp, l, r, thr);
+}
+
 }  // namespace pmk

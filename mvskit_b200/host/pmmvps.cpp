@@ -573,51 +573,29 @@ void PmMvps::run() {                                                // pmmvps.cp
 }
 
 namespace {
-struct HostCam { float center[4]; float ipscale; };
-
-float host_unit(const PmMvps& pm, int index, const Vector4f& X) {   // Optim::getUnit (optim.cpp:34-41)
-    pmk_camera cam;
-    chk(pmk_get_camera(pm.m_ctx, index, 0, &cam), "pmk_get_camera");
-    float s = 0.0f;
-    for (int k = 0; k < 4; ++k) { const float d = X(k) - cam.center[k]; s = s + d * d; }
-    const float fz = std::sqrt(s);
-    if (cam.ipscale == 0.0f) return 1.0f;
-    return (float)(2.0 * fz * (1 << pm.m_level) / cam.ipscale);
+void pack10(const Patch& p, float* o) {
+    for (int k = 0; k < 4; ++k) { o[k] = p.m_coord(k); o[4 + k] = p.m_normal(k); }
+    o[8] = p.m_dscale;
+    o[9] = (float)(p.m_images.empty() ? 0 : p.m_images[0]);
 }
-
-inline float dot4h(const Vector4f& a, const Vector4f& b) { float s = a(0) * b(0); s = s + a(1) * b(1); s = s + a(2) * b(2); s = s + a(3) * b(3); return s; }
+int neighbor_probe(const PmMvps& pm, const Patch& lhs, const Patch& rhs, const float* hunit, const float* radius, float thr) {
+    float l[10], r[10];
+    int out = 0;
+    pack10(lhs, l); pack10(rhs, r);
+    chk(pmk_probe_neighbor(pm.m_ctx, 1, l, r, hunit, radius, thr, &out), "isNeighbor");
+    return out;
+}
 }  // namespace
 
-int PmMvps::isNeighbor(const Patch& lhs, const Patch& rhs, const float neighborThreshold) const {     // pmmvps.cpp:117-121
-    const float hunit = (host_unit(*this, lhs.m_images[0], lhs.m_coord) + host_unit(*this, rhs.m_images[0], rhs.m_coord)) / 2.0f * m_csize;
-    return isNeighbor(lhs, rhs, hunit, neighborThreshold);
+// the three neighbour tests run on the device (the decision arithmetic of pmmvps.cpp:117-180 in the reference's operation order)
+int PmMvps::isNeighbor(const Patch& lhs, const Patch& rhs, const float neighborThreshold) const {
+    return neighbor_probe(*this, lhs, rhs, nullptr, nullptr, neighborThreshold);
 }
 
-int PmMvps::isNeighbor(const Patch& lhs, const Patch& rhs, const float hunit, const float neighborThreshold) const {     // pmmvps.cpp:123-147
-    if (dot4h(lhs.m_normal, rhs.m_normal) < cosf(120.0f / M_PI * 180.0f)) return 0;      // the reference's constant, preserved
-    Vector4f diff, h;
-    for (int k = 0; k < 4; ++k) diff(k) = lhs.m_coord(k) - rhs.m_coord(k);
-    const float vunit = lhs.m_dscale + rhs.m_dscale;
-    const float f0 = dot4h(lhs.m_normal, diff), f1 = dot4h(rhs.m_normal, diff);
-    float ftmp = (fabsf(f0) + fabsf(f1)) / 2.0f;
-    ftmp /= vunit;
-    for (int k = 0; k < 4; ++k) h(k) = ((diff(k) - lhs.m_normal(k) * f0) + diff(k)) - rhs.m_normal(k) * f1;
-    const float hsize = std::sqrt(dot4h(h, h)) / 2.0f / hunit;
-    if (1.0f < hsize) ftmp /= std::min(2.0f, hsize);
-    return ftmp < neighborThreshold ? 1 : 0;
+int PmMvps::isNeighbor(const Patch& lhs, const Patch& rhs, const float hunit, const float neighborThreshold) const {
+    return neighbor_probe(*this, lhs, rhs, &hunit, nullptr, neighborThreshold);
 }
 
-int PmMvps::isNeighborRadius(const Patch& lhs, const Patch& rhs, const float hunit, const float neighborThreshold, const float radius) const {   // :149-180
-    if (dot4h(lhs.m_normal, rhs.m_normal) < cos(120.0f * M_PI / 180.0f)) return 0;
-    Vector4f diff, h;
-    for (int k = 0; k < 4; ++k) diff(k) = rhs.m_coord(k) - lhs.m_coord(k);
-    const float vunit = lhs.m_dscale + rhs.m_dscale;
-    const float f0 = dot4h(lhs.m_normal, diff), f1 = dot4h(rhs.m_normal, diff);
-    float ftmp = (fabsf(f0) + fabsf(f1)) / 2.0f;
-    ftmp /= vunit;
-    for (int k = 0; k < 4; ++k) h(k) = (2.0f * diff(k) - lhs.m_normal(k) * f0) - rhs.m_normal(k) * f1;
-    const float hsize = std::sqrt(dot4h(h, h)) / 2.0f / hunit;
-    if (radius / hunit < hsize) return 0;
-    if (1.0f < hsize) ftmp /= std::min(2.0f, hsize);
-    return ftmp < neighborThreshold ? 1 : 0;
+int PmMvps::isNeighborRadius(const Patch& lhs, const Patch& rhs, const float hunit, const float neighborThreshold, const float radius) const {
+    return neighbor_probe(*this, lhs, rhs, &hunit, &radius, neighborThreshold);
 }

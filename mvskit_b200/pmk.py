@@ -342,6 +342,15 @@ class Context:
         _chk(lib().pmk_filter(self.h, _p(c)))
         return [int(v) for v in c]
 
+    def probe_neighbor(self, lhs10, rhs10, thr: float, hunit=None, radius=None):
+        """PmMvps::isNeighbor / isNeighborRadius on pairs; a patch = coord4, normal4, dscale, reference view."""
+        lhs10, rhs10 = np.ascontiguousarray(lhs10, np.float32), np.ascontiguousarray(rhs10, np.float32)
+        hunit = np.ascontiguousarray(hunit, np.float32) if hunit is not None else None
+        radius = np.ascontiguousarray(radius, np.float32) if radius is not None else None
+        out = np.zeros(len(lhs10), np.int32)
+        _chk(lib().pmk_probe_neighbor(self.h, len(lhs10), _p(lhs10), _p(rhs10), _p(hunit), _p(radius), C.c_float(thr), _p(out)))
+        return out
+
     # -- multi-GPU --------------------------------------------------------------------------------------------
     def comm_init(self, rank: int, nranks: int, unique_id: Optional[bytes]):
         _chk(lib().pmk_comm_init(self.h, rank, nranks, unique_id))

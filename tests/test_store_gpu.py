@@ -278,3 +278,22 @@ def test_filter_run_end_to_end(ctx, reflib, populated, small_scene):
     assert np.quantile(z, 0.9) <= 2.5e-3, np.quantile(z, [0.5, 0.9, 0.99])   # the reference itself: median 6e-4, 90 % 1.3e-3 after one iteration
     rgb = ctx.store_colors(gb.n)
     assert rgb.std() > 5
+
+
+def test_is_neighbor_decisions_bit_exact(ctx, reflib, populated):
+    """PmMvps::isNeighbor (pmmvps.cpp:117-147, including its cosf(120 / pi * 180) constant) on pairs of stored patches: the device
+    decision equals the reference's for every pair (consecutive patches in collect order share cells, so both outcomes occur)."""
+    g = populated
+    _load_both(ctx, reflib, g, 1)
+    rb = reflib.get_patches()
+    n = rb.n
+    rng = np.random.RandomState(5)
+    a = rng.randint(0, n - 64, 4000).astype(np.int32)
+    b = (a + rng.randint(1, 64, 4000)).astype(np.int32)
+    rec = np.concatenate([rb.coord, rb.normal, rb.scal[:, 1:2], rb.images[:, 0:1].astype(np.float32)], axis=1).astype(np.float32)
+    for thr in (0.5, 1.0, 2.0):
+        want = reflib.is_neighbor(a, b, thr)
+        got = ctx.probe_neighbor(rec[a], rec[b], thr)
+        assert np.array_equal(got, want), (thr, int((got != want).sum()))
+        if thr == 0.5:
+            assert 0 < want.sum() < len(want)
