@@ -297,3 +297,51 @@ def test_is_neighbor_decisions_bit_exact(ctx, reflib, populated):
         assert np.array_equal(got, want), (thr, int((got != want).sum()))
         if thr == 0.5:
             assert 0 < want.sum() < len(want)
+
+
+def test_sweep_with_check_at_depth_two(ctx, reflib, populated, small_scene):
+    """m_depth = 2: postProcess ends with Optim::check (optim.cpp:300-323) -- computeGain against the cells, findNeighbors and
+    filterQuad -- reading depth maps and visible lists rebuilt identically on both sides.  Same wavefront steps, same decisions."""
+    g = populated
+    _load_both(ctx, reflib, g, 2)
+    reflib.filter_rebuild(0)
+    assert ctx.filter_rebuild(0) == g.n
+    reflib.refine_seed(SEED)
+    img = 1
+    gw, gh = reflib.grid_dims(img)
+    scale = small_scene.scene_scale
+    tot = dict(calls=0, new_ref=0, new_gpu=0, removed_ref=0, removed_gpu=0, removed_both=0, matched=0, close=0, fail1=0)
+    for d in (40, 41, 42):
+        rb = reflib.get_patches()
+        before = set(_key(rb.coord))
+        calls = reflib.propagate_diag(img, d, 1, 2)
+        st = ctx.propagate_diagonals(2, img, d, 1, SEED)
+        assert st["calls"] == calls, (d, st["calls"], calls)
+        tot["calls"] += calls
+        tot["fail1"] += st["fail1"]
+        ra, ga = reflib.get_patches(), ctx.store_get()
+        rk, gk = set(_key(ra.coord)), set(_key(ga.coord))
+        rrem, grem = before - rk, before - gk
+        tot["removed_ref"] += len(rrem); tot["removed_gpu"] += len(grem); tot["removed_both"] += len(rrem & grem)
+        rnew = [i for i, kk in enumerate(_key(ra.coord)) if kk not in before]
+        gnew = [i for i, kk in enumerate(_key(ga.coord)) if kk not in before]
+        tot["new_ref"] += len(rnew); tot["new_gpu"] += len(gnew)
+        rmap = {}
+        for i in rnew:
+            rmap.setdefault((int(ra.images[i, 0]), tuple(ra.grids[i, 0])), []).append(i)
+        for j in gnew:
+            cand = rmap.get((int(ga.images[j, 0]), tuple(ga.grids[j, 0])), [])
+            if cand:
+                tot["matched"] += 1
+                e = min(np.linalg.norm(ra.coord[i, :3] - ga.coord[j, :3]) for i in cand) / scale
+                tot["close"] += int(e <= 1e-3)
+        # continue from the reference's state on both sides (same records, same order, depth maps and visible lists rebuilt)
+        _load_both(ctx, reflib, reflib.get_patches(), 2)
+        reflib.filter_rebuild(0)
+        ctx.filter_rebuild(0)
+    print("depth-2 sweep parity:", tot)
+    assert tot["calls"] > 150 and tot["new_ref"] > 20, tot
+    assert abs(tot["new_gpu"] - tot["new_ref"]) <= max(3, 0.06 * tot["new_ref"]), tot
+    assert abs(tot["removed_gpu"] - tot["removed_ref"]) <= max(3, 0.06 * max(tot["removed_ref"], 1)), tot
+    assert tot["removed_both"] >= 0.9 * tot["removed_ref"], tot
+    assert tot["matched"] >= 0.9 * tot["new_gpu"] and tot["close"] >= 0.9 * tot["matched"], tot
