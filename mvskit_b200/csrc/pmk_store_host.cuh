@@ -419,8 +419,10 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
             CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_fork, 0));
             a.range_sel = 1; a.wpc = 4;
             k4_sweep<WS><<<std::max(1, std::min(ctx->cand_grid, sa.ntasks)), CAND_WARPS * 32, smem, st>>>(sp, a);
-            a.range_sel = 2; a.wpc = 1; a.wslot_base = ctx->cand_grid * CAND_WARPS;
-            k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, ctx->s_in>>>(sp, a);
+            static const int light_wpc = getenv("PMK_LIGHT_WPC") ? atoi(getenv("PMK_LIGHT_WPC")) : 2;
+            a.range_sel = 2; a.wpc = (light_wpc == 2 || light_wpc == 4) ? light_wpc : 1; a.wslot_base = ctx->cand_grid * CAND_WARPS;
+            const int lgrid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks * a.wpc + CAND_WARPS - 1) / CAND_WARPS));
+            k4_sweep<WS><<<lgrid, CAND_WARPS * 32, smem, ctx->s_in>>>(sp, a);
             CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->s_in));
             CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
             ctx->launches += 2;

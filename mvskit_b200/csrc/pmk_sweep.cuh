@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
             if (lane == 0) {
                 cs.nl = nl; cs.nrem = nrem; cs.nnew = 0; cs.nsrc = nsrc; cs.version = 0; cs.next_try = 0; cs.commit_ptr = 0;
                 // a full cell's tries form a serial chain (each replacement moves the next try): all warps refine ONE candidate
-                cs.coop = (sa.coop && wpc == CAND_WARPS && (sa.coop == 2 || nl >= maxp)) ? 1 : 0;
+                cs.coop = (sa.coop && wpc > 1 && (sa.coop == 2 || nl >= maxp)) ? 1 : 0;
                 cs.cmd = 0;
             }
         }
