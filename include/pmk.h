@@ -212,6 +212,10 @@ int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const f
  * (:149-180; radius non-NULL) on n free-standing pairs.  A patch is 10 floats: coord4, normal4, m_dscale, (float)m_images[0]. */
 int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs10, const float* hunit, const float* radius, float threshold, int* out);
 
+/* Profiling aid: nanoseconds the last sweep spent on every dest cell (all views, view-major, row-major cells).  The first call
+ * (out may be NULL) switches the recording on; every later call returns and clears the times. */
+int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells);
+
 /* Stream control / timing helpers for bench.py (no reference counterpart). */
 int pmk_sync(pmk_ctx* ctx);
 int pmk_device_alloc(pmk_ctx* ctx, uint64_t bytes, void** out);

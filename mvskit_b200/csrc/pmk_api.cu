@@ -1288,4 +1288,23 @@ int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs
     return PMK_OK;
 }
 
+int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_debug_cell_times: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    const size_t n = (size_t)s->d.total_cells;
+    if (!s->cell_ns) {
+        if ((rc = dalloc(ctx, &s->cell_ns, n))) return rc;
+        CUDA_TRY(cudaMemsetAsync(s->cell_ns, 0, n * sizeof(float), ctx->stream));
+    }
+    if (out_total_cells) {
+        CUDA_TRY(cudaMemcpyAsync(out_total_cells, s->cell_ns, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(s->cell_ns, 0, n * sizeof(float), ctx->stream));
+    }
+    return PMK_OK;
+}
+
 }  // extern "C"

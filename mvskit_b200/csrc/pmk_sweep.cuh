@@ -48,6 +48,7 @@ struct SweepArgs {
     int room_weight;                       // cost weight of a try into a cell that still has room (k4_plan)
     unsigned long long* stats;             // SweepStat
     unsigned long long* step_max;          // slowest dest cell of this step, ns (one word per step, zeroed by the host)
+    float* cell_ns;                        // optional [total_cells]: time spent on each dest cell in its last visit (profiling)
 };
 
 struct SweepScratch {                  // per warp
@@ -664,6 +665,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
                 atomicAdd(sa.stats + SS_CELL_NS, t_end - t_begin);
                 atomicMax(sa.step_max, t_end - t_begin);
+                if (sa.cell_ns) sa.cell_ns[cD] = (float)(t_end - t_begin);
             }
         }
         cell_sync();
