@@ -43,21 +43,7 @@ __global__ void k5_count_alive(const unsigned long long* __restrict__ keys, int 
     if (alive && !next_alive) *out = p + 1;
 }
 
-// ---- K5b: gather the surviving patches into collect order (dst arrays are the second buffer set) -----------------------------------
-__global__ void k5_gather(const StoreDev src, const StoreDev dst, const int* __restrict__ perm, int nalive) {
-    const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int q = gwarp; q < nalive; q += nwarps) {
-        const int p = perm[q];
-        const int ni = src.nimg[p], nv = src.nvimg[p];
-        if (lane == 0) {
-            dst.coord[q] = src.coord[p]; dst.normal[q] = src.normal[p]; dst.scal[q] = src.scal[p];
-            dst.nimg[q] = ni; dst.nvimg[q] = nv; dst.state[q] = 1; dst.birth[q] = src.birth[p];
-        }
-        for (int i = lane; i < ni; i += 32) { dst.images[(size_t)q * dst.maxv + i] = src.images[(size_t)p * src.maxv + i]; dst.cells[(size_t)q * dst.maxv + i] = src.cells[(size_t)p * src.maxv + i]; }
-        for (int i = lane; i < nv; i += 32) { dst.vimages[(size_t)q * dst.maxv + i] = src.vimages[(size_t)p * src.maxv + i]; dst.vcells[(size_t)q * dst.maxv + i] = src.vcells[(size_t)p * src.maxv + i]; }
-    }
-}
+// ---- K5b: the gather into collect order is k_gather_rows (pmk_store_host.cuh): one array at a time through a scratch buffer ----
 
 // ---- K5c: m_pgrids from the patch lists ----------------------------------------------------------------------------------------------
 __global__ void k5_register(const StoreParams sp, int n, int first, int with_v, int with_depth) {
