@@ -58,3 +58,34 @@ def test_wavefront_schedule_reproduces_the_raster_sweep(tiny):
     zb = np.abs(b.coord[:, 2]) / scene.scene_scale
     assert abs(np.median(za) - np.median(zb)) <= 1e-4 and abs(np.quantile(za, 0.9) - np.quantile(zb, 0.9)) <= 2e-4
     assert abs(a.scal[:, 0].mean() - b.scal[:, 0].mean()) <= 1e-3
+
+
+def test_reference_run_cannot_pass_iteration_zero(tmp_path):
+    """Provenance of a claim in DESIGN.md: the reference's own PmMvps::run (pmmvps.cpp:76-114) exits at iteration 1, because
+    Propagate::run fills m_queue (propagate.cpp:43) and nothing drains it (:39-42).  End-to-end comparisons therefore use
+    iteration 0 of the reference, and the host mirror's run() is the loop the reference meant to execute."""
+    import subprocess
+    import sys
+    import textwrap
+    from oracle import pyoracle
+    if not os.path.exists(pyoracle.REF_SO):
+        pytest.skip("oracle/_ref/libpmref.so not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    err = tmp_path / "stderr.txt"
+    code = textwrap.dedent(f"""
+        import os, sys, tempfile
+        sys.path.insert(0, {root!r})
+        from mvskit_b200 import synth
+        from oracle import pyoracle
+        scene = synth.make_scene(1, scale=0.4).render()
+        ref = pyoracle.RefLib(synth.write_scene(scene, tempfile.mkdtemp()))
+        ref.L.pmref_quiet(0)
+        os.dup2(os.open({str(err)!r}, os.O_WRONLY | os.O_CREAT | os.O_TRUNC), 2)
+        ref.refine_seed(1)
+        ref.run()
+        print("completed")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    log = open(err).read()
+    assert r.returncode == 1 and "completed" not in r.stdout
+    assert "Iteration: 1" in log and "queue is not empty in propagate" in log and "Iteration: 2" not in log
