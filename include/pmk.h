@@ -212,6 +212,14 @@ int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const f
  * (:149-180; radius non-NULL) on n free-standing pairs.  A patch is 10 floats: coord4, normal4, m_dscale, (float)m_images[0]. */
 int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs10, const float* hunit, const float* radius, float threshold, int* out);
 
+/* The store-reading tail of Optim::postProcess on n free-standing candidates against the current store (optim.cpp:285-323):
+ * PatchManager::setGrids, setVImagesVGrids (patch_manager.cpp:267-301) and Optim::check = Filter::computeGain (filter.cpp:108-146), and,
+ * when the gain is not negative, PatchManager::findNeighbors(patch, 4, 2) + Filter::filterQuad for more than 6 neighbours.
+ * ret = check's return (1 = reject), gain = m_tmp, nneighbors = findNeighbors' size (-1 when the gain already rejected),
+ * vimages_out[n][stride] (-1 padded) / nvimages_out = the visible lists.  stride >= nviews. */
+int pmk_probe_check(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages, int stride,
+                    int* ret, float* gain, int* nneighbors, int* vimages_out, int* nvimages_out);
+
 /* Profiling aid: nanoseconds the last sweep spent on every dest cell (all views, view-major, row-major cells).  The first call
  * (out may be NULL) switches the recording on; every later call returns and clears the times. */
 int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells);

@@ -1307,4 +1307,42 @@ int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells) {
     return PMK_OK;
 }
 
+int pmk_probe_check(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages, int stride,
+                    int* ret, float* gain, int* nneighbors, int* vimages_out, int* nvimages_out) {
+    if (!ctx || !coord4 || !normal4 || !scal4 || !images || !nimages || !ret || !gain || !nneighbors || !vimages_out || !nvimages_out)
+        return fail(PMK_ERR_ARG, "pmk_probe_check: null argument");
+    if (n <= 0) return PMK_OK;
+    if (stride < ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_check: stride must hold every view (vimages_out)");
+    for (int i = 0; i < n; ++i) {
+        if (nimages[i] < 1 || nimages[i] > stride) return fail(PMK_ERR_ARG, "pmk_probe_check: bad image count");
+        for (int k = 0; k < nimages[i]; ++k) if (images[(size_t)i * stride + k] < 0 || images[(size_t)i * stride + k] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_check: image index out of range");
+    }
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    const size_t N = (size_t)n;
+    void *dc, *dn, *ds, *di, *dni, *dret, *dg, *dnn, *dvi, *dnv;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, scal4, N * 16, &ds)) ||
+        (rc = stage_in(ctx, 3, images, N * stride * 4, &di)) || (rc = stage_in(ctx, 4, nimages, N * 4, &dni)) || (rc = stage_in(ctx, 5, nullptr, N * 4, &dret)) ||
+        (rc = stage_in(ctx, 6, nullptr, N * 4, &dg)) || (rc = stage_in(ctx, 7, nullptr, N * 4, &dnn)) || (rc = stage_in(ctx, 8, nullptr, N * stride * 4, &dvi)) ||
+        (rc = stage_in(ctx, 9, nullptr, N * 4, &dnv)))
+        return rc;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    const size_t smem = CAND_WARPS * (sizeof(WarpScratch) + 3 * CAND_MAXV * sizeof(int));
+    k_probe_check<<<grid, CAND_WARPS * 32, smem, ctx->stream>>>(sp, n, (const float4*)dc, (const float4*)dn, (const float4*)ds, (const int*)di, (const int*)dni, stride,
+                                                               (int*)dret, (float*)dg, (int*)dnn, (int*)dvi, (int*)dnv);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(ret, dret, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(gain, dg, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nneighbors, dnn, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(vimages_out, dvi, N * stride * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nvimages_out, dnv, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return store_check_overflow(ctx);
+}
+
 }  // extern "C"

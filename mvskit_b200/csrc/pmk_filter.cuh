@@ -312,4 +312,48 @@ __global__ void k_probe_neighbor(const StoreParams sp, int n, const float* __res
     else out[i] = is_neighbor(sp, l, r, thr);
 }
 
+// PatchManager::setGrids + setVImagesVGrids + Optim::check (optim.cpp:285-323) on free-standing candidates against the current store:
+// ret = check's return (1 = rejected), gain = m_tmp, nn = findNeighbors count, vimages/vcells = the visible lists it used.
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_probe_check(const StoreParams sp, int n, const float4* __restrict__ coord, const float4* __restrict__ normal,
+                                                                  const float4* __restrict__ scal, const int* __restrict__ images, const int* __restrict__ nimg, int stride,
+                                                                  int* __restrict__ ret, float* __restrict__ gain_out, int* __restrict__ nn_out,
+                                                                  int* __restrict__ vimages_out, int* __restrict__ nvimg_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& ws = warp_scratch(smem_raw);
+    int* cells = reinterpret_cast<int*>(smem_raw + CAND_WARPS * sizeof(WarpScratch)) + (threadIdx.x >> 5) * 3 * CAND_MAXV;
+    int* vimg = cells + CAND_MAXV;
+    int* vcell = vimg + CAND_MAXV;
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    const Overlay none{-1, nullptr, 0, nullptr, 0};
+    int* nb = sp.nb_scratch + (size_t)gwarp * NB_STRIDE;
+    for (int h = gwarp; h < n; h += gridDim.x * CAND_WARPS) {
+        const V4 X = f4v(coord[h]), N = f4v(normal[h]);
+        const float4 sc = scal[h];
+        const int nv = min(min(nimg[h], stride), CAND_MAXV);
+        for (int i = lane; i < nv; i += 32) {
+            const int v = images[(size_t)h * stride + i];
+            ws.images[i] = v;
+            const V3 q = project(p.views[v].P, X);
+            cells[i] = pack_cell(cell_of(q.x, p.csize), cell_of(q.y, p.csize));
+        }
+        __syncwarp();
+        const int nvv = warp_set_vimages(sp, ws, X, N, ws.images, nv, vimg, vcell, 0, lane);
+        PGeo me; me.X = X; me.N = N; me.dscale = sc.y; me.ref = ws.images[0];
+        const PatchLists pl{ws.images, cells, nv, vimg, vcell, nvv};
+        const float gain = warp_compute_gain(sp, me, sc.x, pl, none, lane);
+        int r = 0, nn = -1;
+        if (gain < 0.0f) r = 1;
+        else {
+            nn = warp_find_neighbors(sp, me, pl, 4.0f, 2, none, nb, lane);
+            if (6 < nn && warp_filter_quad(sp, me, pl, nb, nn, nullptr, lane)) r = 1;
+        }
+        if (lane == 0) { ret[h] = r; gain_out[h] = gain; nn_out[h] = nn; nvimg_out[h] = nvv; }
+        for (int i = lane; i < stride; i += 32) vimages_out[(size_t)h * stride + i] = i < nvv ? vimg[i] : -1;
+        __syncwarp();
+    }
+}
+
 }  // namespace pmk

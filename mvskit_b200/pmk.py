@@ -351,6 +351,16 @@ class Context:
         _chk(lib().pmk_probe_neighbor(self.h, len(lhs10), _p(lhs10), _p(rhs10), _p(hunit), _p(radius), C.c_float(thr), _p(out)))
         return out
 
+    def probe_check(self, coord, normal, scal, images, nimages):
+        """setVImagesVGrids + Optim::check on free-standing candidates -> ret, gain, neighbour count, vimages, nvimages."""
+        coord, normal, images, nimages = self._cv(coord, normal, images, nimages)
+        scal = np.ascontiguousarray(scal, np.float32)
+        n, stride = images.shape
+        ret, gain, nn = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        vimg, nvimg = np.zeros((n, stride), np.int32), np.zeros(n, np.int32)
+        _chk(lib().pmk_probe_check(self.h, n, _p(coord), _p(normal), _p(scal), _p(images), _p(nimages), stride, _p(ret), _p(gain), _p(nn), _p(vimg), _p(nvimg)))
+        return ret, gain, nn, vimg, nvimg
+
     # -- multi-GPU --------------------------------------------------------------------------------------------
     def comm_init(self, rank: int, nranks: int, unique_id: Optional[bytes]):
         _chk(lib().pmk_comm_init(self.h, rank, nranks, unique_id))

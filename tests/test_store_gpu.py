@@ -345,3 +345,36 @@ def test_sweep_with_check_at_depth_two(ctx, reflib, populated, small_scene):
     assert abs(tot["removed_gpu"] - tot["removed_ref"]) <= max(3, 0.06 * max(tot["removed_ref"], 1)), tot
     assert tot["removed_both"] >= 0.9 * tot["removed_ref"], tot
     assert tot["matched"] >= 0.9 * tot["new_gpu"] and tot["close"] >= 0.9 * tot["matched"], tot
+
+
+def test_check_on_free_standing_candidates(ctx, reflib, populated, small_scene):
+    """Optim::check (optim.cpp:300-323) with its setVImagesVGrids prelude on candidates that are NOT in the store: stored patches
+    pushed off the surface (their neighbours out-score them -> negative gain) and lightly perturbed ones (accepted).  Visible
+    lists bit-exact, gains equal (exact arithmetic on identical inputs), the same accept / reject decisions."""
+    g = populated
+    _load_both(ctx, reflib, g, 2)
+    reflib.filter_rebuild(0)
+    assert ctx.filter_rebuild(0) == g.n
+    rb = reflib.get_patches()
+    rng = np.random.RandomState(11)
+    pick = rng.choice(rb.n, 600, replace=False)
+    coord, normal, scal = rb.coord[pick].copy(), rb.normal[pick].copy(), rb.scal[pick].copy()
+    images, nimages = rb.images[pick].copy(), rb.nimages[pick].copy()
+    images[images < 0] = 0
+    shift = np.where(np.arange(600) % 2 == 0, 0.08, 0.0005)[:, None] * small_scene.scene_scale      # far off / almost on the surface
+    coord[:, :3] += normal[:, :3] * shift
+    scal[:, 0] = np.where(np.arange(600) % 2 == 0, 0.72, scal[:, 0])                                     # a mediocre score for the far ones
+    ret, gain, nn, vimg, nvimg = ctx.probe_check(coord, normal, scal, images, nimages)
+    same_v = same_ret = 0
+    rgain = np.zeros(600, np.float32)
+    rret = np.zeros(600, np.int32)
+    for i in range(600):
+        r, gn, out = reflib.check(coord[i], normal[i], scal[i], images[i, :nimages[i]])
+        rret[i], rgain[i] = r, gn
+        k = out.nvimages[0]
+        same_v += int(k == nvimg[i] and np.array_equal(out.vimages[0, :k], vimg[i, :k]))
+        same_ret += int(r == ret[i])
+    assert same_v == 600, same_v                                                   # isVisible0 decisions
+    assert np.abs(gain - rgain).max() <= 1e-5, np.abs(gain - rgain).max()         # computeGain
+    assert 50 < rret.sum() < 550, rret.sum()                                       # both outcomes occur
+    assert same_ret >= 590, same_ret                                               # gain sign exact; quad fit tolerance-bound
