@@ -3,11 +3,31 @@
 // `--filter-only ITER` is test/test_filter.cpp: m_depth = 1, readPatches(ITER), Filter::run.
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 
 #include "pmmvps.hpp"
 
+// --patch-io <in.patch> <out.patch>: parse a .patch file with the mirror's stream operators and write it back (no GPU needed);
+// the CPU test suite compares the records with what the reference itself reads from the same file.
+static int patch_io(const char* in_name, const char* out_name) {
+    std::ifstream in(in_name);
+    if (!in.is_open()) { std::cerr << "cannot open " << in_name << std::endl; return 1; }
+    std::string header;
+    int pnum = 0;
+    in >> header >> pnum;
+    std::ofstream out(out_name);
+    out << "PATCHES" << std::endl << pnum << std::endl;
+    for (int p = 0; p < pnum; ++p) {
+        Patch patch;
+        in >> patch;
+        out << patch << "\n";
+    }
+    return in.fail() ? 1 : 0;
+}
+
 int main(int argc, char* argv[]) {
+    if (argc == 4 && !strcmp(argv[1], "--patch-io")) return patch_io(argv[2], argv[3]);
     if (argc < 2) {
         std::cerr << "usage: " << argv[0] << " <prefix/> [option] [--device N] [--group G] [--filter-only ITER]" << std::endl;
         return 2;

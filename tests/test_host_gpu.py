@@ -79,3 +79,27 @@ def test_pmmvps_run_end_to_end(scene_dir, small_scene):
     assert (nimg >= 3).all() and np.median(ncc) > 0.95
     z = np.abs(coord[:, 2]) / small_scene.scene_scale
     assert np.quantile(z, 0.9) <= 2.0e-3, np.quantile(z, [0.5, 0.9, 0.99])
+
+
+def test_patch_file_round_trip_matches_what_the_reference_reads(scene_dir, reflib, tmp_path):
+    """The mirror's Patch stream operators (patch.cpp:31-88 format) on CPU: parse the seed file, write it back, and compare the
+    records with what the reference's own readPatches got from the same file."""
+    src = os.path.join(scene_dir, "ply", "00000000.patch")
+    out = str(tmp_path / "roundtrip.patch")
+    r = subprocess.run([_exe(), "--patch-io", src, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    coord, ncc, nimg = read_patch_file(out)
+    reflib.clear_patches()
+    reflib.set_depth(0)
+    reflib.create_patches()
+    rb = reflib.get_patches()
+    assert len(coord) == rb.n
+    # the reference's m_ppatches is in collect order, the file in write order: compare as sets of (coord, images count)
+    # (operator<< prints 6 significant digits, so the written coordinates agree to ~1e-5 of their magnitude)
+    ia, ib = np.lexsort(np.round(coord[:, :3], 3).T[::-1]), np.lexsort(np.round(rb.coord[:, :3], 3).T[::-1])
+    assert np.abs(coord[ia, :3] - rb.coord[ib, :3]).max() <= 1e-4
+    assert np.array_equal(nimg[ia], rb.nimages[ib])
+    # and a second pass through the operators is the identity on the text
+    out2 = str(tmp_path / "roundtrip2.patch")
+    assert subprocess.run([_exe(), "--patch-io", out, out2]).returncode == 0
+    assert open(out).read() == open(out2).read()
