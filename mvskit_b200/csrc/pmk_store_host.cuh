@@ -74,7 +74,10 @@ int store_init(pmk_ctx* ctx) {
     int rc = upload_views(ctx);
     if (rc) return rc;
     if (ctx->cfg.nviews > CAND_MAXV) return fail(PMK_ERR_ARG, "pmk: the patch store supports at most 128 views");
-    if (2 * ctx->cfg.csize * ctx->cfg.csize > 32) return fail(PMK_ERR_ARG, "pmk: csize too large for the sweep (2*csize^2 <= 32)");
+    // a dest cell receives the patches of two source cells (<= MAX_NUM_OF_PATCHES each) with two tries per patch: SRC_MAX sources and
+    // NEW_MAX staged patches per cell bound MAX_NUM_OF_PATCHES = 2 * csize^2 by 16
+    if (2 * ctx->cfg.csize * ctx->cfg.csize > SRC_MAX / 2 || 4 * ctx->cfg.csize * ctx->cfg.csize > NEW_MAX / 2 * 2)
+        return fail(PMK_ERR_ARG, "pmk: csize > 2 is not supported by the patch store (MAX_NUM_OF_PATCHES = 2 * csize^2 must be <= 16)");
     pmk_store* s = new pmk_store();
     ctx->store = s;
     const int nv = ctx->cfg.nviews;
