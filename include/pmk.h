@@ -215,7 +215,7 @@ int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs
 /* The store-reading tail of Optim::postProcess on n free-standing candidates against the current store (optim.cpp:285-323):
  * PatchManager::setGrids, setVImagesVGrids (patch_manager.cpp:267-301) and Optim::check = Filter::computeGain (filter.cpp:108-146), and,
  * when the gain is not negative, PatchManager::findNeighbors(patch, 4, 2) + Filter::filterQuad for more than 6 neighbours.
- * ret = check's return (1 = reject), gain = m_tmp, nneighbors = findNeighbors' size (-1 when the gain already rejected),
+ * ret = check's return (1 = reject; -2 = a listed view does not see the candidate inside its grid), gain = m_tmp, nneighbors = findNeighbors' size (-1 when the gain already rejected),
  * vimages_out[n][stride] (-1 padded) / nvimages_out = the visible lists.  stride >= nviews. */
 int pmk_probe_check(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages, int stride,
                     int* ret, float* gain, int* nneighbors, int* vimages_out, int* nvimages_out);

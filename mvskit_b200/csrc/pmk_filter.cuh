@@ -333,13 +333,24 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_probe_check(const StorePara
         const V4 X = f4v(coord[h]), N = f4v(normal[h]);
         const float4 sc = scal[h];
         const int nv = min(min(nimg[h], stride), CAND_MAXV);
+        bool outside = false;
         for (int i = lane; i < nv; i += 32) {
             const int v = images[(size_t)h * stride + i];
             ws.images[i] = v;
             const V3 q = project(p.views[v].P, X);
-            cells[i] = pack_cell(cell_of(q.x, p.csize), cell_of(q.y, p.csize));
+            const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
+            outside |= ix < 0 || p.views[v].gw <= ix || iy < 0 || p.views[v].gh <= iy;
+            cells[i] = pack_cell(ix, iy);
         }
         __syncwarp();
+        if (__any_sync(0xffffffffu, outside)) {
+            // the reference would index m_pgrids out of bounds here (computeGain, filter.cpp:113-118); such a candidate cannot come out
+            // of postProcess (addImages keeps only views whose projection lies inside the image): reported as ret = -2
+            if (lane == 0) { ret[h] = -2; gain_out[h] = 0.0f; nn_out[h] = -1; nvimg_out[h] = 0; }
+            for (int i = lane; i < stride; i += 32) vimages_out[(size_t)h * stride + i] = -1;
+            __syncwarp();
+            continue;
+        }
         const int nvv = warp_set_vimages(sp, ws, X, N, ws.images, nv, vimg, vcell, 0, lane);
         PGeo me; me.X = X; me.N = N; me.dscale = sc.y; me.ref = ws.images[0];
         const PatchLists pl{ws.images, cells, nv, vimg, vcell, nvv};
