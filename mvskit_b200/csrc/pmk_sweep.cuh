@@ -544,11 +544,18 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                                 outcome = r == 0 ? TRY_ACCEPT : TRY_FAIL1;
                                 cd.X = X; cd.N = N; cd.nv = nv; cd.ncc = ncc; cd.dscale = dscale; cd.ascale = ascale;
                                 if (r == 0) {
+                                    bool outside = false;
                                     for (int i = lane; i < nv; i += 32) {                      // setGrids (optim.cpp:285)
                                         const V3 q = project(p.views[ws.images[i]].P, X);
-                                        ss.cells[i] = pack_cell(cell_of(q.x, p.csize), cell_of(q.y, p.csize));
+                                        const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
+                                        outside |= ix < 0 || p.views[ws.images[i]].gw <= ix || iy < 0 || p.views[ws.images[i]].gh <= iy;
+                                        ss.cells[i] = pack_cell(ix, iy);
                                     }
                                     __syncwarp();
+                                    // Views inherited from the source patch are not re-checked by addImages, and the refinement moves
+                                    // the patch: a view can end up seeing it outside its grid.  The reference then writes m_pgrids out of
+                                    // bounds (addPatch, patch_manager.cpp:164-170); here the candidate is rejected like any postProcess failure.
+                                    if (__any_sync(0xffffffffu, outside)) outcome = TRY_FAIL1;
                                 }
                             }
                         }
