@@ -236,13 +236,14 @@ __device__ __forceinline__ float warp_compute_gain(const StoreParams& sp, const 
 
 // ---- PatchManager::findNeighbors (patch_manager.cpp:671-728): unique patches of the +-margin cells of every view of m_images
 // (m_pgrids and m_vpgrids) that pass isNeighborRadius.  Ids go to `out` in ascending order; returns the count.
-// Per view the (2 margin + 1)^2 cells are flattened into one slot range spread over the lanes; uniqueness (sort + unique by
-// pointer in the reference) comes from a warp-private open-addressing table of (call token, id) words in global scratch.
-constexpr int NB_HASH = 8192;          // table entries per warp (power of two, >= 2 * NB_CAP)
+// Per view the (2 margin + 1)^2 cells are flattened into one slot range spread over the lanes (binary search on a prefix held in
+// the lanes); a warp-private open-addressing table of (call token, id) words in global scratch makes every patch be tested once,
+// however many views' cells it shows up in (sort + unique by pointer in the reference).
+constexpr int NB_HASH = 16384;         // table entries per warp (power of two): every patch id SEEN in the searched cells goes in
 constexpr int NB_STRIDE = 2 * NB_CAP + 2 * NB_HASH + 4;   // ints of findNeighbors scratch per warp
 
-__device__ __forceinline__ bool nb_insert(unsigned long long* table, unsigned int token, int id) {
-    unsigned int h = ((unsigned int)id * 2654435761u) >> 19;                  // 13 bits
+__device__ __forceinline__ bool nb_insert(unsigned long long* table, unsigned int token, int id, bool& full) {
+    unsigned int h = ((unsigned int)id * 2654435761u) >> 18;                  // 14 bits
     const unsigned long long mine = ((unsigned long long)token << 32) | (unsigned int)id;
     for (int probe = 0; probe < NB_HASH; ++probe) {
         const unsigned long long cur = __ldcg(table + h);                    // L2: the table is written with atomics
@@ -256,6 +257,7 @@ __device__ __forceinline__ bool nb_insert(unsigned long long* table, unsigned in
         }
         h = (h + 1) & (NB_HASH - 1);
     }
+    full = true;                                                               // reported by the caller, never silent
     return false;
 }
 
@@ -307,15 +309,15 @@ __device__ __forceinline__ int warp_find_neighbors(const StoreParams& sp, const 
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         for (int base = 0; base < total; base += 32) {
-            const int f = base + lane;
-            int c = -1, slot = 0, nslot = 0;
-            for (int j = 0; j < ncell; ++j) {
-                const int pj = __shfl_sync(0xffffffffu, incl, j), nj = __shfl_sync(0xffffffffu, myn, j);
-                const int cj = __shfl_sync(0xffffffffu, myc, j), sj = __shfl_sync(0xffffffffu, mynslot, j);
-                if (c < 0 && f < pj && nj > 0 && f < total) { c = cj; slot = f - (pj - nj); nslot = sj; }
-            }
+            const int f = min(base + lane, total - 1);
+            // which cell does flat index f fall into: binary search on the inclusive prefix held by the lanes
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, j + step - 1); if (v <= f) j += step; }
+            const int c = __shfl_sync(0xffffffffu, myc, j), nslot = __shfl_sync(0xffffffffu, mynslot, j);
+            const int slot = f - (__shfl_sync(0xffffffffu, incl, j) - __shfl_sync(0xffffffffu, myn, j));
             int id = -1;
-            if (c >= 0) {
+            if (base + lane < total && c >= 0) {
                 if (slot < nslot) {
                     const int e = st.cslots[(size_t)c * st.cell_cap + slot];
                     if ((e & 0x7fffffff) != SLOT_TOMB) {
@@ -325,9 +327,9 @@ __device__ __forceinline__ int warp_find_neighbors(const StoreParams& sp, const 
                     }
                 } else id = ov.ids[slot - nslot];
             }
+            // a patch shows up in the cells of every view it is registered in: look at it once (the test does not depend on the view)
             bool hit = false;
-            if (id >= 0) hit = is_neighbor_radius(sp, me, load_geo(st, id), unit, thr, radius) != 0;
-            if (hit) hit = nb_insert(table, token, id);
+            if (id >= 0 && nb_insert(table, token, id, overflow)) hit = is_neighbor_radius(sp, me, load_geo(st, id), unit, thr, radius) != 0;
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (hit) { const int pos = nuni + __popc(m & ((1u << lane) - 1u)); if (pos < NB_CAP) out[pos] = id; }
             nuni += __popc(m);
@@ -335,7 +337,7 @@ __device__ __forceinline__ int warp_find_neighbors(const StoreParams& sp, const 
     }
     __syncwarp();
     if (nuni > NB_CAP) { overflow = true; nuni = NB_CAP; }
-    if (overflow && lane == 0) atomicAdd(st.counters + SC_NBOVER, 1);
+    if (__any_sync(0xffffffffu, overflow) && lane == 0) atomicAdd(st.counters + SC_NBOVER, 1);
     // ascending id order (ids follow creation order, identical on every replica and for every number of GPUs): the quadric fit
     // sums over the neighbours and must do so in one order everywhere
     int* tmp = out + NB_CAP;
