@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PMK_ABI_VERSION 2
+#define PMK_ABI_VERSION 3
 #define PMK_MAX_LEVELS 6
 #define PMK_MAX_TAU 8
 
@@ -92,6 +92,18 @@ int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int
  * absent) becomes an nvJPEG decode straight into the staging buffer K0 reads.  JPEG decoders differ in the last bit (IDCT, chroma
  * upsampling): against libjpeg the mean pixel difference is below 0.6 grey levels on 4:4:4 streams.  width_out / height_out may be NULL. */
 int pmk_set_view_jpeg(pmk_ctx* ctx, int view, const float* P, const uint8_t* jpeg, uint64_t nbytes, int* width_out, int* height_out);
+
+/* The silhouette mask of one view: Image::alloc's mask branch (image/image.cpp:143-161: readPGMImage / readPBMImage, grey > 127 ->
+ * 255 else 0) + Image::buildMaskPyramid (:717-747) on the device (kernel K0m).  `grey` is width*height u8, same dimensions as the
+ * view's image; call after pmk_set_view(view).  Views without a mask answer -1 to getMask, like the reference without a mask file.
+ * From then on Optim::postProcess rejects candidates for which PhotoSet::getMask(coord, m_level) == 0 (optim.cpp:265,
+ * photoSet.cpp:223-233), in pmk_post_process and inside pmk_propagate alike. */
+int pmk_set_view_mask(pmk_ctx* ctx, int view, const uint8_t* grey, int width, int height);
+/* Image::m_masks[level] of one view (*has_mask = 0 and mask_out untouched when the view has none; mask_out may be NULL) */
+int pmk_get_level_mask(pmk_ctx* ctx, int view, int level, uint8_t* mask_out, int* has_mask);
+/* PhotoSet::getMask(coord, m_level) over all views (view < 0: 0 or -1; photoSet.cpp:223-233) or PhotoSet::getMask(view, coord, m_level)
+ * = Photo::getMask (photo.cpp:44-52; -1, 0 or 255) on n points */
+int pmk_probe_mask(pmk_ctx* ctx, int n, int view, const float* coord4, int* out);
 
 int pmk_get_thresholds(pmk_ctx* ctx, pmk_thresholds* out);
 int pmk_set_depth(pmk_ctx* ctx, int depth);                 /* PmMvps::m_depth (pmmvps.hpp:61)      */

@@ -93,6 +93,7 @@ struct pmk_ctx {
     std::vector<ViewConst> h_views;          // working-level constants (device mirror in d_views)
     std::vector<std::vector<float> > P_all;  // per view: nlevels * 12
     std::vector<char> view_set;
+    std::vector<std::vector<uint8_t*> > masks;   // per view: the mask pyramid (nlevels device arrays), empty = no mask
     std::vector<void*> owned;                // every device allocation of the context
     ViewConst* d_views = nullptr;
     unsigned int* d_counters = nullptr;      // work-queue heads
@@ -150,6 +151,8 @@ void refresh_params(pmk_ctx* ctx) {
     p.ncc_threshold = ctx->ncc_threshold;
     p.ncc_threshold_before = ctx->ncc_threshold_before;
     p.level_scale = (float)(1 << ctx->cfg.level);
+    p.has_masks = 0;
+    for (const auto& m : ctx->masks) if (!m.empty()) p.has_masks = 1;
     for (int k = 0; k < PMK_MAX_LEVELS; ++k) p.level_thr[k] = INFINITY;
     int slot = 0;
     for (int k = -ctx->cfg.level + 1; k <= 2 && slot < PMK_MAX_LEVELS; ++k) p.level_thr[slot++] = level_threshold(k);
@@ -328,6 +331,7 @@ int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
     std::memset(ctx->h_views.data(), 0, sizeof(ViewConst) * cfg->nviews);
     ctx->P_all.resize(cfg->nviews);
     ctx->view_set.assign(cfg->nviews, 0);
+    ctx->masks.assign(cfg->nviews, std::vector<uint8_t*>());
     CUDA_TRY(cudaMalloc((void**)&ctx->d_views, sizeof(ViewConst) * cfg->nviews));
     CUDA_TRY(cudaMalloc((void**)&ctx->d_counters, 64 * sizeof(unsigned int)));
     // thresholds, pmmvps.cpp:54-67
@@ -453,6 +457,75 @@ static int set_view_impl(pmk_ctx* ctx, int view, const float* P, const uint8_t* 
 int pmk_set_view(pmk_ctx* ctx, int view, const float* P, const uint8_t* rgb, int width, int height) {
     if (!rgb) return fail(PMK_ERR_ARG, "pmk_set_view: null argument");
     return set_view_impl(ctx, view, P, rgb, false, width, height);
+}
+
+// ---- masks: Image::alloc's mask branch (image/image.cpp:143-161) + buildMaskPyramid (:717-747) -----------------------------------
+int pmk_set_view_mask(pmk_ctx* ctx, int view, const uint8_t* grey, int width, int height) {
+    if (!ctx || !grey) return fail(PMK_ERR_ARG, "pmk_set_view_mask: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_set_view_mask: view out of range");
+    if (!ctx->view_set[view]) return fail(PMK_ERR_STATE, "pmk_set_view_mask: upload the view first (pmk_set_view)");
+    if (!ctx->masks[view].empty()) return fail(PMK_ERR_STATE, "pmk_set_view_mask: mask already uploaded");
+    ViewConst& vc = ctx->h_views[view];
+    // the reference lets the mask's header overwrite m_widths[0] / m_heights[0] (image.cpp:146) and then indexes the image with them
+    if (width != vc.w[0] || height != vc.h[0]) return fail(PMK_ERR_ARG, "pmk_set_view_mask: mask and image dimensions differ");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    const int nlevels = ctx->cfg.level + 3;
+    const size_t npix0 = (size_t)width * height;
+    { const int rc = ensure(ctx, ctx->s_misc[0], npix0); if (rc) return rc; }
+    CUDA_TRY(cudaMemcpyAsync(ctx->s_misc[0].p, grey, npix0, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint8_t*> lv(nlevels, nullptr);
+    for (int l = 0; l < nlevels; ++l) {
+        void* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, (size_t)vc.w[l] * vc.h[l]));
+        ctx->owned.push_back(d);
+        lv[l] = (uint8_t*)d;
+    }
+    k0_mask_threshold<<<(unsigned)((npix0 + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->s_misc[0].p, lv[0], (int)npix0);
+    ctx->launches++;
+    for (int l = 1; l < nlevels; ++l) {
+        dim3 blk(32, 8), grd((vc.w[l] + 31) / 32, (vc.h[l] + 7) / 8);
+        k0_mask_downsample<<<grd, blk, 0, ctx->stream>>>(lv[l - 1], vc.w[l - 1], vc.h[l - 1], lv[l], vc.w[l], vc.h[l]);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));       // grey is a caller buffer
+    ctx->masks[view] = lv;
+    vc.mask = lv[ctx->cfg.level];
+    ctx->views_dirty = true;
+    ctx->params.has_masks = 1;
+    return PMK_OK;
+}
+
+int pmk_get_level_mask(pmk_ctx* ctx, int view, int level, uint8_t* mask_out, int* has_mask) {
+    int w = 0, h = 0;
+    const int rc = pmk_get_level_dims(ctx, view, level, &w, &h);
+    if (rc) return rc;
+    if (!has_mask) return fail(PMK_ERR_ARG, "pmk_get_level_mask: null argument");
+    *has_mask = ctx->masks[view].empty() ? 0 : 1;
+    if (!*has_mask || !mask_out) return PMK_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(mask_out, ctx->masks[view][level], (size_t)w * h, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_probe_mask(pmk_ctx* ctx, int n, int view, const float* coord4, int* out) {
+    if (!ctx || !coord4 || !out) return fail(PMK_ERR_ARG, "pmk_probe_mask: null argument");
+    if (view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_mask: view out of range");
+    if (n <= 0) return PMK_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    const size_t N = (size_t)n;
+    Scratch* s = ctx->s_misc;
+    if ((rc = ensure(ctx, s[1], N * 16)) || (rc = ensure(ctx, s[4], N * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s[1].p, coord4, N * 16, cudaMemcpyHostToDevice, ctx->stream));
+    k_probe_mask<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->params, n, view, (const float4*)s[1].p, (int*)s[4].p);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, s[4].p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
 }
 
 // ---- JPEG ingest: nvJPEG decodes straight into the staging buffer K0 reads (Image::readJpeg, image/image.cpp:827-879) ----------------

@@ -783,7 +783,7 @@ __device__ PMK_CAND_INLINE int warp_post_process(const CandParams& cp, WarpScrat
     int r = -1;
     do {
         if (nv < p.min_image_num) break;                                                             // :261
-        // getMask: the synthetic / maskless case returns -1 != 0 (photoSet.cpp:223-233), nothing to do   :265
+        if (warp_get_mask(p, X, lane) == 0) break;                                                   // :265
         nv = warp_add_images(p, X, N, ws.images, nv, CAND_MAXV, ws.mark, lane);                      // :268
         warp_set_inccs<WS, GW>(p, X, N, ws.images, nv, 0, ws.inccs, lane);                           // :269
         nv = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, lane);

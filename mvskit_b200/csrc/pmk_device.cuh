@@ -73,6 +73,8 @@ struct __align__(16) ViewConst {
     int w[PMK_MAX_LEVELS];                // image.cpp:135-138
     int h[PMK_MAX_LEVELS];
     const Texel* img[PMK_MAX_LEVELS];     // RGBX half-float texels holding the u8-rounded pyramid (image.cpp:245-315)
+    const uint8_t* mask;                  // working-level silhouette mask (0 / 255), NULL = the view has none (image.cpp:143-161,717-747)
+    uint64_t pad1;
 };
 
 // scalars shared by all kernels (passed by value)
@@ -89,6 +91,7 @@ struct Params {
     // levelDiff = -level + #{k : ratio >= level_thr[k]}, thresholds found on the host with the same
     // libm expression the reference evaluates (optim.cpp:808); PMK_MAX_LEVELS-1 entries, +inf padded
     float level_thr[PMK_MAX_LEVELS];
+    int has_masks;        // some view carries a mask (pmk_set_view_mask); 0 skips PhotoSet::getMask's loop altogether
 };
 
 // ---- Camera::project (camera.cpp:310-326) ------------------------------------------------------------
@@ -115,6 +118,27 @@ __device__ __forceinline__ V3 project(const Proj& P, V4 X) {
     r.y = max_std(lo, min_std(hi, xdiv(i1, i2)));
     r.z = (i2 < __int_as_float(0x7f800000)) ? 1.0f : __int_as_float(0x7fc00000);   // z / z for z > 0: 1, or NaN at +inf
     return r;
+}
+
+// ---- Photo::getMask(coord, m_level) (photo.cpp:44-52) -> Image::getMask(fx, fy, level) (image.cpp:749-781) ------------
+// -1: the view has no mask, or the rounded pixel lies outside the image; else the mask value (0 outside / 255 inside).
+// The reference converts floorf(f + 0.5f) to int first (x86: INT_MIN for NaN and out-of-range, i.e. "outside"); comparing the
+// floored floats against the image size decides the same way without the conversion.
+__device__ __forceinline__ int view_mask(const ViewConst& vc, int level, V4 X) {
+    if (vc.mask == nullptr) return -1;
+    const V3 ic = project(vc.P, X);
+    const float fx = floorf(xadd(ic.x, 0.5f)), fy = floorf(xadd(ic.y, 0.5f));
+    const int W = vc.w[level], H = vc.h[level];
+    if (!(fx >= 0.0f && fx < (float)W && fy >= 0.0f && fy < (float)H)) return -1;
+    return (int)__ldg(vc.mask + (size_t)(int)fy * W + (int)fx);
+}
+
+// ---- PhotoSet::getMask(coord, m_level) (photoSet.cpp:223-233), warp-cooperative: 0 as soon as one view says outside, else -1 ----
+__device__ __forceinline__ int warp_get_mask(const Params& p, V4 X, int lane) {
+    if (!p.has_masks) return -1;
+    bool outside = false;
+    for (int v = lane; v < p.nviews; v += 32) outside |= view_mask(p.views[v], p.level, X) == 0;
+    return __any_sync(0xffffffffu, outside) ? 0 : -1;
 }
 
 // ---- Optim::getUnit (optim.cpp:34-41): (float)(2.0 * fz * (1 << level) / ipscale), evaluated in double --------

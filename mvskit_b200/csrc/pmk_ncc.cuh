@@ -49,6 +49,35 @@ __global__ void k0_rgbx_to_u8(const Texel* __restrict__ src, uint8_t* __restrict
     dst[(size_t)i * 3] = (uint8_t)r; dst[(size_t)i * 3 + 1] = (uint8_t)g; dst[(size_t)i * 3 + 2] = (uint8_t)b;
 }
 
+// K0m: silhouette masks.  Image::alloc thresholds the level-0 mask (grey > 127 -> 255, else 0; image.cpp:149-156) and
+// buildMaskPyramid (:717-747) marks a coarse pixel inside when any of its 2x2 fine pixels is.  u8 in, u8 out, exact.
+__global__ void k0_mask_threshold(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npix) dst[i] = src[i] > 127 ? 255 : 0;
+}
+
+__global__ void k0_mask_downsample(const uint8_t* __restrict__ src, int Wp, int Hp, uint8_t* __restrict__ dst, int W, int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    // W = Wp / 2, so 2x + 1 <= Wp - 1: the reference's min(m_widths[level - 1], 2x + 1) (:725) never binds
+    const uint8_t* r0 = src + (size_t)(2 * y) * Wp + 2 * x;
+    const uint8_t* r1 = r0 + Wp;
+    dst[(size_t)y * W + x] = (r0[0] | r0[1] | r1[0] | r1[1]) ? 255 : 0;
+}
+
+// PhotoSet::getMask(coord, m_level) (view < 0) or PhotoSet::getMask(view, coord, m_level), one thread per point
+__global__ void k_probe_mask(const Params p, int n, int view, const float4* __restrict__ coord, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = coord[i];
+    const V4 X{c.x, c.y, c.z, c.w};
+    int r = -1;
+    if (view >= 0) r = view_mask(p.views[view], p.level, X);
+    else for (int v = 0; v < p.nviews; ++v) if (view_mask(p.views[v], p.level, X) == 0) { r = 0; break; }
+    out[i] = r;
+}
+
 // =====================================================================================================
 // K1: batched hypothesis NCC = PatchManager::computeNcc (patch_manager.cpp:401-404).
 //

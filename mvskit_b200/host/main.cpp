@@ -26,8 +26,20 @@ static int patch_io(const char* in_name, const char* out_name) {
     return in.fail() ? 1 : 0;
 }
 
+// --mask-io <prefix/mask/%08d> <out.pgm>: read a mask with the mirror's reader and write the grey values back as P5 (no GPU needed)
+static int mask_io(const char* base, const char* out_name) {
+    std::vector<unsigned char> grey;
+    int w = 0, h = 0;
+    if (!PhotoSet::readMask(base, grey, w, h)) { std::cerr << "no mask at " << base << std::endl; return 1; }
+    std::ofstream out(out_name, std::ios::binary);
+    out << "P5\n" << w << " " << h << "\n255\n";
+    out.write((const char*)grey.data(), (std::streamsize)grey.size());
+    return 0;
+}
+
 int main(int argc, char* argv[]) {
     if (argc == 4 && !strcmp(argv[1], "--patch-io")) return patch_io(argv[2], argv[3]);
+    if (argc == 4 && !strcmp(argv[1], "--mask-io")) return mask_io(argv[2], argv[3]);
     if (argc < 2) {
         std::cerr << "usage: " << argv[0] << " <prefix/> [option] [--device N] [--group G] [--filter-only ITER]" << std::endl;
         return 2;

@@ -150,7 +150,42 @@ bool read_ppm(const string& name, vector<unsigned char>& rgb, int& w, int& h) {
     return ok;
 }
 
+// <prefix>mask/%08d.pgm (binary P5) or .pbm (binary P4), the two formats Image::alloc accepts (image.cpp:143-161; completeName
+// prefers .pgm, :82-89).  Like readPBMImage (:881-943) the P4 bits are taken as ONE stream (no per-row padding), bit set = 0.
 }  // namespace
+bool PhotoSet::readMask(const string& base, vector<unsigned char>& grey, int& w, int& h) {
+    auto token = [](FILE* f, int& out) {
+        int c = fgetc(f);
+        while (c == '#' || isspace(c)) { if (c == '#') while (c != '\n' && c != EOF) c = fgetc(f); c = fgetc(f); }
+        out = 0;
+        while (c >= '0' && c <= '9') { out = out * 10 + (c - '0'); c = fgetc(f); }
+    };
+    char magic[2] = {0, 0};
+    if (FILE* f = fopen((base + ".pgm").c_str(), "rb")) {
+        int maxval = 0;
+        bool ok = fread(magic, 1, 2, f) == 2 && magic[0] == 'P' && magic[1] == '5';
+        if (ok) { token(f, w); token(f, h); token(f, maxval); ok = w > 0 && h > 0; }
+        if (ok) { grey.resize((size_t)w * h); ok = fread(grey.data(), 1, grey.size(), f) == grey.size(); }
+        fclose(f);
+        if (!ok) cerr << "Only accept binary pgm format" << base << ".pgm" << endl;
+        return ok;
+    }
+    if (FILE* f = fopen((base + ".pbm").c_str(), "rb")) {
+        bool ok = fread(magic, 1, 2, f) == 2 && magic[0] == 'P' && magic[1] == '4';
+        if (ok) { token(f, w); token(f, h); ok = w > 0 && h > 0; }
+        if (ok) {
+            const size_t n = (size_t)w * h;
+            vector<unsigned char> bits((n + 7) / 8);
+            ok = fread(bits.data(), 1, bits.size(), f) == bits.size();
+            grey.resize(n);
+            for (size_t i = 0; ok && i < n; ++i) grey[i] = ((bits[i >> 3] >> (7 - (i & 7))) & 1) ? 0 : 255;
+        }
+        fclose(f);
+        if (!ok) cerr << "Only accept binary pbm format: " << base << ".pbm" << endl;
+        return ok;
+    }
+    return false;
+}
 
 void PhotoSet::init(PmMvps& pmmvps, const vector<int>& images, const string prefix, const int nimages, const int nillums, const int maxLevel,
                     const int size, const int alloc) {
@@ -189,6 +224,14 @@ void PhotoSet::init(PmMvps& pmmvps, const vector<int>& images, const string pref
             fclose(f);
             chk(pmk_set_view_jpeg(pmmvps.m_ctx, i, P, bytes.data(), bytes.size(), &w, &h), "pmk_set_view_jpeg");
         }
+        char mname[1024];
+        snprintf(mname, sizeof(mname), "%smask/%08d", prefix.c_str(), i);                    // photoSet.cpp:48
+        vector<unsigned char> grey;
+        int mw = 0, mh = 0;
+        if (readMask(mname, grey, mw, mh)) {
+            cerr << "Read mask: " << mname << endl;                                           // image.cpp:148
+            chk(pmk_set_view_mask(pmmvps.m_ctx, i, grey.data(), mw, mh), "pmk_set_view_mask");
+        }
         cerr << "*" << std::flush;
     }
     cerr << endl;
@@ -202,6 +245,16 @@ Vector3f PhotoSet::project(const int index, const Vector4f& coord, const int lev
     float c[4] = {coord(0), coord(1), coord(2), coord(3)}, out[3];
     chk(pmk_probe(m_pmmvps->m_ctx, 1, &index, c, nullptr, out, nullptr, nullptr, nullptr, nullptr, nullptr), "project");
     return Vector3f(out[0], out[1], out[2]);
+}
+
+// PhotoSet::getMask(coord, level) (photoSet.cpp:223-233) and getMask(index, coord, level) (:219-221), on the device (pmk_probe_mask)
+int PhotoSet::getMask(const Vector4f& coord, const int level) const { return getMask(-1, coord, level); }
+int PhotoSet::getMask(const int index, const Vector4f& coord, const int level) const {
+    if (level != m_pmmvps->m_level) die("PhotoSet::getMask: only the working level is resident on the device");
+    const float c[4] = {coord(0), coord(1), coord(2), coord(3)};
+    int out = -1;
+    chk(pmk_probe_mask(m_pmmvps->m_ctx, 1, index, c, &out), "getMask");
+    return out;
 }
 
 int PhotoSet::image2index(const int image) const {

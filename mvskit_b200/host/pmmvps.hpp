@@ -106,6 +106,10 @@ public:
     int getWidth(const int index, const int level) const;
     int getHeight(const int index, const int level) const;
     Vector3f project(const int index, const Vector4f& coord, const int level) const;      // Camera::project on the device (pmk_probe)
+    // <base>.pgm (P5) or <base>.pbm (P4) -> grey values as Image::readPGMImage / readPBMImage deliver them (image.cpp:881-999)
+    static bool readMask(const string& base, vector<unsigned char>& grey, int& w, int& h);
+    int getMask(const Vector4f& coord, const int level) const;                             // photoSet.cpp:223-233 (0 / -1)
+    int getMask(const int index, const Vector4f& coord, const int level) const;            // photo.cpp:44-52 (-1 / 0 / 255)
     int image2index(const int image) const;
     void setDistances() {}
 

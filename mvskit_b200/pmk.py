@@ -144,9 +144,31 @@ class Context:
         _chk(lib().pmk_set_view_jpeg(self.h, view, _p(P), _p(buf), C.c_uint64(len(buf)), C.byref(w), C.byref(h)))
         return w.value, h.value
 
-    def set_scene(self, P: np.ndarray, images: Sequence[np.ndarray]):
+    def set_view_mask(self, view: int, grey: np.ndarray):
+        grey = np.ascontiguousarray(grey, np.uint8)
+        assert grey.ndim == 2
+        _chk(lib().pmk_set_view_mask(self.h, view, _p(grey), grey.shape[1], grey.shape[0]))
+
+    def level_mask(self, view: int, level: int):
+        """Image::m_masks[level] (None when the view has no mask)."""
+        w, h = self.level_dims(view, level)
+        out = np.empty((h, w), np.uint8)
+        has = C.c_int()
+        _chk(lib().pmk_get_level_mask(self.h, view, level, _p(out), C.byref(has)))
+        return out if has.value else None
+
+    def probe_mask(self, coord, view: int = -1) -> np.ndarray:
+        """PhotoSet::getMask(coord, m_level) (view < 0) or PhotoSet::getMask(view, coord, m_level)."""
+        coord = np.ascontiguousarray(coord, np.float32)
+        out = np.empty(len(coord), np.int32)
+        _chk(lib().pmk_probe_mask(self.h, len(coord), view, _p(coord), _p(out)))
+        return out
+
+    def set_scene(self, P: np.ndarray, images: Sequence[np.ndarray], masks=None):
         for v in range(self.nviews):
             self.set_view(v, P[v], images[v])
+            if masks and masks[v] is not None:
+                self.set_view_mask(v, masks[v])
 
     def thresholds(self) -> Thresholds:
         t = Thresholds()

@@ -228,6 +228,8 @@ class Scene:
     threshold: float = 0.7
     iters: int = 3
     images: List[np.ndarray] = field(default_factory=list)   # (H, W, 3) uint8, filled by render()
+    masks: List[Optional[np.ndarray]] = field(default_factory=list)   # (H, W) uint8 grey or None per view, filled by make_masks()
+    mask_formats: List[str] = field(default_factory=list)             # "pgm" | "pbm" per view (how write_scene stores them)
 
     @property
     def nviews(self) -> int:
@@ -280,6 +282,31 @@ class Scene:
             sky = 96.0 + 24.0 * np.sin(xs * 0.05 + v)[..., None] * np.cos(ys * 0.043)[..., None] * np.ones(3)
             img = np.where(hit[..., None], col, sky)
             self.images[v] = np.clip(np.floor(img + 0.5), 0, 255).astype(np.uint8)
+        return self
+
+    def make_masks(self, seed: int = 77, maskless=(2,), pbm=(1,)) -> "Scene":
+        """Silhouette masks in the reference's sense (image.cpp:143-161: grey > 127 = inside): one ellipse per view with a
+        ragged grey rim (values on both sides of the 127 threshold, odd positions so 2x2 pyramid blocks straddle the edge).
+        Views in `maskless` get none (Image::getMask = -1 there), views in `pbm` are stored as binary P4."""
+        rng = np.random.default_rng(seed)
+        ys, xs = np.mgrid[0:self.height, 0:self.width].astype(np.float64)
+        self.masks, self.mask_formats = [], []
+        for v in range(self.nviews):
+            if v in maskless:
+                self.masks.append(None); self.mask_formats.append("pgm")
+                continue
+            cx = self.width * (0.5 + 0.06 * math.cos(1.3 * v)); cy = self.height * (0.5 + 0.05 * math.sin(0.9 * v))
+            rx = self.width * (0.31 + 0.015 * v); ry = self.height * (0.33 + 0.01 * v)
+            d = np.sqrt(((xs - cx) / rx) ** 2 + ((ys - cy) / ry) ** 2)
+            grey = np.clip(255.0 * (1.06 - d) / 0.12, 0, 255)                 # ramp 255 -> 0 across the rim
+            grey = np.clip(grey + rng.integers(-40, 41, size=grey.shape), 0, 255)
+            m = np.floor(grey + 0.5).astype(np.uint8)
+            if v in pbm:
+                m = np.where(m > 127, 255, 0).astype(np.uint8)
+                self.mask_formats.append("pbm")
+            else:
+                self.mask_formats.append("pgm")
+            self.masks.append(m)
         return self
 
     # -- hypotheses for the NCC micro-benchmark / parity tests -----------------------------------------
@@ -504,6 +531,22 @@ def write_scene(scene: Scene, prefix: str, with_seeds: bool = True, seed_stride:
         with open(prefix + "image/%04d0000.jpg" % v, "wb") as fh:
             fh.write(b"P6\n%d %d\n255\n" % (im.shape[1], im.shape[0]))
             fh.write(np.ascontiguousarray(im).tobytes())
+    if scene.masks:
+        # <prefix>mask/%08d.pgm (binary P5) or .pbm (binary P4; the reference reads the bits as ONE stream without the
+        # per-row padding of the format, bit set = outside, image.cpp:881-943) -- photoSet.cpp:48, image.cpp:82-89,143-161
+        os.makedirs(prefix + "mask", exist_ok=True)
+        for v, m in enumerate(scene.masks):
+            if m is None:
+                continue
+            if scene.mask_formats[v] == "pbm":
+                bits = np.packbits((np.ascontiguousarray(m).reshape(-1) <= 127).astype(np.uint8))
+                with open(prefix + "mask/%08d.pbm" % v, "wb") as fh:
+                    fh.write(b"P4\n%d %d\n" % (m.shape[1], m.shape[0]))
+                    fh.write(bits.tobytes() + b"\0")
+            else:
+                with open(prefix + "mask/%08d.pgm" % v, "wb") as fh:
+                    fh.write(b"P5\n%d %d\n255\n" % (m.shape[1], m.shape[0]))
+                    fh.write(np.ascontiguousarray(m).tobytes())
     if with_seeds:
         recs = scene.seeds(stride=seed_stride)
         with open(prefix + "ply/00000000.patch", "w") as fh:

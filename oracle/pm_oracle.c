@@ -73,12 +73,14 @@ pmo_scene* pmo_scene_create(int nviews, int level, int csize, int wsize, int min
     s->img = (unsigned char**)calloc(nl, sizeof(unsigned char*));
     s->w = (int*)calloc(nl, sizeof(int)); s->h = (int*)calloc(nl, sizeof(int));
     s->gw = (int*)calloc((size_t)nviews, sizeof(int)); s->gh = (int*)calloc((size_t)nviews, sizeof(int));
+    s->mask = (unsigned char**)calloc(nl, sizeof(unsigned char*));
     return s;
 }
 
 void pmo_scene_destroy(pmo_scene* s) {
     if (!s) return;
-    for (int i = 0; i < s->nviews * s->nlevels; ++i) free(s->img[i]);
+    for (int i = 0; i < s->nviews * s->nlevels; ++i) { free(s->img[i]); free(s->mask[i]); }
+    free(s->mask);
     free(s->P); free(s->Minv); free(s->center); free(s->oaxis); free(s->xaxis); free(s->yaxis); free(s->zaxis);
     free(s->ipscale); free(s->img); free(s->w); free(s->h); free(s->gw); free(s->gh); free(s);
 }
@@ -447,4 +449,43 @@ int pmo_cell(const pmo_scene* s, int view, const float* X, int* ix, int* iy) {
     *ix = ((int)floorf(ic[0] + 0.5f)) / s->csize;
     *iy = ((int)floorf(ic[1] + 0.5f)) / s->csize;
     return (0 <= *ix && *ix < s->gw[view] && 0 <= *iy && *iy < s->gh[view]) ? 1 : 0;
+}
+
+/* ---- masks -------------------------------------------------------------------------------------------- */
+void pmo_set_mask(pmo_scene* s, int view, const unsigned char* grey, int w, int h) {
+    const size_t base = (size_t)view * s->nlevels;
+    if (w != s->w[base] || h != s->h[base]) return;      /* the reference lets the mask's header overwrite m_widths[0] (image.cpp:146) */
+    free(s->mask[base]);
+    unsigned char* m0 = s->mask[base] = (unsigned char*)malloc((size_t)w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i) m0[i] = (127 < (int)grey[i]) ? 255 : 0;            /* image.cpp:149-156 */
+    for (int l = 1; l < s->nlevels; ++l) {                                                       /* image.cpp:717-747 */
+        const int W = s->w[base + l], H = s->h[base + l], Wp = s->w[base + l - 1], Hp = s->h[base + l - 1];
+        const unsigned char* src = s->mask[base + l - 1];
+        free(s->mask[base + l]);
+        unsigned char* dst = s->mask[base + l] = (unsigned char*)malloc((size_t)W * H + 1);
+        for (int y = 0; y < H; ++y) {
+            const int ys[2] = {2 * y, (Hp < 2 * y + 1) ? Hp : 2 * y + 1};                        /* :723 (min against the height itself) */
+            for (int x = 0; x < W; ++x) {
+                const int xs[2] = {2 * x, (Wp < 2 * x + 1) ? Wp : 2 * x + 1};
+                int inside = 0;
+                for (int j = 0; j < 2; ++j) for (int i = 0; i < 2; ++i) if (src[(size_t)ys[j] * Wp + xs[i]]) ++inside;
+                dst[(size_t)y * W + x] = (0 < inside) ? 255 : 0;
+            }
+        }
+    }
+}
+
+int pmo_get_mask_view(const pmo_scene* s, int view, const float* X, int level) {
+    const size_t idx = (size_t)view * s->nlevels + level;
+    if (!s->mask[idx]) return -1;                                                                 /* photo.cpp:45-47 */
+    float ic[3];
+    pmo_project(s, view, X, level, ic);
+    const int ix = (int)floorf(ic[0] + 0.5f), iy = (int)floorf(ic[1] + 0.5f);                     /* image.cpp:759-760 */
+    if (ix < 0 || s->w[idx] <= ix || iy < 0 || s->h[idx] <= iy) return -1;                        /* :775-778 */
+    return s->mask[idx][(size_t)iy * s->w[idx] + ix];
+}
+
+int pmo_get_mask(const pmo_scene* s, const float* X, int level) {
+    for (int v = 0; v < s->nviews; ++v) if (pmo_get_mask_view(s, v, X, level) == 0) return 0;     /* photoSet.cpp:224-231 */
+    return -1;
 }

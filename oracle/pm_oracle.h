@@ -42,6 +42,7 @@ typedef struct pmo_scene {
     int* h;
     int* gw;            /* nviews: cell grid (patch_manager.cpp:36-37) */
     int* gh;
+    unsigned char** mask;/* nviews * nlevels pointers to the u8 mask pyramid (0 / 255), NULL where a view has no mask */
 } pmo_scene;
 
 pmo_scene* pmo_scene_create(int nviews, int level, int csize, int wsize, int min_image_num, float ncc_threshold);
@@ -77,6 +78,15 @@ void  pmo_set_inccs(const pmo_scene* s, const float* X4, const float* N4, const 
 void  pmo_set_inccs_pair(const pmo_scene* s, const float* X4, const float* N4, const int* views, int nviews, int robust, float* out);
 /* patch_manager.cpp:223-249: cell index of X in a view; returns 1 if inside the grid */
 int   pmo_cell(const pmo_scene* s, int view, const float* X4, int* ix, int* iy);
+
+/* image.cpp:143-161 (grey > 127 -> 255, else 0) + buildMaskPyramid :717-747 (a coarse pixel is inside when any of its
+ * 2x2 fine pixels is) from a level-0 u8 mask (copied); call after pmo_set_image, same dimensions */
+void  pmo_set_mask(pmo_scene* s, int view, const unsigned char* grey, int w, int h);
+/* Photo::getMask(coord, level) photo.cpp:44-52 -> Image::getMask(float, float, level) image.cpp:749-781:
+ * -1 without a mask or outside the image, else 0 / 255 at the rounded pixel */
+int   pmo_get_mask_view(const pmo_scene* s, int view, const float* X4, int level);
+/* PhotoSet::getMask(coord, level) photoSet.cpp:223-233: 0 as soon as one view's mask says outside, else -1 */
+int   pmo_get_mask(const pmo_scene* s, const float* X4, int level);
 
 #ifdef __cplusplus
 }

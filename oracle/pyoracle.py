@@ -121,6 +121,19 @@ class RefLib:
         return dict(P=P.reshape(3, 4), center=c, oaxis=o, xaxis=x, yaxis=y, zaxis=z, ipscale=np.float32(ip.value))
 
     # -- per-function probes -----------------------------------------------------------------------
+    def mask_level(self, view: int, level: int):
+        """Image::m_masks[level] of one view (None when the view has no mask)."""
+        w, h = self.image_dims(view, level)
+        out = np.zeros((h, w), np.uint8)
+        return out if self.L.pmref_get_mask_level(view, level, _p(out)) else None
+
+    def get_mask(self, coord, view: int = -1, level=None) -> np.ndarray:
+        """PhotoSet::getMask(coord, level) (view < 0) or PhotoSet::getMask(view, coord, level)."""
+        coord = _f32(coord)
+        out = np.zeros(len(coord), np.int32)
+        self.L.pmref_get_mask(len(coord), view, _p(coord), self.level if level is None else level, _p(out))
+        return out
+
     def project(self, views, coord, level=None):
         views, coord = _i32(views), _f32(coord)
         out = np.zeros((len(views), 3), np.float32)
@@ -353,7 +366,7 @@ class RefLib:
 class COracle:
     """The plain-C restatement, fed with arrays (no files)."""
 
-    def __init__(self, P: np.ndarray, images, level=1, csize=2, wsize=7, min_image_num=3, ncc_threshold=0.7):
+    def __init__(self, P: np.ndarray, images, level=1, csize=2, wsize=7, min_image_num=3, ncc_threshold=0.7, masks=None):
         if not os.path.exists(ORACLE_SO):
             build(ref=False)
         self.L = L = C.CDLL(ORACLE_SO)
@@ -370,6 +383,24 @@ class COracle:
             L.pmo_set_camera(self.s, v, _p(P[v]))
             im = np.ascontiguousarray(images[v], np.uint8)
             L.pmo_set_image(self.s, v, _p(im), im.shape[1], im.shape[0])
+            if masks and masks[v] is not None:
+                m = np.ascontiguousarray(masks[v], np.uint8)
+                L.pmo_set_mask(self.s, v, _p(m), m.shape[1], m.shape[0])
+
+    def mask_level(self, view: int, level: int):
+        S = self._scene()
+        w, h = self.image_dims(view, level)
+        ptrs = np.ctypeslib.as_array(C.cast(S.mask, C.POINTER(C.c_uint64)), (self.nviews * self.nlevels,))
+        p = int(ptrs[view * self.nlevels + level])
+        return self._arr(p, (h, w), np.uint8) if p else None
+
+    def get_mask(self, coord, view: int = -1, level=None) -> np.ndarray:
+        coord = _f32(coord)
+        lv = self.level if level is None else level
+        out = np.zeros(len(coord), np.int32)
+        for i in range(len(coord)):
+            out[i] = self.L.pmo_get_mask(self.s, _p(coord[i]), lv) if view < 0 else self.L.pmo_get_mask_view(self.s, view, _p(coord[i]), lv)
+        return out
 
     def __del__(self):
         try:
@@ -382,7 +413,7 @@ class COracle:
             _fields_ = [(k, C.c_int) for k in ("nviews", "level", "nlevels", "csize", "wsize", "tau", "min_image_num", "depth")] + \
                        [(k, C.c_float) for k in ("ncc_threshold", "ncc_threshold_before", "angle_threshold0", "angle_threshold1",
                                                  "max_angle_threshold", "quad_threshold", "neighbor_threshold", "neighbor_threshold1", "neighbor_threshold2")] + \
-                       [(k, C.c_void_p) for k in ("P", "center", "oaxis", "xaxis", "yaxis", "zaxis", "ipscale", "Minv", "img", "w", "h", "gw", "gh")]
+                       [(k, C.c_void_p) for k in ("P", "center", "oaxis", "xaxis", "yaxis", "zaxis", "ipscale", "Minv", "img", "w", "h", "gw", "gh", "mask")]
         return C.cast(self.s, C.POINTER(S)).contents
 
     def _arr(self, ptr, shape, dtype):

@@ -399,6 +399,23 @@ void pmref_post_process(int n, const float* coord4, const float* normal4, const 
     }
 }
 
+// ---- masks: Image::getMask (image.cpp:749-781) over Image::alloc's thresholded level 0 (:143-161) and
+// buildMaskPyramid (:717-747); Photo::getMask (photo.cpp:44-52); PhotoSet::getMask (photoSet.cpp:215-233) ----
+// One pyramid level of a view's mask through Image::getMask(ix, iy, level); returns 0 when the view has no mask.
+int pmref_get_mask_level(int view, int level, unsigned char* out) {
+    const int w = g_pm->m_photoSet.getWidth(view, level), h = g_pm->m_photoSet.getHeight(view, level);
+    if (g_pm->m_photoSet.getMask(view, 0, 0, level) == -1) return 0;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) out[(size_t)y * w + x] = (unsigned char)g_pm->m_photoSet.getMask(view, x, y, level);
+    return 1;
+}
+
+// PhotoSet::getMask(index, coord, level) per view (view >= 0) or PhotoSet::getMask(coord, level) over all views (view < 0)
+void pmref_get_mask(int n, int view, const float* coord4, int level, int* out) {
+    for (int i = 0; i < n; ++i)
+        out[i] = view >= 0 ? g_pm->m_photoSet.getMask(view, v4(coord4 + 4 * i), level) : g_pm->m_photoSet.getMask(v4(coord4 + 4 * i), level);
+}
+
 // ---- patch store -------------------------------------------------------------------------------------
 void pmref_clear_patches(void) { g_pm->m_patchManager.init(); }
 

@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.pmk_abi_version() == 2
+    assert L.pmk_abi_version() == 3
 
 
 def test_no_cpu_fallback():
