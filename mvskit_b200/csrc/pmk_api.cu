@@ -99,6 +99,9 @@ struct pmk_ctx {
     unsigned int* d_counters = nullptr;      // work-queue heads
     bool views_dirty = true;
     Scratch s_coord, s_normal, s_views, s_nviews, s_incc, s_ncc, s_levels, s_misc[8];
+    Scratch s_ready;                         // per-chunk arrival words of the streamed host-buffer NCC call
+    unsigned int* h_epoch = nullptr;         // pinned source of those words
+    unsigned int epoch = 0;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     uint64_t launches = 0;
@@ -160,7 +163,7 @@ void refresh_params(pmk_ctx* ctx) {
 
 template <int WS, int MINB>
 int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
-              void* incc, void* ncc, void* levels) {
+              void* incc, void* ncc, void* levels, const unsigned int* ready, unsigned int epoch, int chunk_shift) {
     const int fstride = ctx->params.tau * K1_FRAME_WORDS + 4;
     const size_t smem = (size_t)K1_WARPS * 32 * fstride * sizeof(float);
     if (!ctx->k1_attr_done) {
@@ -176,25 +179,26 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
     const int grid = std::max(1, std::min(want, ctx->sm_count * per_sm));
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), ctx->stream));
     k1_ncc<WS, MINB><<<grid, K1_WARPS * 32, smem, ctx->stream>>>(ctx->params, n, (const float4*)coord, (const float4*)normal, (const int*)views,
-                                                          (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels, ctx->d_counters);
+                                                          (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels, ctx->d_counters,
+                                                          ready, epoch, chunk_shift);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return PMK_OK;
 }
 
 int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
-                void* incc, void* ncc, void* levels) {
+                void* incc, void* ncc, void* levels, const unsigned int* ready = nullptr, unsigned int epoch = 0, int chunk_shift = 0) {
     static const int minb = getenv("PMK_K1_MINB") ? atoi(getenv("PMK_K1_MINB")) : 4;   // tuning knob: CTAs/SM the kernel is compiled for
 #ifdef PMK_WS_ONLY
-    if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+    if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
     (void)minb;
 #else
     switch (ctx->cfg.wsize) {
-        case 5: return launch_k1<5, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
-        case 7: return minb == 3 ? launch_k1<7, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels)
-                                 : launch_k1<7, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
-        case 9: return launch_k1<9, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
-        case 11: return launch_k1<11, 2>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels);
+        case 5: return launch_k1<5, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
+        case 7: return minb == 3 ? launch_k1<7, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift)
+                                 : launch_k1<7, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
+        case 9: return launch_k1<9, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
+        case 11: return launch_k1<11, 2>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
     }
 #endif
     return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11");
@@ -354,7 +358,8 @@ void pmk_destroy(pmk_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->owned) cudaFree(p);
-    Scratch* all[] = {&ctx->s_coord, &ctx->s_normal, &ctx->s_views, &ctx->s_nviews, &ctx->s_incc, &ctx->s_ncc, &ctx->s_levels};
+    Scratch* all[] = {&ctx->s_coord, &ctx->s_normal, &ctx->s_views, &ctx->s_nviews, &ctx->s_incc, &ctx->s_ncc, &ctx->s_levels, &ctx->s_ready};
+    if (ctx->h_epoch) cudaFreeHost(ctx->h_epoch);
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     for (Scratch& s : ctx->s_misc) if (s.p) cudaFree(s.p);
     for (Scratch& s : ctx->pool) if (s.p) cudaFree(s.p);
@@ -693,19 +698,56 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
         (rc = ensure(ctx, ctx->s_nviews, N * 4)) || (rc = ensure(ctx, ctx->s_incc, N * 4)) || (rc = ensure(ctx, ctx->s_ncc, N * 4)) ||
         (rc = ensure(ctx, ctx->s_levels, N * tau * 4)))
         return rc;
-    // Three-stage pipeline over chunks of the batch: H2D on s_in, K1 on the context stream, D2H on s_out, chained by events, so
-    // the PCIe copies of one chunk overlap the kernel of another (host buffers should be pinned for the copies to be asynchronous).
     cudaStream_t st = ctx->stream;
-    const size_t chunk = 1 << 17;
+    static const int mode_chunks = getenv("PMK_E2E_MODE") && !strcmp(getenv("PMK_E2E_MODE"), "chunks");
+    static const int chunk_log2 = getenv("PMK_E2E_CHUNK_LOG2") ? std::min(24, std::max(10, atoi(getenv("PMK_E2E_CHUNK_LOG2")))) : 17;
+    const size_t chunk = (size_t)1 << chunk_log2;
     const int nchunks = (int)((N + chunk - 1) / chunk);
+    CUDA_TRY(cudaEventRecord(ctx->ev1, st));                      // the copies must not overtake earlier work on the context stream
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev1, 0));
+    if (!mode_chunks) {
+        // Streamed: ONE K1 launch over the whole batch consumes the hypotheses while they cross PCIe.  The copy stream moves the
+        // inputs chunk by chunk and, after each chunk, a 4-byte copy-engine write of this call's epoch into ready[chunk]; a warp that
+        // draws a batch of a chunk that has not landed waits on that word (k1_ncc).  Every copy is enqueued BEFORE the kernel is
+        // launched, so the kernel never depends on a later host action (tools that serialise launches cannot hang it).  Scores go
+        // straight into the caller's buffers when those are mapped pinned memory (coalesced 128-byte posted writes), else through
+        // device staging and one D2H; the strided levels_out always takes the staging path.
+        if ((rc = ensure(ctx, ctx->s_ready, (size_t)nchunks * 4))) return rc;
+        if (!ctx->h_epoch) CUDA_TRY(cudaHostAlloc((void**)&ctx->h_epoch, sizeof(unsigned int), cudaHostAllocDefault));
+        const unsigned int epoch = ++ctx->epoch;
+        *ctx->h_epoch = epoch;
+        if ((rc = upload_views(ctx))) return rc;
+        for (int c = 0; c < nchunks; ++c) {
+            const size_t o = (size_t)c * chunk, m = std::min(chunk, N - o);
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_coord.p + o * 16, coord4 + o * 4, m * 16, cudaMemcpyHostToDevice, ctx->s_in));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_normal.p + o * 16, normal4 + o * 4, m * 16, cudaMemcpyHostToDevice, ctx->s_in));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_views.p + o * stride * 4, views + o * stride, m * stride * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_nviews.p + o * 4, nviews + o, m * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            CUDA_TRY(cudaMemcpyAsync((unsigned int*)ctx->s_ready.p + c, ctx->h_epoch, 4, cudaMemcpyHostToDevice, ctx->s_in));
+        }
+        void *d_incc = nullptr, *d_ncc = nullptr;
+        bool direct = cudaHostGetDevicePointer(&d_incc, incc_out, 0) == cudaSuccess && (!ncc_out || cudaHostGetDevicePointer(&d_ncc, ncc_out, 0) == cudaSuccess);
+        if (!direct) { (void)cudaGetLastError(); d_incc = ctx->s_incc.p; d_ncc = ncc_out ? ctx->s_ncc.p : nullptr; }
+        rc = dispatch_k1(ctx, n, ctx->s_coord.p, ctx->s_normal.p, ctx->s_views.p, ctx->s_nviews.p, stride, d_incc, d_ncc,
+                         levels_out ? ctx->s_levels.p : nullptr, (const unsigned int*)ctx->s_ready.p, epoch, chunk_log2);
+        if (rc) return rc;
+        if (!direct) {
+            CUDA_TRY(cudaMemcpyAsync(incc_out, ctx->s_incc.p, N * 4, cudaMemcpyDeviceToHost, st));
+            if (ncc_out) CUDA_TRY(cudaMemcpyAsync(ncc_out, ctx->s_ncc.p, N * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (levels_out) CUDA_TRY(cudaMemcpyAsync(levels_out, ctx->s_levels.p, N * tau * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
+        return PMK_OK;
+    }
+    // PMK_E2E_MODE=chunks (kept for A/B measurements): three-stage pipeline over chunks of the batch, H2D on s_in, one K1 launch per
+    // chunk on the context stream, D2H on s_out, chained by events.
     while ((int)ctx->ev_in.size() < nchunks) {
         cudaEvent_t a, b;
         CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
         ctx->ev_in.push_back(a); ctx->ev_k.push_back(b);
     }
-    CUDA_TRY(cudaEventRecord(ctx->ev1, st));                      // the copies must not overtake earlier work on the context stream
-    CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev1, 0));
     for (int c = 0; c < nchunks; ++c) {
         const size_t o = (size_t)c * chunk, m = std::min(chunk, N - o);
         CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_coord.p + o * 16, coord4 + o * 4, m * 16, cudaMemcpyHostToDevice, ctx->s_in));

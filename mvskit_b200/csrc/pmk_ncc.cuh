@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
                                                               const float4* __restrict__ normal, const int* __restrict__ views,
                                                               const int* __restrict__ nviews, int stride,
                                                               float* __restrict__ incc_out, float* __restrict__ ncc_out,
-                                                              int* __restrict__ levels_out, unsigned int* __restrict__ next_batch) {
+                                                              int* __restrict__ levels_out, unsigned int* __restrict__ next_batch,
+                                                              const unsigned int* __restrict__ ready, unsigned int epoch, int chunk_shift) {
     constexpr int NSAMP = WS * WS;
     constexpr int GW = WS <= 8 ? 8 : 16;                  // lanes that share one hypothesis in phase C
     constexpr int G = 32 / GW;                            // hypotheses sampled concurrently by a warp
@@ -136,15 +137,30 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
         if (lane == 0) batch = (int)atomicAdd(next_batch, 1u);
         batch = __shfl_sync(0xffffffffu, batch, 0);
         if (batch >= nbatch) break;
+        // streamed input (pmk_ncc_eval with host buffers): the hypotheses arrive over PCIe in chunks of 1 << chunk_shift while this
+        // kernel runs; a copy-engine write of `epoch` into ready[chunk] follows each chunk's copies on the same stream.  The queue
+        // hands batches out in input order, so a warp only waits when the kernel has caught up with the link.
+        if (ready != nullptr) {
+            if (lane == 0) {
+                const unsigned int* f = ready + ((batch * 32) >> chunk_shift);
+                unsigned int seen;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                    if (seen == epoch) break;
+                    __nanosleep(256);
+                }
+            }
+            __syncwarp();
+        }
         const int h = batch * 32 + lane;
         const bool live = h < n;
         // ---------------- phase A/B: lane = hypothesis ----------------
         V4 X{0.f, 0.f, 0.f, 1.f}, N{0.f, 0.f, 1.f, 0.f};
         int nv = 0;
         if (live) {
-            const float4 c = __ldg(coord + h), m = __ldg(normal + h);
+            const float4 c = __ldcg(coord + h), m = __ldcg(normal + h);   // read once; L2 only (the streamed inputs land during the kernel)
             X = V4{c.x, c.y, c.z, c.w}; N = V4{m.x, m.y, m.z, m.w};
-            nv = __ldg(nviews + h);
+            nv = __ldcg(nviews + h);
         }
         const int sz = min(p.tau, nv);
         const bool usable = live && nv >= 2;              // optim.cpp:631,643: fewer than 2 images -> 2.0
@@ -155,7 +171,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
             V4 px{0.f, 0.f, 0.f, 0.f}, py{0.f, 0.f, 0.f, 0.f};
             bool ref_ok = false;
             if (usable) {
-                const int ref = __ldg(vrow);
+                const int ref = ready ? __ldcg(vrow) : __ldg(vrow);              // streamed rows must not take the non-coherent path
                 ref_ok = ref >= 0 && ref < p.nviews;
                 if (ref_ok) get_paxes(p.views[ref], X, N, p.level_scale, px, py);
             }
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
                 float w = 0.0f;
                 int vk = 0;
                 if (ref_ok && k < sz) {
-                    const int v = __ldg(vrow + k);
+                    const int v = ready ? __ldcg(vrow + k) : __ldg(vrow + k);
                     if (v >= 0 && v < p.nviews) {
                         vk = v;
                         const ViewConst& vc = p.views[v];

@@ -151,6 +151,36 @@ def test_ncc_batch_invariance_large(ctx, small_scene):
     assert ok.mean() > 0.5 and (a[ok] >= 0).all() and (a[ok] < 0.7).all()     # robust incc range: x/(1+3x) < 1/3 .. 2/7
 
 
+def test_streamed_host_call_equals_the_device_call(ctx, small_scene):
+    """pmk_ncc_eval with host buffers streams the hypotheses over PCIe into ONE running K1 launch (per-chunk arrival words) and,
+    with mapped pinned outputs, lets the kernel write the scores straight into the caller's buffers.  Whatever the buffers are
+    (pinned or pageable) and wherever the chunk boundaries fall (ragged tail, fewer hypotheses than one chunk), the results are the
+    bits of the device-pointer call on the same inputs."""
+    from mvskit_b200 import pmk
+    N = 3 * (1 << 17) + 12345
+    c, n, vw, nv = small_scene.hypotheses(N, seed=123, well_observed=False)
+    d = [ctx.alloc(a.nbytes).upload(a) for a in (c, n, vw, nv)]
+    d_incc, d_ncc, d_lv = ctx.alloc(N * 4), ctx.alloc(N * 4), ctx.alloc(N * ctx.tau * 4)
+    ctx.ncc_eval_dev(N, d[0], d[1], d[2], d[3], vw.shape[1], d_incc, d_ncc, d_lv)
+    want_incc, want_ncc, want_lv = np.empty(N, np.float32), np.empty(N, np.float32), np.empty((N, ctx.tau), np.int32)
+    d_incc.download(want_incc); d_ncc.download(want_ncc); d_lv.download(want_lv)
+    # pageable numpy buffers
+    incc, ncc, lv = ctx.ncc_eval(c, n, vw, nv, want_levels=True)
+    assert_bits_equal(incc, want_incc, "pageable incc"); assert_bits_equal(ncc, want_ncc, "pageable ncc"); assert np.array_equal(lv, want_lv)
+    # pinned buffers: zero-copy outputs; run twice so stale arrival words of the previous call are in place
+    h = [pmk.pinned_empty(a.shape, a.dtype) for a in (c, n, vw, nv)]
+    for dst, src in zip(h, (c, n, vw, nv)):
+        dst[:] = src
+    h_incc, h_ncc = pmk.pinned_empty((N,), np.float32), pmk.pinned_empty((N,), np.float32)
+    for m in (N, 1000, N - 7):
+        h_incc[:] = -7.0; h_ncc[:] = -7.0
+        pmk._chk(pmk.lib().pmk_ncc_eval(ctx.h, m, pmk._p(h[0]), pmk._p(h[1]), pmk._p(h[2]), pmk._p(h[3]), vw.shape[1], pmk._p(h_incc), pmk._p(h_ncc), None))
+        assert_bits_equal(h_incc[:m], want_incc[:m], f"pinned incc n={m}"); assert_bits_equal(h_ncc[:m], want_ncc[:m], f"pinned ncc n={m}")
+        assert (h_incc[m:] == -7.0).all()
+    for b in d + [d_incc, d_ncc, d_lv]:
+        b.free()
+
+
 def test_state_errors(small_scene):
     from mvskit_b200 import pmk
     c = pmk.Context(nviews=small_scene.nviews)
