@@ -101,6 +101,7 @@ struct pmk_ctx {
     Scratch s_coord, s_normal, s_views, s_nviews, s_incc, s_ncc, s_levels, s_misc[8];
     Scratch s_ready;                         // per-chunk arrival words of the streamed host-buffer NCC call
     unsigned int* h_epoch = nullptr;         // pinned source of those words
+    size_t h_epoch_cap = 0;
     unsigned int epoch = 0;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -699,37 +700,52 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
         (rc = ensure(ctx, ctx->s_levels, N * tau * 4)))
         return rc;
     cudaStream_t st = ctx->stream;
-    static const int mode_chunks = getenv("PMK_E2E_MODE") && !strcmp(getenv("PMK_E2E_MODE"), "chunks");
-    static const int chunk_log2 = getenv("PMK_E2E_CHUNK_LOG2") ? std::min(24, std::max(10, atoi(getenv("PMK_E2E_CHUNK_LOG2")))) : 17;
+    static const char* mode_env = getenv("PMK_E2E_MODE");
+    static const int mode_chunks = mode_env && !strcmp(mode_env, "chunks");
+    static const int chunk_log2 = getenv("PMK_E2E_CHUNK_LOG2") ? std::min(24, std::max(14, atoi(getenv("PMK_E2E_CHUNK_LOG2")))) : 17;
+    static const int nstreams = getenv("PMK_E2E_STREAMS") ? std::min(2, std::max(1, atoi(getenv("PMK_E2E_STREAMS")))) : 2;
     const size_t chunk = (size_t)1 << chunk_log2;
     const int nchunks = (int)((N + chunk - 1) / chunk);
     CUDA_TRY(cudaEventRecord(ctx->ev1, st));                      // the copies must not overtake earlier work on the context stream
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev1, 0));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev1, 0));
     if (!mode_chunks) {
-        // Streamed: ONE K1 launch over the whole batch consumes the hypotheses while they cross PCIe.  The copy stream moves the
-        // inputs chunk by chunk and, after each chunk, a 4-byte copy-engine write of this call's epoch into ready[chunk]; a warp that
-        // draws a batch of a chunk that has not landed waits on that word (k1_ncc).  Every copy is enqueued BEFORE the kernel is
-        // launched, so the kernel never depends on a later host action (tools that serialise launches cannot hang it).  Scores go
-        // straight into the caller's buffers when those are mapped pinned memory (coalesced 128-byte posted writes), else through
-        // device staging and one D2H; the strided levels_out always takes the staging path.
-        if ((rc = ensure(ctx, ctx->s_ready, (size_t)nchunks * 4))) return rc;
-        if (!ctx->h_epoch) CUDA_TRY(cudaHostAlloc((void**)&ctx->h_epoch, sizeof(unsigned int), cudaHostAllocDefault));
+        // Streamed: ONE K1 launch over the whole batch consumes the hypotheses while they cross PCIe.  The copy streams move the
+        // inputs chunk by chunk and, after each chunk, a copy-engine write of this call's epoch into the arrival words of the chunk's
+        // slots (one word per 2^14 hypotheses); a warp that draws a batch whose slot has not landed waits on that word (k1_ncc).
+        // Every copy is enqueued BEFORE the kernel is launched (a failed enqueue returns before any launch), so the kernel never
+        // depends on a later host action and tools that make launches synchronous cannot hang it.  Scores go straight into the caller's buffers when those are mapped pinned memory
+        // (coalesced 128-byte posted writes), else through device staging and one D2H; the strided levels_out always takes staging.
+        constexpr int SLOT_LOG2 = 14;
+        const size_t slot = (size_t)1 << SLOT_LOG2, nslots = (N + slot - 1) / slot;
+        if ((rc = ensure(ctx, ctx->s_ready, nslots * 4))) return rc;
+        if (ctx->h_epoch_cap < nslots) {
+            if (ctx->h_epoch) CUDA_TRY(cudaFreeHost(ctx->h_epoch));
+            ctx->h_epoch = nullptr; ctx->h_epoch_cap = 0;
+            CUDA_TRY(cudaHostAlloc((void**)&ctx->h_epoch, (nslots + 64) * sizeof(unsigned int), cudaHostAllocDefault));
+            ctx->h_epoch_cap = nslots + 64;
+        }
         const unsigned int epoch = ++ctx->epoch;
-        *ctx->h_epoch = epoch;
+        for (size_t k = 0; k < nslots; ++k) ctx->h_epoch[k] = epoch;
         if ((rc = upload_views(ctx))) return rc;
-        for (int c = 0; c < nchunks; ++c) {
-            const size_t o = (size_t)c * chunk, m = std::min(chunk, N - o);
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_coord.p + o * 16, coord4 + o * 4, m * 16, cudaMemcpyHostToDevice, ctx->s_in));
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_normal.p + o * 16, normal4 + o * 4, m * 16, cudaMemcpyHostToDevice, ctx->s_in));
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_views.p + o * stride * 4, views + o * stride, m * stride * 4, cudaMemcpyHostToDevice, ctx->s_in));
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_nviews.p + o * 4, nviews + o, m * 4, cudaMemcpyHostToDevice, ctx->s_in));
-            CUDA_TRY(cudaMemcpyAsync((unsigned int*)ctx->s_ready.p + c, ctx->h_epoch, 4, cudaMemcpyHostToDevice, ctx->s_in));
+        cudaStream_t sin[2] = {ctx->s_in, ctx->s_out};
+        unsigned int* d_ready = (unsigned int*)ctx->s_ready.p;
+        const size_t cslots = chunk >> SLOT_LOG2;
+        int c = 0;
+        for (size_t s0 = 0; s0 < nslots; s0 += cslots, ++c) {
+            const size_t take = std::min(cslots, nslots - s0), o = s0 << SLOT_LOG2, m = std::min(take << SLOT_LOG2, N - o);
+            cudaStream_t si = sin[c % nstreams];                            // two copy streams: one's set-up gaps hide under the other's transfer
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_coord.p + o * 16, coord4 + o * 4, m * 16, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_normal.p + o * 16, normal4 + o * 4, m * 16, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_views.p + o * stride * 4, views + o * stride, m * stride * 4, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_nviews.p + o * 4, nviews + o, m * 4, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync(d_ready + s0, ctx->h_epoch + s0, take * 4, cudaMemcpyHostToDevice, si));
         }
         void *d_incc = nullptr, *d_ncc = nullptr;
         bool direct = cudaHostGetDevicePointer(&d_incc, incc_out, 0) == cudaSuccess && (!ncc_out || cudaHostGetDevicePointer(&d_ncc, ncc_out, 0) == cudaSuccess);
         if (!direct) { (void)cudaGetLastError(); d_incc = ctx->s_incc.p; d_ncc = ncc_out ? ctx->s_ncc.p : nullptr; }
         rc = dispatch_k1(ctx, n, ctx->s_coord.p, ctx->s_normal.p, ctx->s_views.p, ctx->s_nviews.p, stride, d_incc, d_ncc,
-                         levels_out ? ctx->s_levels.p : nullptr, (const unsigned int*)ctx->s_ready.p, epoch, chunk_log2);
+                         levels_out ? ctx->s_levels.p : nullptr, (const unsigned int*)d_ready, epoch, SLOT_LOG2);
         if (rc) return rc;
         if (!direct) {
             CUDA_TRY(cudaMemcpyAsync(incc_out, ctx->s_incc.p, N * 4, cudaMemcpyDeviceToHost, st));
@@ -738,6 +754,7 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
         if (levels_out) CUDA_TRY(cudaMemcpyAsync(levels_out, ctx->s_levels.p, N * tau * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
+        CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
         return PMK_OK;
     }
     // PMK_E2E_MODE=chunks (kept for A/B measurements): three-stage pipeline over chunks of the batch, H2D on s_in, one K1 launch per
