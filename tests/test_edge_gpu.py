@@ -118,3 +118,51 @@ def test_sweep_is_deterministic_and_group_size_only_changes_the_schedule(small_s
     z1 = np.quantile(np.abs(g1.coord[:, 2]) / small_scene.scene_scale, 0.9)
     z5 = np.quantile(np.abs(g5.coord[:, 2]) / small_scene.scene_scale, 0.9)
     assert z5 <= 1.2 * z1 + 1e-4, (z1, z5)
+
+
+@pytest.mark.parametrize("level,csize", [(0, 2), (2, 2), (1, 1), (0, 1)])
+def test_other_levels_and_cell_sizes_match_the_oracle(level, csize):
+    """Option::m_level and m_csize other than the defaults (option.cpp:20,22): the pyramid depth (level + 3), the working-level
+    projection, the cell grid ((w + csize - 1) / csize, patch_manager.cpp:36-37), cell indices, pyramid-level decisions and
+    scores against the C oracle configured the same way; and one sweep on the store with that geometry."""
+    from mvskit_b200 import pmk, synth
+    from oracle import pyoracle
+    from conftest import assert_bits_equal
+    scene = synth.make_scene(1, scale=1.0 if level == 2 else 0.5).render()
+    pyoracle.build(ref=False)
+    orc = pyoracle.COracle(scene.P, scene.images, level=level, csize=csize)
+    ctx = pmk.Context(nviews=scene.nviews, level=level, csize=csize)
+    ctx.set_scene(scene.P, scene.images)
+    assert ctx.nlevels == level + 3
+    for v in range(scene.nviews):
+        for lvl in range(ctx.nlevels):
+            assert ctx.level_dims(v, lvl) == orc.image_dims(v, lvl)
+        assert np.array_equal(ctx.level_image(v, ctx.nlevels - 1), orc.image(v, ctx.nlevels - 1))
+        w, h = orc.image_dims(v, level)
+        assert ctx.grid_dims(v) == ((w + csize - 1) // csize, (h + csize - 1) // csize)
+    c, n, vw, nv = scene.hypotheses(1024, seed=41, well_observed=False)
+    v0 = vw[:, 0].copy()
+    got = ctx.probe(v0, c, n)
+    assert_bits_equal(got["project"], orc.project(v0, c), "project")
+    assert_bits_equal(got["unit"], orc.get_unit(v0, c), "getUnit")
+    cells, ok = orc.cells(v0, c)
+    assert np.array_equal(got["cell"], cells) and np.array_equal(got["cell_ok"], ok)
+    incc, ncc, lv = ctx.ncc_eval(c, n, vw, nv, want_levels=True)
+    oi, on, ol = orc.compute_ncc(c, n, vw, nv, True)
+    assert np.array_equal(lv, ol)
+    assert lv.max() <= level + 2 and lv[lv >= 0].min() >= 0
+    assert np.array_equal(incc == 2.0, oi == 2.0)
+    good = oi != 2.0
+    assert good.sum() > 200 and np.abs(incc[good] - oi[good]).max() <= 1e-4
+    # one sweep of view 0's wavefront on that geometry: new patches appear, every stored cell is setGrids of the stored coordinate
+    seeds = synth.seed_arrays(scene, stride=8)
+    ctx.set_depth(0); ctx.store_clear(); ctx.store_add(*seeds); ctx.set_depth(1)
+    n0 = ctx.store_count()
+    st = ctx.propagate_diagonals(0, 0, 0, 60, 7)
+    g = ctx.store_get()
+    assert g.n > n0 and st["added"] > 0
+    pr = ctx.probe(g.images[:, 0].copy(), g.coord)
+    assert np.array_equal(pr["cell"], g.grids[:, 0])
+    gw, gh = ctx.grid_dims(0)
+    assert (g.grids[:, 0, 0] < gw).all() and (g.grids[:, 0, 1] < gh).all()
+    ctx.close()

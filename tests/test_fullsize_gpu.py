@@ -69,3 +69,45 @@ def test_full_size_pass_invariants_and_determinism(full_scene):
     again = ctx2.filter()
     assert again[0] == counts[5] and again[5] >= 0.9 * again[0]
     ctx2.close()
+
+
+def test_large_images_parity_with_the_oracle():
+    """Image dimensions of BASELINE.json configs[3] (3072 wide, level 1 working level over a 4-level pyramid): config 1 rendered at
+    768x576 and enlarged 4x (bilinear) with the cameras scaled to match, so building the scene stays cheap.  The K0 pyramid, projections,
+    cells, pyramid-level decisions and scores are compared with the C oracle exactly as on the small scenes: integer work and everything
+    that feeds it bit-exact, scores within 1e-4."""
+    import dataclasses
+    from scipy import ndimage
+    from mvskit_b200 import pmk, synth
+    from oracle import pyoracle
+    from conftest import assert_bits_equal
+    base = synth.make_scene(1, scale=1.2).render()
+    k = 4
+    P = base.P.copy()
+    P[:, :2, :] *= np.float32(k)
+    images = [np.clip(np.floor(ndimage.zoom(im.astype(np.float32), (k, k, 1), order=1) + 0.5), 0, 255).astype(np.uint8) for im in base.images]
+    big = dataclasses.replace(base, width=base.width * k, height=base.height * k, f=base.f * k, P=P, images=images)
+    assert (big.width, big.height) == (3072, 2304)
+    ctx = pmk.Context(nviews=big.nviews)
+    ctx.set_scene(big.P, big.images)
+    pyoracle.build(ref=False)
+    co = pyoracle.COracle(big.P, big.images)
+    for v in range(big.nviews):
+        for lvl in range(ctx.nlevels):
+            assert ctx.level_dims(v, lvl) == co.image_dims(v, lvl)
+            assert np.array_equal(ctx.level_image(v, lvl), co.image(v, lvl)), (v, lvl)
+    c, n, vw, nv = big.hypotheses(2048, seed=17, well_observed=False, normal_jitter_deg=30.0)
+    v0 = vw[:, 0].copy()
+    got = ctx.probe(v0, c, n)
+    assert_bits_equal(got["project"], co.project(v0, c), "project")
+    assert_bits_equal(got["unit"], co.get_unit(v0, c), "getUnit")
+    cells, ok = co.cells(v0, c)
+    assert np.array_equal(got["cell"], cells) and np.array_equal(got["cell_ok"], ok)
+    assert cells[:, 0].max() > 500                                   # the grid really is 768 cells wide
+    incc, ncc, lv = ctx.ncc_eval(c, n, vw, nv, want_levels=True)
+    oi, on, ol = co.compute_ncc(c, n, vw, nv, True)
+    assert np.array_equal(lv, ol)
+    good = oi != 2.0
+    assert np.array_equal(incc != 2.0, good) and good.mean() > 0.3
+    assert np.abs(incc[good] - oi[good]).max() <= 1e-4
+    ctx.close()
