@@ -259,6 +259,51 @@ def test_filter_stages_match_reference(ctx, reflib, populated):
         assert ((gflag == 0) == (ralive == 1)).mean() >= 0.98
 
 
+def test_filter_neighbor_given_the_reference_state(ctx, reflib, populated):
+    """filterNeighbor in isolation.  In test_filter_stages_match_reference the two sides enter stage 3 with slightly different
+    stores (filterExact's setRefImage is an argmin over INCC sums and tolerance-bound), which blurs what findNeighbors itself
+    does.  Here the GPU store is re-loaded from the REFERENCE's state after its filterOutside + filterExact, so both sides
+    run findNeighbors / filterQuad on identical patches: the neighbour counts (isNeighborRadius over the +-2 cells of every
+    view, integer work) must agree for every patch, and the rejections wherever the quadric residual is not within tolerance
+    of m_quadThreshold (the reference solves the fit with an SVD stand-in, the device with normal equations in double)."""
+    import copy
+    g = populated
+    reflib.set_ncc_thresholds(0.7, 0.4)
+    _load_both(ctx, reflib, g, 1)
+    reflib.filter_rebuild(0)
+    reflib.stage_begin(); reflib.filter_stage(1)
+    reflib.filter_rebuild(1)
+    reflib.stage_begin(); reflib.filter_stage(2)
+    reflib.filter_rebuild(1)
+    n0 = reflib.stage_begin()
+    rp = copy.deepcopy(reflib.get_patches())      # the reference's survivors of filterOutside + filterExact, m_images as filterExact left them
+    for k in ("coord", "normal", "scal", "images", "nimages"):
+        setattr(rp, k, getattr(rp, k)[:n0].copy())
+    # both sides start over from these records (fresh registration, m_vimages rebuilt from scratch by the non-additive rebuild)
+    _load_both(ctx, reflib, rp, 1)
+    reflib.filter_rebuild(0)
+    assert ctx.filter_rebuild(0) == n0
+    n = reflib.stage_begin()
+    assert n == n0
+    gp, rq = ctx.store_get(), reflib.get_patches()
+    assert_bits_equal(gp.coord, rq.coord[:n], "collect order of the re-loaded store")
+    assert np.array_equal(gp.images[:, 0], rq.images[:n, 0]) and np.array_equal(gp.nimages, rq.nimages[:n])
+    assert np.array_equal(gp.nvimages, rq.nvimages[:n])
+    for v in range(reflib.nviews):
+        assert np.array_equal(ctx.store_depth_map(v), reflib.depth_map(v)), v
+        assert np.array_equal(ctx.store_cell_counts(v, 0), reflib.cell_counts(v, 0)) and np.array_equal(ctx.store_cell_counts(v, 1), reflib.cell_counts(v, 1))
+    rcount, rquad = reflib.stage_neighbors()
+    reflib.filter_stage(3)
+    rrej = reflib.stage_rejects()
+    gres, grej, gcount, killed = ctx.filter_stage(3, n)
+    assert np.array_equal(gcount, rcount), (np.nonzero(gcount != rcount)[0][:10], (gcount != rcount).sum())
+    differ = (grej != 0) != (rrej != 0)
+    thr = reflib.threshold(5)
+    near = np.abs(gres - thr) <= 2e-2 * thr                       # residual within 2 % of m_quadThreshold: either solver may tip it
+    assert not (differ & ~near).any(), (np.nonzero(differ & ~near)[0][:10], gres[differ & ~near][:10])
+    assert differ.sum() <= max(2, n // 200), differ.sum()
+
+
 def test_filter_run_end_to_end(ctx, reflib, populated, small_scene):
     """Filter::run on both sides from the same store: survivors agree, and they lie on the ground-truth plane."""
     g = populated
