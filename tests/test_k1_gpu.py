@@ -172,7 +172,7 @@ def test_streamed_host_call_equals_the_device_call(ctx, small_scene):
     for dst, src in zip(h, (c, n, vw, nv)):
         dst[:] = src
     h_incc, h_ncc = pmk.pinned_empty((N,), np.float32), pmk.pinned_empty((N,), np.float32)
-    for m in (N, 1000, N - 7):
+    for m in (N, 1000, N - 7, 1, 31, (1 << 14) - 1, 1 << 14, (1 << 14) + 1, (1 << 17) + 33):     # slot (2^14) and chunk (2^17) boundaries
         h_incc[:] = -7.0; h_ncc[:] = -7.0
         pmk._chk(pmk.lib().pmk_ncc_eval(ctx.h, m, pmk._p(h[0]), pmk._p(h[1]), pmk._p(h[2]), pmk._p(h[3]), vw.shape[1], pmk._p(h_incc), pmk._p(h_ncc), None))
         assert_bits_equal(h_incc[:m], want_incc[:m], f"pinned incc n={m}"); assert_bits_equal(h_ncc[:m], want_ncc[:m], f"pinned ncc n={m}")
