@@ -452,7 +452,7 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes * N,
                          "kernel": "k1_ncc<7,4>", "algorithmic_bytes_per_eval": algo_bytes, "valid_views_per_eval": valid_views,
                          "layout_bytes_per_eval": layout_bytes, "achieved_layout": per_gpu * layout_bytes / 1e9, "frac_layout": per_gpu * layout_bytes / 1e9 / peak,
-                         "note": "not HBM-bound: the pyramid stays L2/L1 resident; binding units per ncu (profiles/): L1TEX data pipe ~71%, issue slots ~74%", "peak_source": peak_src,
+                         "note": "not HBM-bound: the pyramid stays L2/L1 resident; binding units per ncu (profiles/r01_k1_ncc_v4_streamed.txt): L1TEX data pipe 85%, issue slots 78%", "peak_source": peak_src,
                          "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0)},
         }
         if pipe_mg is not None:
