@@ -718,14 +718,20 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
         // (coalesced 128-byte posted writes), else through device staging and one D2H; the strided levels_out always takes staging.
         constexpr int SLOT_LOG2 = 14;
         const size_t slot = (size_t)1 << SLOT_LOG2, nslots = (N + slot - 1) / slot;
-        if ((rc = ensure(ctx, ctx->s_ready, nslots * 4))) return rc;
+        {
+            const void* before = ctx->s_ready.p;
+            if ((rc = ensure(ctx, ctx->s_ready, nslots * 4))) return rc;
+            // fresh device memory may hold anything (a freed array of small ints, say): no word may equal a future epoch
+            if (ctx->s_ready.p != before) CUDA_TRY(cudaMemset(ctx->s_ready.p, 0, ctx->s_ready.cap));
+        }
         if (ctx->h_epoch_cap < nslots) {
             if (ctx->h_epoch) CUDA_TRY(cudaFreeHost(ctx->h_epoch));
             ctx->h_epoch = nullptr; ctx->h_epoch_cap = 0;
             CUDA_TRY(cudaHostAlloc((void**)&ctx->h_epoch, (nslots + 64) * sizeof(unsigned int), cudaHostAllocDefault));
             ctx->h_epoch_cap = nslots + 64;
         }
-        const unsigned int epoch = ++ctx->epoch;
+        if (++ctx->epoch == 0) ctx->epoch = 1;                    // 0 is what cleared words hold
+        const unsigned int epoch = ctx->epoch;
         for (size_t k = 0; k < nslots; ++k) ctx->h_epoch[k] = epoch;
         if ((rc = upload_views(ctx))) return rc;
         cudaStream_t sin[2] = {ctx->s_in, ctx->s_out};
