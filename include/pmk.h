@@ -236,6 +236,12 @@ int pmk_probe_check(pmk_ctx* ctx, int n, const float* coord4, const float* norma
  * (out may be NULL) switches the recording on; every later call returns and clears the times. */
 int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells);
 
+/* Profiling aid: nanoseconds of warp time the sweeps spent in each phase of a propagatePatch try, summed over all warps since the last
+ * call: [0] generatePatch + computeNcc, [1] preProcess, [2] refinePatch, [3] postProcess (store-independent part), [4] its store-reading
+ * tail (setVImagesVGrids, check), [5] waiting for the try's turn, [6] tries, [7] tries that reached refinePatch.  The first call (out8 may
+ * be NULL) switches the recording on; every later call returns and clears the sums. */
+int pmk_debug_phase_times(pmk_ctx* ctx, uint64_t* out8);
+
 /* Stream control / timing helpers for bench.py (no reference counterpart). */
 int pmk_sync(pmk_ctx* ctx);
 int pmk_device_alloc(pmk_ctx* ctx, uint64_t bytes, void** out);

@@ -1445,6 +1445,24 @@ int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells) {
     return PMK_OK;
 }
 
+int pmk_debug_phase_times(pmk_ctx* ctx, uint64_t* out8) {
+    if (!ctx) return fail(PMK_ERR_ARG, "pmk_debug_phase_times: null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    if (!s->phase_ns) {
+        if ((rc = dalloc(ctx, &s->phase_ns, 8))) return rc;
+        CUDA_TRY(cudaMemsetAsync(s->phase_ns, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    }
+    if (out8) {
+        CUDA_TRY(cudaMemcpyAsync(out8, s->phase_ns, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(s->phase_ns, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    }
+    return PMK_OK;
+}
+
 int pmk_probe_check(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages, int stride,
                     int* ret, float* gain, int* nneighbors, int* vimages_out, int* nvimages_out) {
     if (!ctx || !coord4 || !normal4 || !scal4 || !images || !nimages || !ret || !gain || !nneighbors || !vimages_out || !nvimages_out)

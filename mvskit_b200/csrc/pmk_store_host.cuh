@@ -25,6 +25,7 @@ struct pmk_store {
     int* rem_list = nullptr; int* task_new = nullptr; int* final_id = nullptr; int* order = nullptr;
     unsigned long long* stats = nullptr; unsigned long long* step_max = nullptr;
     float* cell_ns = nullptr;            // per-cell sweep time of the last pass (allocated on first pmk_debug_cell_times call)
+    unsigned long long* phase_ns = nullptr;   // warp time by try phase (allocated on first pmk_debug_phase_times call)
     unsigned long long* keys = nullptr; unsigned long long* keys2 = nullptr;
     int* vals = nullptr; int* vals2 = nullptr;
     void* cub_tmp = nullptr; size_t cub_bytes = 0;
@@ -473,7 +474,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     sa.inc = inc; sa.iter = iter;
     sa.jitter_mode = ctx->cfg.jitter_mode;
     for (int i = 0; i < 4; ++i) sa.jitter[i] = s->jitter[i];
-    sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order; sa.step_max = s->step_max; sa.cell_ns = s->cell_ns;
+    sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order; sa.step_max = s->step_max; sa.cell_ns = s->cell_ns; sa.phase_ns = s->phase_ns;
     int max_steps = 0;
     for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
     for (int k = step_first; k < step_first + step_count && k < max_steps; ++k) {

@@ -49,6 +49,8 @@ struct SweepArgs {
     unsigned long long* stats;             // SweepStat
     unsigned long long* step_max;          // slowest dest cell of this step, ns (one word per step, zeroed by the host)
     float* cell_ns;                        // optional [total_cells]: time spent on each dest cell in its last visit (profiling)
+    unsigned long long* phase_ns;          // optional [8]: warp time by phase of a try (profiling, pmk_debug_phase_times): generatePatch + computeNcc,
+                                           // preProcess, refinePatch, postProcess, its store-reading tail, waiting for the turn / commit, tries, refined tries
 };
 
 struct SweepScratch {                  // per warp
@@ -476,6 +478,17 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
             int outcome = TRY_GEN_NULL;
             bool have_turn = false;
             TrySnap sn;
+            unsigned long long ph_t = 0;
+            // profiling only: close the phase that ends here (lane 0 of the warp, one global atomic)
+#define PMK_PHASE(slot)                                                                                        \
+            if (sa.phase_ns != nullptr && lane == 0) {                                                         \
+                unsigned long long now_;                                                                       \
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                                       \
+                if ((slot) >= 0) atomicAdd(sa.phase_ns + (slot), now_ - ph_t);                                 \
+                ph_t = now_;                                                                                   \
+            }
+            PMK_PHASE(-1)
+            if (sa.phase_ns != nullptr && lane == 0) atomicAdd(sa.phase_ns + 6, 1ull);
             for (int attempt = 0; attempt < 3; ++attempt) {
                 sn = take_snapshot(cs, ss.l_snap, maxp, lane);
                 // ---------------- stage A: everything up to postProcess's store-independent part ----------------
@@ -520,12 +533,16 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                     if (nv > 0) {
                         float ncc = warp_compute_ncc<WS>(p, ws, X, N, nv, lane);
                         ncc = __shfl_sync(0xffffffffu, ncc, 0);
+                        PMK_PHASE(0)
                         if (sn.np >= maxp && ncc < sn.wncc) outcome = TRY_LOSE;
                         else {
                             // ---- patch optimisation (propagate.cpp:176-193) ----
                             float dscale, ascale;
-                            if (warp_pre_process<WS>(cp, ws, X, N, nv, dscale, ascale, lane) == -1) outcome = TRY_FAIL0;
+                            const int pre = warp_pre_process<WS>(cp, ws, X, N, nv, dscale, ascale, lane);
+                            PMK_PHASE(1)
+                            if (pre == -1) outcome = TRY_FAIL0;
                             else {
+                                if (sa.phase_ns != nullptr && lane == 0) atomicAdd(sa.phase_ns + 7, 1ull);
                                 if (coop) {
                                     if (lane == 0) {
                                         cs.rs_x[0] = X.x; cs.rs_x[1] = X.y; cs.rs_x[2] = X.z; cs.rs_x[3] = X.w;
@@ -540,7 +557,9 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                                 ncc = __shfl_sync(0xffffffffu, ncc, 0);
                                 X = V4{__shfl_sync(0xffffffffu, X.x, 0), __shfl_sync(0xffffffffu, X.y, 0), __shfl_sync(0xffffffffu, X.z, 0), __shfl_sync(0xffffffffu, X.w, 0)};
                                 N = V4{__shfl_sync(0xffffffffu, N.x, 0), __shfl_sync(0xffffffffu, N.y, 0), __shfl_sync(0xffffffffu, N.z, 0), 0.0f};
+                                PMK_PHASE(2)
                                 const int r = warp_post_process<WS>(cp, ws, X, N, nv, gwarp, lane);
+                                PMK_PHASE(3)
                                 outcome = r == 0 ? TRY_ACCEPT : TRY_FAIL1;
                                 cd.X = X; cd.N = N; cd.nv = nv; cd.ncc = ncc; cd.dscale = dscale; cd.ascale = ascale;
                                 if (r == 0) {
@@ -584,6 +603,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                             }
                         }
                         stage_b_done = true;
+                        PMK_PHASE(4)
                     }
                     if (have_turn) break;
                     // ---------------- wait for this try's turn ----------------
@@ -601,6 +621,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, PMK_SWEEP_MINB) k4_sweep(cons
                 }
                 if (outcome >= 0) break;
             }
+            PMK_PHASE(5)
+#undef PMK_PHASE
             // ================= commit (this warp holds the turn) =================
             stat[SS_CALLS] += (k == 0) ? 1 : 0;
             stat[SS_TRIES] += 1;
