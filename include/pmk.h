@@ -124,6 +124,11 @@ int pmk_get_level_image(pmk_ctx* ctx, int view, int level, uint8_t* rgb_out);   
  * Host-pointer variant: copies inputs H2D, runs, copies results D2H, returns when they landed. */
 int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views,
                  const int* nviews, int stride, float* incc_out, float* ncc_out, int* levels_out);
+/* Byte-lean form of the host-pointer call for PCIe-bound callers (31 B instead of 60 B per hypothesis at stride 6): coord3 / normal3 are
+ * rows of 3 floats (w = 1 and w = 0 implied -- what Patch::m_coord and a refined Patch::m_normal hold, patch.hpp:33-35), views8 rows of
+ * `stride` bytes (view ids; the context must have nviews <= 255, so that 255 is an id no view has), nviews8 one byte each.  Results are bit-identical to pmk_ncc_eval on the widened inputs. */
+int pmk_ncc_eval_packed(pmk_ctx* ctx, int n, const float* coord3, const float* normal3, const uint8_t* views8, const uint8_t* nviews8, int stride,
+                        float* incc_out, float* ncc_out, int* levels_out);
 /* Device-pointer variant: enqueues on the context stream and returns. */
 int pmk_ncc_eval_dev(pmk_ctx* ctx, int n, const void* d_coord4, const void* d_normal4, const void* d_views,
                      const void* d_nviews, int stride, void* d_incc_out, void* d_ncc_out, void* d_levels_out);

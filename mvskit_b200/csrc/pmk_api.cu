@@ -164,7 +164,7 @@ void refresh_params(pmk_ctx* ctx) {
 
 template <int WS, int MINB>
 int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
-              void* incc, void* ncc, void* levels, const unsigned int* ready, unsigned int epoch, int chunk_shift) {
+              void* incc, void* ncc, void* levels, const unsigned int* ready, unsigned int epoch, int chunk_shift, int packed) {
     const int fstride = ctx->params.tau * K1_FRAME_WORDS + 4;
     const size_t smem = (size_t)K1_WARPS * 32 * fstride * sizeof(float);
     if (!ctx->k1_attr_done) {
@@ -181,25 +181,25 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), ctx->stream));
     k1_ncc<WS, MINB><<<grid, K1_WARPS * 32, smem, ctx->stream>>>(ctx->params, n, (const float4*)coord, (const float4*)normal, (const int*)views,
                                                           (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels, ctx->d_counters,
-                                                          ready, epoch, chunk_shift);
+                                                          ready, epoch, chunk_shift, packed);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return PMK_OK;
 }
 
 int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
-                void* incc, void* ncc, void* levels, const unsigned int* ready = nullptr, unsigned int epoch = 0, int chunk_shift = 0) {
+                void* incc, void* ncc, void* levels, const unsigned int* ready = nullptr, unsigned int epoch = 0, int chunk_shift = 0, int packed = 0) {
     static const int minb = getenv("PMK_K1_MINB") ? atoi(getenv("PMK_K1_MINB")) : 4;   // tuning knob: CTAs/SM the kernel is compiled for
 #ifdef PMK_WS_ONLY
-    if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
+    if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift, packed);
     (void)minb;
 #else
     switch (ctx->cfg.wsize) {
-        case 5: return launch_k1<5, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
-        case 7: return minb == 3 ? launch_k1<7, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift)
-                                 : launch_k1<7, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
-        case 9: return launch_k1<9, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
-        case 11: return launch_k1<11, 2>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift);
+        case 5: return launch_k1<5, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift, packed);
+        case 7: return minb == 3 ? launch_k1<7, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift, packed)
+                                 : launch_k1<7, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift, packed);
+        case 9: return launch_k1<9, 3>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift, packed);
+        case 11: return launch_k1<11, 2>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift, packed);
     }
 #endif
     return fail(PMK_ERR_ARG, "pmk: wsize must be 5, 7, 9 or 11");
@@ -685,8 +685,23 @@ int pmk_ncc_eval_dev(pmk_ctx* ctx, int n, const void* d_coord4, const void* d_no
     return dispatch_k1(ctx, n, d_coord4, d_normal4, d_views, d_nviews, stride, d_incc, d_ncc, d_levels);
 }
 
+static int ncc_eval_host(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride,
+                         float* incc_out, float* ncc_out, int* levels_out, int packed);
+
 int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride,
                  float* incc_out, float* ncc_out, int* levels_out) {
+    return ncc_eval_host(ctx, n, coord4, normal4, views, nviews, stride, incc_out, ncc_out, levels_out, 0);
+}
+
+int pmk_ncc_eval_packed(pmk_ctx* ctx, int n, const float* coord3, const float* normal3, const uint8_t* views8, const uint8_t* nviews8, int stride,
+                        float* incc_out, float* ncc_out, int* levels_out) {
+    if (ctx && ctx->cfg.nviews > 255) return fail(PMK_ERR_ARG, "pmk_ncc_eval_packed: byte view ids need nviews <= 255 (255 marks an invalid entry)");
+    return ncc_eval_host(ctx, n, coord3, normal3, (const int*)views8, (const int*)nviews8, stride, incc_out, ncc_out, levels_out, 1);
+}
+
+// element sizes of the four input arrays: float4 / float4 / int rows / int, or (packed) 3 floats / 3 floats / byte rows / byte
+static int ncc_eval_host(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride,
+                         float* incc_out, float* ncc_out, int* levels_out, int packed) {
     if (!ctx) return fail(PMK_ERR_ARG, "pmk_ncc_eval: null ctx");
     if (n < 0 || stride < 1) return fail(PMK_ERR_ARG, "pmk_ncc_eval: bad n/stride");
     if (n == 0) return PMK_OK;
@@ -695,6 +710,8 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
     const size_t N = (size_t)n;
     const int tau = ctx->params.tau;
     int rc;
+    const size_t ec = packed ? 12 : 16, ev = (packed ? 1 : 4) * (size_t)stride, en = packed ? 1 : 4;      // bytes per hypothesis: coord = normal, view row, nviews
+    const char *h_c = (const char*)coord4, *h_n = (const char*)normal4, *h_v = (const char*)views, *h_nv = (const char*)nviews;
     if ((rc = ensure(ctx, ctx->s_coord, N * 16)) || (rc = ensure(ctx, ctx->s_normal, N * 16)) || (rc = ensure(ctx, ctx->s_views, N * stride * 4)) ||
         (rc = ensure(ctx, ctx->s_nviews, N * 4)) || (rc = ensure(ctx, ctx->s_incc, N * 4)) || (rc = ensure(ctx, ctx->s_ncc, N * 4)) ||
         (rc = ensure(ctx, ctx->s_levels, N * tau * 4)))
@@ -709,7 +726,7 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
     CUDA_TRY(cudaEventRecord(ctx->ev1, st));                      // the copies must not overtake earlier work on the context stream
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev1, 0));
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev1, 0));
-    if (!mode_chunks) {
+    if (!mode_chunks || packed) {
         // Streamed: ONE K1 launch over the whole batch consumes the hypotheses while they cross PCIe.  The copy streams move the
         // inputs chunk by chunk and, after each chunk, a copy-engine write of this call's epoch into the arrival words of the chunk's
         // slots (one word per 2^14 hypotheses); a warp that draws a batch whose slot has not landed waits on that word (k1_ncc).
@@ -741,17 +758,17 @@ int pmk_ncc_eval(pmk_ctx* ctx, int n, const float* coord4, const float* normal4,
         for (size_t s0 = 0; s0 < nslots; s0 += cslots, ++c) {
             const size_t take = std::min(cslots, nslots - s0), o = s0 << SLOT_LOG2, m = std::min(take << SLOT_LOG2, N - o);
             cudaStream_t si = sin[c % nstreams];                            // two copy streams: one's set-up gaps hide under the other's transfer
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_coord.p + o * 16, coord4 + o * 4, m * 16, cudaMemcpyHostToDevice, si));
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_normal.p + o * 16, normal4 + o * 4, m * 16, cudaMemcpyHostToDevice, si));
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_views.p + o * stride * 4, views + o * stride, m * stride * 4, cudaMemcpyHostToDevice, si));
-            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_nviews.p + o * 4, nviews + o, m * 4, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_coord.p + o * ec, h_c + o * ec, m * ec, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_normal.p + o * ec, h_n + o * ec, m * ec, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_views.p + o * ev, h_v + o * ev, m * ev, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaMemcpyAsync((char*)ctx->s_nviews.p + o * en, h_nv + o * en, m * en, cudaMemcpyHostToDevice, si));
             CUDA_TRY(cudaMemcpyAsync(d_ready + s0, ctx->h_epoch + s0, take * 4, cudaMemcpyHostToDevice, si));
         }
         void *d_incc = nullptr, *d_ncc = nullptr;
         bool direct = cudaHostGetDevicePointer(&d_incc, incc_out, 0) == cudaSuccess && (!ncc_out || cudaHostGetDevicePointer(&d_ncc, ncc_out, 0) == cudaSuccess);
         if (!direct) { (void)cudaGetLastError(); d_incc = ctx->s_incc.p; d_ncc = ncc_out ? ctx->s_ncc.p : nullptr; }
         rc = dispatch_k1(ctx, n, ctx->s_coord.p, ctx->s_normal.p, ctx->s_views.p, ctx->s_nviews.p, stride, d_incc, d_ncc,
-                         levels_out ? ctx->s_levels.p : nullptr, (const unsigned int*)d_ready, epoch, SLOT_LOG2);
+                         levels_out ? ctx->s_levels.p : nullptr, (const unsigned int*)d_ready, epoch, SLOT_LOG2, packed);
         if (rc) return rc;
         if (!direct) {
             CUDA_TRY(cudaMemcpyAsync(incc_out, ctx->s_incc.p, N * 4, cudaMemcpyDeviceToHost, st));

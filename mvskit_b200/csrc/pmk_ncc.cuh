@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
                                                               const int* __restrict__ nviews, int stride,
                                                               float* __restrict__ incc_out, float* __restrict__ ncc_out,
                                                               int* __restrict__ levels_out, unsigned int* __restrict__ next_batch,
-                                                              const unsigned int* __restrict__ ready, unsigned int epoch, int chunk_shift) {
+                                                              const unsigned int* __restrict__ ready, unsigned int epoch, int chunk_shift,
+                                                              int packed) {
+    // packed != 0 (pmk_ncc_eval_packed): coord / normal are rows of 3 floats (w = 1 / w = 0 implied), views rows of `stride` bytes,
+    // nviews bytes -- 31 B per hypothesis over PCIe instead of 60; everything downstream is unchanged
     constexpr int NSAMP = WS * WS;
     constexpr int GW = WS <= 8 ? 8 : 16;                  // lanes that share one hypothesis in phase C
     constexpr int G = 32 / GW;                            // hypotheses sampled concurrently by a warp
@@ -158,9 +161,16 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
         V4 X{0.f, 0.f, 0.f, 1.f}, N{0.f, 0.f, 1.f, 0.f};
         int nv = 0;
         if (live) {
-            const float4 c = __ldcg(coord + h), m = __ldcg(normal + h);   // read once; L2 only (the streamed inputs land during the kernel)
-            X = V4{c.x, c.y, c.z, c.w}; N = V4{m.x, m.y, m.z, m.w};
-            nv = __ldcg(nviews + h);
+            if (packed) {
+                const float* c3 = reinterpret_cast<const float*>(coord) + 3 * (size_t)h;
+                const float* n3 = reinterpret_cast<const float*>(normal) + 3 * (size_t)h;
+                X = V4{__ldcg(c3), __ldcg(c3 + 1), __ldcg(c3 + 2), 1.0f}; N = V4{__ldcg(n3), __ldcg(n3 + 1), __ldcg(n3 + 2), 0.0f};
+                nv = (int)__ldcg(reinterpret_cast<const unsigned char*>(nviews) + h);
+            } else {
+                const float4 c = __ldcg(coord + h), m = __ldcg(normal + h);   // read once; L2 only (the streamed inputs land during the kernel)
+                X = V4{c.x, c.y, c.z, c.w}; N = V4{m.x, m.y, m.z, m.w};
+                nv = __ldcg(nviews + h);
+            }
         }
         const int sz = min(p.tau, nv);
         const bool usable = live && nv >= 2;              // optim.cpp:631,643: fewer than 2 images -> 2.0
@@ -168,10 +178,11 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
         float* myrow = frames + (size_t)lane * fstride;
         {
             const int* vrow = views + (size_t)h * stride;
+            const unsigned char* vrow8 = reinterpret_cast<const unsigned char*>(views) + (size_t)h * stride;
             V4 px{0.f, 0.f, 0.f, 0.f}, py{0.f, 0.f, 0.f, 0.f};
             bool ref_ok = false;
             if (usable) {
-                const int ref = ready ? __ldcg(vrow) : __ldg(vrow);              // streamed rows must not take the non-coherent path
+                const int ref = packed ? (int)__ldcg(vrow8) : ready ? __ldcg(vrow) : __ldg(vrow);              // streamed rows must not take the non-coherent path
                 ref_ok = ref >= 0 && ref < p.nviews;
                 if (ref_ok) get_paxes(p.views[ref], X, N, p.level_scale, px, py);
             }
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
                 float w = 0.0f;
                 int vk = 0;
                 if (ref_ok && k < sz) {
-                    const int v = ready ? __ldcg(vrow + k) : __ldg(vrow + k);
+                    const int v = packed ? (int)__ldcg(vrow8 + k) : ready ? __ldcg(vrow + k) : __ldg(vrow + k);
                     if (v >= 0 && v < p.nviews) {
                         vk = v;
                         const ViewConst& vc = p.views[v];

@@ -218,6 +218,24 @@ class Context:
         _chk(lib().pmk_ncc_eval(self.h, n, _p(coord), _p(normal), _p(views), _p(nviews), stride, _p(incc), _p(ncc), _p(levels)))
         return (incc, ncc, levels) if want_levels else (incc, ncc)
 
+    @staticmethod
+    def pack_hypotheses(coord, normal, views, nviews):
+        """float4 / float4 / int32 records -> the byte-lean layout of pmk_ncc_eval_packed (w = 1 / w = 0 implied, byte view ids)."""
+        views, nviews = np.asarray(views), np.asarray(nviews)
+        assert nviews.min() >= 0 and nviews.max() < 256
+        v8 = np.where((views < 0) | (views > 254), 255, views).astype(np.uint8)      # 255 = "no such view" (the call needs nviews <= 255)
+        return (np.ascontiguousarray(np.asarray(coord, np.float32)[:, :3]), np.ascontiguousarray(np.asarray(normal, np.float32)[:, :3]),
+                np.ascontiguousarray(v8), np.ascontiguousarray(nviews, np.uint8))
+
+    def ncc_eval_packed(self, coord3, normal3, views8, nviews8, want_levels: bool = False, out=None):
+        """pmk_ncc_eval_packed: host arrays (n,3) f32, (n,3) f32, (n,stride) u8, (n,) u8 -> incc, ncc[, levels]."""
+        n, stride = coord3.shape[0], views8.shape[1]
+        assert coord3.dtype == np.float32 and normal3.dtype == np.float32 and views8.dtype == np.uint8 and nviews8.dtype == np.uint8
+        incc, ncc = out if out is not None else (np.empty(n, np.float32), np.empty(n, np.float32))
+        levels = np.empty((n, self.tau), np.int32) if want_levels else None
+        _chk(lib().pmk_ncc_eval_packed(self.h, n, _p(coord3), _p(normal3), _p(views8), _p(nviews8), stride, _p(incc), _p(ncc), _p(levels)))
+        return (incc, ncc, levels) if want_levels else (incc, ncc)
+
     def ncc_eval_dev(self, n: int, coord: DeviceBuffer, normal: DeviceBuffer, views: DeviceBuffer, nviews: DeviceBuffer, stride: int,
                      incc: DeviceBuffer, ncc: Optional[DeviceBuffer] = None, levels: Optional[DeviceBuffer] = None):
         _chk(lib().pmk_ncc_eval_dev(self.h, n, coord.ptr, normal.ptr, views.ptr, nviews.ptr, stride, incc.ptr,

@@ -181,6 +181,29 @@ def test_streamed_host_call_equals_the_device_call(ctx, small_scene):
         b.free()
 
 
+def test_packed_host_call_is_bit_identical(ctx, small_scene):
+    """pmk_ncc_eval_packed (3-float coordinates / normals, byte view ids: 31 B per hypothesis instead of 60) against pmk_ncc_eval on the
+    widened records -- same bits, scores and pyramid levels, through pageable and pinned buffers, ragged sizes."""
+    from mvskit_b200 import pmk
+    N = 2 * (1 << 17) + 777
+    c, n, vw, nv = small_scene.hypotheses(N, seed=321, well_observed=False)
+    assert (c[:, 3] == 1).all()
+    n = n.copy(); n[:, 3] = 0.0
+    incc, ncc, lv = ctx.ncc_eval(c, n, vw, nv, want_levels=True)
+    c3, n3, v8, nv8 = ctx.pack_hypotheses(c, n, vw, nv)
+    pi, pn, pl = ctx.ncc_eval_packed(c3, n3, v8, nv8, want_levels=True)
+    assert_bits_equal(pi, incc, "packed incc"); assert_bits_equal(pn, ncc, "packed ncc"); assert np.array_equal(pl, lv)
+    h = [pmk.pinned_empty(a.shape, a.dtype) for a in (c3, n3, v8, nv8)]
+    for dst, src in zip(h, (c3, n3, v8, nv8)):
+        dst[:] = src
+    out = (pmk.pinned_empty((N,), np.float32), pmk.pinned_empty((N,), np.float32))
+    for m in (N, 1, 31, (1 << 14) + 1, (1 << 17) - 5):
+        out[0][:] = -7.0
+        ctx.ncc_eval_packed(h[0][:m], h[1][:m], h[2][:m], h[3][:m], out=(out[0][:m], out[1][:m]))
+        assert_bits_equal(out[0][:m], incc[:m], f"pinned packed incc n={m}"); assert_bits_equal(out[1][:m], ncc[:m], f"pinned packed ncc n={m}")
+        assert (out[0][m:] == -7.0).all()
+
+
 def test_state_errors(small_scene):
     from mvskit_b200 import pmk
     c = pmk.Context(nviews=small_scene.nviews)
