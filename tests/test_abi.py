@@ -48,3 +48,19 @@ def test_bad_arguments():
     cfg.nviews, cfg.wsize = 5, 8
     assert L.pmk_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"wsize" in L.pmk_last_error()
+
+
+def test_pack_hypotheses_layout():
+    """The byte-lean records of pmk_ncc_eval_packed: xyz of coord / normal, byte view ids with 255 for "no such view", byte counts."""
+    import numpy as np
+    from mvskit_b200 import pmk
+    coord = np.array([[1, 2, 3, 1], [4, 5, 6, 1]], np.float32)
+    normal = np.array([[0, 0, 1, 0], [0, 1, 0, 0]], np.float32)
+    views = np.array([[3, 0, 254, -1], [7, -1, -1, 300]], np.int32)
+    nviews = np.array([3, 1], np.int32)
+    c3, n3, v8, nv8 = pmk.Context.pack_hypotheses(coord, normal, views, nviews)
+    assert c3.dtype == np.float32 and c3.shape == (2, 3) and c3.flags["C_CONTIGUOUS"] and np.array_equal(c3, coord[:, :3])
+    assert np.array_equal(n3, normal[:, :3])
+    assert v8.dtype == np.uint8 and v8.tolist() == [[3, 0, 254, 255], [7, 255, 255, 255]]
+    assert nv8.dtype == np.uint8 and nv8.tolist() == [3, 1]
+    assert c3.nbytes + n3.nbytes + v8.nbytes + nv8.nbytes == 2 * (12 + 12 + 4 + 1)
