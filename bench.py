@@ -11,7 +11,8 @@ the evals are independent; images are replicated), so scaling is weak.
 
 Prints ONE JSON line (rank 0).  `value` = whole-job evals/s with inputs resident in HBM (CUDA events on the
 launching stream, L2 flushed between steps, max over ranks); `e2e` = the same metric through the host-buffer
-C-ABI call (pinned host inputs, H2D and D2H inside the timed region).
+C-ABI call (pinned host inputs, H2D and D2H inside the timed region).  `e2e_packed` (informational) = the same steps through
+pmk_ncc_eval_packed, the byte-lean form of that call (31 B instead of 60 B per hypothesis over PCIe, bit-identical results).
 """
 from __future__ import annotations
 
