@@ -1088,8 +1088,9 @@ int pmk_store_clear(pmk_ctx* ctx) {
     pmk_store* s = ctx->store;
     const StoreDev& d = s->d;
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, SC_COUNT * sizeof(int), ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(d.ccount, 0, (size_t)d.total_cells * sizeof(int), ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(d.dmap, 0xff, (size_t)d.total_cells * sizeof(unsigned long long), ctx->stream));
+    k_reset_cells<<<(d.total_cells + 255) / 256, 256, 0, ctx->stream>>>(d);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(d.state, 0, ((size_t)d.cap + d.stage_cap) * sizeof(int), ctx->stream));
     s->n = 0;
     s->canonical = true;

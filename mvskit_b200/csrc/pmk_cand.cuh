@@ -59,8 +59,8 @@ __device__ __forceinline__ double uniform_pm1(uint32_t v) { return ((double)(v >
 #define PMK_GRAB_INLINE __noinline__     // one copy of the texture grab: the sweep kernel is I-cache bound with it inlined 15 times
 #endif
 template <int WS, int GW>
-__device__ PMK_GRAB_INLINE int group_grab(const Params& p, int view, V4 X, V4 N, V4 px, V4 py, int col, float cmask,
-                                          float t[WS][3], float& inv_msd, unsigned gm = 0xffffffffu) {
+__device__ __forceinline__ int group_grab_body(const Params& p, int view, V4 X, V4 N, V4 px, V4 py, int col, float cmask,
+                                               float t[WS][3], float& inv_msd, unsigned gm) {
     constexpr int NSAMP = WS * WS;
     constexpr float INV_NSAMP = 1.0f / (float)NSAMP, INV_3NSAMP = 1.0f / (float)(3 * NSAMP);
     Frame f;
@@ -95,6 +95,11 @@ __device__ PMK_GRAB_INLINE int group_grab(const Params& p, int view, V4 X, V4 N,
     const float var = group_sum<GW>(ssd, gm) * INV_3NSAMP;
     inv_msd = var > 0.0f ? rsqrtf(var) : 1.0f;
     return level;
+}
+template <int WS, int GW>
+__device__ PMK_GRAB_INLINE int group_grab(const Params& p, int view, V4 X, V4 N, V4 px, V4 py, int col, float cmask,
+                                          float t[WS][3], float& inv_msd, unsigned gm = 0xffffffffu) {
+    return group_grab_body<WS, GW>(p, view, X, N, px, py, col, cmask, t, inv_msd, gm);
 }
 
 // Optim::dot of two grabbed textures (optim.cpp:601-609); both centred, scales applied here

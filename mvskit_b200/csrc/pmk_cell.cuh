@@ -1,0 +1,876 @@
+// mvskit_b200/csrc/pmk_cell.cuh -- K4 "PMS1c": the wavefront sweep of pmk_sweep.cuh with ONE CTA PER DEST CELL.
+//
+// Same schedule, same arithmetic and therefore the same store as the one-warp-per-cell kernel of round 1 (the tests compare
+// the checksums), but every propagatePatch try (pmmvps/propagate.cpp:123-218) is spread over all evaluator groups of a CTA
+// instead of being walked by one warp:
+//   * a texture grab (Optim::getTex + normalize, optim.cpp:790-844,917-940) is still the work of one 8-lane group, but it lands
+//     in a SHARED-MEMORY slot (centred lattice, column-major per lane) instead of registers, so any group can pair any two;
+//   * Optim::setINCCs (optim.cpp:708-746) -> one group per view, all views of a candidate at once;
+//   * Optim::refinePatch / PMR1 (optim.cpp:470-547) -> the 8 candidates x tau views of a level are 48 independent grabs, then
+//     40 dots from shared memory, then every thread sums the per-view terms in view order (Optim::cost_func, :401-468): a
+//     level costs one grab latency instead of twelve;
+//   * Optim::setRefImage (optim.cpp:348-383) -> grabs one group per view, the pairs spread over all threads;
+//   * Optim::check (optim.cpp:300-323) -> computeGain one warp per registration, findNeighbors one warp per view with a
+//     CTA-wide hash table, filterQuad on the first warp.
+// The list logic (addImages, constraintImages, sortImages, ...) stays on warp 0 and is tiny.  The kernel needs <= 80 registers
+// (the monolith needed 254), runs 3 CTAs x 8 warps per SM, and a dest cell's chain of tries is ~6x shorter, which is what
+// bounds a wavefront step.
+#pragma once
+
+#include "pmk_sweep.cuh"
+
+namespace pmk {
+
+#ifndef PMK_CELL_WARPS
+#define PMK_CELL_WARPS 8
+#endif
+#ifndef PMK_CELL_MINB
+#define PMK_CELL_MINB 3
+#endif
+constexpr int CELL_WARPS = PMK_CELL_WARPS;
+constexpr int EVAL_SLOTS = PMR1_CANDS * PMK_MAX_TAU;      // (candidate, view) items of one PMR1 level
+
+template <int WS>
+struct CellGeom {
+    static constexpr int GW = WS <= 8 ? 8 : 16;              // lanes of an evaluator group
+    static constexpr int G = 32 / GW;                         // groups per warp
+    static constexpr int TG = CELL_WARPS * G;                 // groups per CTA
+    static constexpr int SLOT = WS * 3 * GW;                  // floats of one texture slot: [row][channel][column]
+    __host__ __device__ static constexpr int nslots(int tau) { return (PMR1_CANDS * tau > TG + 1) ? PMR1_CANDS * tau : TG + 1; }
+};
+
+struct CellCta {                       // one per CTA, shared memory
+    int l_id[LKEEP];                   // the dest cell's m_pgrids list, sorted (sortPatches)
+    float l_ncc[LKEEP];
+    unsigned int l_birth[LKEEP];
+    int src_id[SRC_MAX];
+    int removed[REM_OVERLAY + NEW_MAX];
+    int nl, nrem, nnew, nsrc;
+    int bi[8];                         // small broadcasts from warp 0
+    float bf[8];
+    int lvl[EVAL_SLOTS + 4];           // per texture slot: pyramid level sampled, or -1 (getTex == -1)
+    float inv[EVAL_SLOTS + 4];         //                   1 / msd of Optim::normalize
+    float val[EVAL_SLOTS + 4];         //                   robustincc(1 - dot(reference, view))
+    float mp[2 * CAND_MAXV];           // computeGain: per registration, the strongest non-neighbour of its cell
+    int negs[32];                      // preamble: list entries whose m_ncc has to be recomputed
+    int nneg;
+    int nb_count, nb_over;             // findNeighbors
+    unsigned int nb_token;
+    int task;
+    unsigned int stat[SS_COUNT];
+    unsigned long long t_begin, ph_t;
+};
+
+// ---- one texture grab by one evaluator group, into a shared-memory slot -------------------------------------------------------
+// Optim::getTex + Optim::normalize for (X, N, px, py) in `view` (optim.cpp:790-844, 917-940).  Arithmetic identical to
+// group_grab (pmk_cand.cuh); the centred, masked lattice column of each lane goes to slot[(row * 3 + channel) * GW + col].
+// Returns the pyramid level or -1 (then nothing is sampled or written); *inv_msd = 1 / sqrt(ssd / (3 n)) (1 when ssd == 0).
+template <int WS, int GW>
+__device__ __noinline__ int grab_slot(const Params& p, int view, V4 X, V4 N, V4 px, V4 py, int col, unsigned gm, float* __restrict__ slot,
+                                      float* __restrict__ inv_msd) {
+    constexpr int NSAMP = WS * WS;
+    constexpr float INV_NSAMP = 1.0f / (float)NSAMP, INV_3NSAMP = 1.0f / (float)(3 * NSAMP);
+    if (view < 0 || view >= p.nviews) return -1;
+    const ViewConst& vc = p.views[view];
+    const Frame f = make_frame(p, vc, X, N, px, py);
+    const int level = f.level;
+    if (level < 0) return -1;
+    const float cmask = col < WS ? 1.0f : 0.0f;
+    const Texel* img = vc.img[level];
+    const int W = vc.w[level];
+    const float fcol = (float)(col < WS ? col : WS - 1);
+    const float bx = fmaf(f.dxx, fcol, f.tlx), by = fmaf(f.dxy, fcol, f.tly);
+    float t[WS][3];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int y = 0; y < WS; ++y) {
+        bilinear(img, W, fmaf(f.dyx, (float)y, bx), fmaf(f.dyy, (float)y, by), t[y][0], t[y][1], t[y][2]);
+        s0 = fmaf(t[y][0], cmask, s0); s1 = fmaf(t[y][1], cmask, s1); s2 = fmaf(t[y][2], cmask, s2);
+    }
+    const float m0 = -group_sum<GW>(s0, gm) * INV_NSAMP * cmask, m1 = -group_sum<GW>(s1, gm) * INV_NSAMP * cmask, m2 = -group_sum<GW>(s2, gm) * INV_NSAMP * cmask;
+    float ssd = 0.f;
+#pragma unroll
+    for (int y = 0; y < WS; ++y) {
+        t[y][0] = fmaf(t[y][0], cmask, m0); t[y][1] = fmaf(t[y][1], cmask, m1); t[y][2] = fmaf(t[y][2], cmask, m2);
+        ssd = fmaf(t[y][0], t[y][0], fmaf(t[y][1], t[y][1], fmaf(t[y][2], t[y][2], ssd)));
+        slot[(y * 3 + 0) * GW + col] = t[y][0]; slot[(y * 3 + 1) * GW + col] = t[y][1]; slot[(y * 3 + 2) * GW + col] = t[y][2];
+    }
+    const float var = group_sum<GW>(ssd, gm) * INV_3NSAMP;
+    *inv_msd = var > 0.0f ? rsqrtf(var) : 1.0f;
+    return level;
+}
+
+// Optim::dot (optim.cpp:601-609) of two slots; same order of operations as group_dot(a = reference, b = view)
+template <int WS, int GW>
+__device__ __forceinline__ float dot_slots(const float* __restrict__ a, float inv_a, const float* __restrict__ b, float inv_b, int col, unsigned gm) {
+    float dp = 0.f;
+#pragma unroll
+    for (int y = 0; y < WS; ++y)
+        dp = fmaf(a[(y * 3 + 0) * GW + col], b[(y * 3 + 0) * GW + col],
+                  fmaf(a[(y * 3 + 1) * GW + col], b[(y * 3 + 1) * GW + col], fmaf(a[(y * 3 + 2) * GW + col], b[(y * 3 + 2) * GW + col], dp)));
+    return group_sum<GW>(dp, gm) * inv_a * inv_b * (1.0f / (float)(3 * WS * WS));
+}
+
+// per-thread coordinates inside the CTA
+template <int WS>
+struct CellLane {
+    int tid, warp, lane, col, g;
+    unsigned gm;
+    __device__ __forceinline__ CellLane() {
+        constexpr int GW = CellGeom<WS>::GW;
+        tid = threadIdx.x; warp = tid >> 5; lane = tid & 31; col = lane % GW;
+        g = warp * CellGeom<WS>::G + lane / GW;
+        gm = group_mask<GW>(lane);
+    }
+};
+
+// ---- Optim::setINCCs 1-vs-all (optim.cpp:708-746) by the CTA: one group per view -----------------------------------------------
+// images / inccs live in shared memory; every thread holds the same X, N, n.  Ends with a CTA barrier.
+template <int WS>
+__device__ __forceinline__ void cta_set_inccs(const Params& p, CellCta& cs, float* tex, V4 X, V4 N, const int* images, int n, int robust, float* inccs) {
+    typedef CellGeom<WS> Gm;
+    const CellLane<WS> L;
+    V4 px, py;
+    get_paxes(p.views[images[0]], X, N, p.level_scale, px, py);
+    float* mine = tex + (size_t)(1 + L.g) * Gm::SLOT;             // slot 0: the reference view; slot 1 + g: this group's view
+    int lv = -1;
+    float inv = 1.0f;
+    if (L.g < n) {
+        lv = grab_slot<WS, Gm::GW>(p, images[L.g], X, N, px, py, L.col, L.gm, L.g == 0 ? tex : mine, &inv);
+        if (L.g == 0 && L.col == 0) { cs.lvl[0] = lv; cs.inv[0] = inv; }
+    }
+    __syncthreads();
+    const int l0 = cs.lvl[0];
+    const float inv0 = cs.inv[0];
+    if (l0 < 0) {
+        for (int k = L.tid; k < n; k += CELL_WARPS * 32) inccs[k] = 2.0f;
+        __syncthreads();
+        return;
+    }
+    if (L.tid == 0) inccs[0] = 0.0f;
+#pragma unroll 1
+    for (int base = 0; base < n; base += Gm::TG) {
+        const int i = base + L.g;
+        if (i >= n) break;
+        if (base > 0) lv = grab_slot<WS, Gm::GW>(p, images[i], X, N, px, py, L.col, L.gm, mine, &inv);
+        if (i == 0) continue;
+        float r = 2.0f;
+        if (lv >= 0) {
+            __syncwarp(L.gm);
+            const float d = dot_slots<WS, Gm::GW>(tex, inv0, mine, inv, L.col, L.gm);
+            r = xsub(1.0f, d);
+            if (robust) r = robustincc(r);
+        }
+        if (L.col == 0) inccs[i] = r;
+    }
+    __syncthreads();
+}
+
+// PatchManager::computeNcc (patch_manager.cpp:401-404) on {X, N, ws.images[0..nv)}: every thread returns m_ncc
+template <int WS>
+__device__ __forceinline__ float cta_compute_ncc(const Params& p, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int nv) {
+    const int tid = threadIdx.x;
+    if (tid < 32) compute_weights(p, X, N, ws.images, nv, ws.units, tid);
+    float incc = 2.0f;
+    if (nv >= 2) {
+        const int sz = min(p.tau, nv);
+        cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, sz, 1, ws.inccs);
+        float score = 0.0f, tw = 0.0f;
+        for (int i = 1; i < sz; ++i) {
+            const float v = ws.inccs[i];
+            if (v != 2.0f) { tw = xadd(tw, ws.units[i]); score = xadd(score, xmul(v, ws.units[i])); }
+        }
+        incc = (tw == 0.0f) ? 2.0f : xdiv(score, tw);
+    }
+    __syncthreads();
+    return xsub(1.0f, unrobustincc(incc));
+}
+
+// ---- Optim::cost_func (optim.cpp:401-468) for `ncand` encoded points at once -------------------------------------------------------
+// item = (candidate c, view i): grab into slot c * sz + i, then the dots against the candidate's reference slot.  gen(c, x) yields
+// candidate c's encoded point.  On return (after a CTA barrier) cs.lvl / cs.val hold what eval_cost needs.
+template <int WS, typename Gen>
+__device__ __forceinline__ void cta_costs(const CandParams& cp, const RefineCtx& rc, CellCta& cs, float* tex, const int* images, int sz, int ncand, Gen gen) {
+    typedef CellGeom<WS> Gm;
+    const Params& p = cp.p;
+    const CellLane<WS> L;
+    const int nitems = ncand * sz;
+#pragma unroll 1
+    for (int item = L.g; item < nitems; item += Gm::TG) {
+        const int c = item / sz, i = item - c * sz;
+        double xc[3];
+        gen(c, xc);
+        V4 coord, normal, px, py;
+        decode(cp, rc, xc, coord, normal);
+        get_paxes(p.views[rc.ref], coord, normal, p.level_scale, px, py);
+        float inv = 1.0f;
+        const int lv = grab_slot<WS, Gm::GW>(p, images[i], coord, normal, px, py, L.col, L.gm, tex + (size_t)item * Gm::SLOT, &inv);
+        if (L.col == 0) { cs.lvl[item] = lv; cs.inv[item] = inv; }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int item = L.g; item < nitems; item += Gm::TG) {
+        const int c = item / sz, i = item - c * sz;
+        if (i == 0 || cs.lvl[c * sz] < 0 || cs.lvl[item] < 0) continue;
+        const float d = dot_slots<WS, Gm::GW>(tex + (size_t)(c * sz) * Gm::SLOT, cs.inv[c * sz], tex + (size_t)item * Gm::SLOT, cs.inv[item], L.col, L.gm);
+        if (L.col == 0) cs.val[item] = robustincc(__double2float_rn(1.0 - (double)d));
+    }
+    __syncthreads();
+}
+// the cost of candidate c from the per-view terms, summed in view order as cost_func does
+__device__ __forceinline__ double eval_cost(const CellCta& cs, int c, int sz, int minimum) {
+    if (cs.lvl[c * sz] < 0) return 2.0;
+    double ans = 0.0;
+    int denom = 0;
+    for (int i = 1; i < sz; ++i) if (cs.lvl[c * sz + i] >= 0) { ans += (double)cs.val[c * sz + i]; ++denom; }
+    if (denom < minimum - 1) return 2.0;
+    return ans / (double)denom;
+}
+
+__device__ __forceinline__ void pmr1_point(const CandParams& cp, uint64_t stream, int level, int cnd, const double best[3], const double r[3], double xc[3]) {
+    const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
+    const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
+    uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)level, (uint32_t)cnd};
+    philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xc[i] = fmax(fmin(__dadd_rn(best[i], __dmul_rn(r[i], uniform_pm1(ctr[i]))), ub[i]), lb[i]);
+}
+
+// ---- Optim::refinePatch (optim.cpp:470-547), schedule PMR1, by the CTA ------------------------------------------------------------------
+// Same points, same costs, same argmin as warp_refine (pmk_cand.cuh).  Every thread returns the same X, N and m_ncc.
+template <int WS>
+__device__ __forceinline__ float cta_refine(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4& X, V4& N, int nv, float dscale, uint64_t stream) {
+    const Params& p = cp.p;
+    const int tid = threadIdx.x;
+    const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
+    const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
+    RefineCtx rc;
+    rc.center = X;
+    rc.ref = ws.images[0];
+    rc.ray = sub4(X, ld4(p.views[rc.ref].center));
+    rc.ray = div4(rc.ray, norm4(rc.ray));
+    rc.dscale = dscale;
+    if (tid < 32) compute_weights(p, X, N, ws.images, nv, ws.units, tid);          // m_weights of the UNREFINED patch (optim.cpp:490)
+    double best[3];
+    encode(cp, rc, X, N, best);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) best[i] = fmax(fmin(best[i], ub[i]), lb[i]);
+    const int sz = min(p.tau, nv);
+    const int minimum = min(p.min_image_num, sz);
+    cta_costs<WS>(cp, rc, cs, tex, ws.images, sz, 1, [&](int, double* x) { x[0] = best[0]; x[1] = best[1]; x[2] = best[2]; });
+    double fbest = eval_cost(cs, 0, sz, minimum);
+    double r[3] = {4.0, 4.0, 4.0};
+#pragma unroll 1
+    for (int level = 0; level < PMR1_LEVELS; ++level) {
+        __syncthreads();                                                           // eval_cost readers of the previous level are done
+        cta_costs<WS>(cp, rc, cs, tex, ws.images, sz, PMR1_CANDS, [&](int c, double* x) { pmr1_point(cp, stream, level, c, best, r, x); });
+        // argmin over the level's candidates in index order, lowest index on ties (strict <)
+        double fwin = eval_cost(cs, 0, sz, minimum);
+        int cwin = 0;
+        for (int c = 1; c < PMR1_CANDS; ++c) { const double fc = eval_cost(cs, c, sz, minimum); if (fc < fwin) { fwin = fc; cwin = c; } }
+        if (fwin < fbest) { fbest = fwin; double xw[3]; pmr1_point(cp, stream, level, cwin, best, r, xw); best[0] = xw[0]; best[1] = xw[1]; best[2] = xw[2]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = __dmul_rn(r[i], 0.6);
+    }
+    __syncthreads();
+    // optim.cpp:534-541: decode, normal.w = 0, ncc = 1.0 - unrobustincc(computeINCC(...)) with the stale weights
+    V4 Xf, Nf;
+    decode(cp, rc, best, Xf, Nf);
+    float incc = 2.0f;
+    if (nv >= 2) {
+        cta_costs<WS>(cp, rc, cs, tex, ws.images, sz, 1, [&](int, double* x) { x[0] = best[0]; x[1] = best[1]; x[2] = best[2]; });
+        if (cs.lvl[0] >= 0) {
+            float score = 0.0f, tw = 0.0f;
+            for (int i = 1; i < sz; ++i)
+                if (cs.lvl[i] >= 0) { tw = xadd(tw, ws.units[i]); score = xadd(score, xmul(cs.val[i], ws.units[i])); }
+            incc = (tw == 0.0f) ? 2.0f : xdiv(score, tw);
+        }
+    }
+    __syncthreads();
+    X = Xf;
+    N = V4{Nf.x, Nf.y, Nf.z, 0.0f};
+    return __double2float_rn(1.0 - (double)unrobustincc(incc));
+}
+
+// ---- Optim::setRefImage (optim.cpp:348-383) by the CTA; same arithmetic as warp_set_ref_image ------------------------------------------
+template <int WS>
+__device__ __forceinline__ void cta_set_ref_image(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int nv, int wslot) {
+    typedef CellGeom<WS> Gm;
+    constexpr int TEXW = WS * WS * 3;
+    const Params& p = cp.p;
+    const CellLane<WS> L;
+    float* gtex = cp.tex_scratch + (size_t)wslot * p.nviews * (TEXW + 4);
+    float* mat = cp.mat_scratch + (size_t)wslot * p.nviews * p.nviews;
+    V4 px, py;
+    get_paxes(p.views[ws.images[0]], X, N, p.level_scale, px, py);
+    float* mine = tex + (size_t)L.g * Gm::SLOT;
+#pragma unroll 1
+    for (int base = 0; base < nv; base += Gm::TG) {
+        const int i = base + L.g;
+        if (i >= nv) break;
+        float inv = 1.0f;
+        const int lv = grab_slot<WS, Gm::GW>(p, ws.images[i], X, N, px, py, L.col, L.gm, mine, &inv);
+        float* dst = gtex + (size_t)i * (TEXW + 4);
+        if (lv >= 0 && L.col < WS) {
+#pragma unroll
+            for (int y = 0; y < WS; ++y) {
+                float* q = dst + (y * WS + L.col) * 3;
+                q[0] = mine[(y * 3 + 0) * Gm::GW + L.col] * inv; q[1] = mine[(y * 3 + 1) * Gm::GW + L.col] * inv; q[2] = mine[(y * 3 + 2) * Gm::GW + L.col] * inv;
+            }
+        }
+        if (L.col == 0) dst[TEXW] = lv >= 0 ? 1.0f : 0.0f;
+        __syncwarp(L.gm);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = L.tid; q < nv * nv; q += CELL_WARPS * 32) {
+        const int i = q / nv, j = q % nv;
+        if (j < i) continue;
+        float v = 0.0f;
+        if (j > i) {
+            const float* a = gtex + (size_t)i * (TEXW + 4);
+            const float* b = gtex + (size_t)j * (TEXW + 4);
+            v = 2.0f;
+            if (a[TEXW] != 0.0f && b[TEXW] != 0.0f) {
+                float dp = 0.0f;
+                for (int e = 0; e < TEXW; ++e) dp = fmaf(a[e], b[e], dp);
+                v = robustincc(xsub(1.0f, dp * (1.0f / (float)TEXW)));
+            }
+        }
+        mat[i * nv + j] = v; mat[j * nv + i] = v;
+    }
+    __syncthreads();
+    if (L.warp == 0) {
+        float best = 1073741824.0f;
+        int bi = -1;
+        for (int i = L.lane; i < nv; i += 32) {
+            float sum = 0.0f;
+            for (int j = 0; j < nv; ++j) sum = xadd(sum, mat[i * nv + j]);
+            if (sum < best) { best = sum; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+        }
+        if (L.lane == 0 && bi > 0) { const int tmp = ws.images[0]; ws.images[0] = ws.images[bi]; ws.images[bi] = tmp; }
+    }
+    __syncthreads();
+}
+
+// ---- Optim::preProcess (optim.cpp:137-163) by the CTA; every thread gets the same return value, nv, dscale, ascale ------------------
+template <int WS>
+__device__ __forceinline__ int cta_pre_process(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int& nv, float& dscale, float& ascale) {
+    const Params& p = cp.p;
+    const int tid = threadIdx.x;
+    dscale = 0.0f; ascale = 0.0f;
+    if (nv < 1) { nv = 0; return -1; }
+    if (tid < 32) {
+        const int n2 = warp_add_images(p, X, N, ws.images, nv, CAND_MAXV, ws.mark, tid);                // optim.cpp:139
+        if (tid == 0) cs.bi[0] = n2;
+    }
+    __syncthreads();
+    nv = cs.bi[0];
+    cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // constraintImages, :141
+    if (tid < 32) {
+        int n2 = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold_before, tid);
+        __syncwarp();
+        n2 = warp_sort_images(cp, X, N, ws, n2, tid);                                                   // :143
+        __syncwarp();
+        float ds = 0.0f, as = 0.0f;
+        int r = -1;
+        if (n2 > 0) warp_set_scales(p, X, ws.images, n2, ds, as, ws.units, tid);                         // :145-147
+        if (n2 >= p.min_image_num) {                                                                    // :149
+            if (warp_check_angles(cp, X, ws, n2, tid)) r = 0;                                           // :153-160
+            else n2 = 0;
+        }
+        if (tid == 0) { cs.bi[0] = n2; cs.bi[1] = r; cs.bf[0] = ds; cs.bf[1] = as; }
+    }
+    __syncthreads();
+    nv = cs.bi[0]; dscale = cs.bf[0]; ascale = cs.bf[1];
+    const int r = cs.bi[1];
+    __syncthreads();
+    return r;
+}
+
+// ---- Optim::postProcess (optim.cpp:260-290), the store-independent part, by the CTA ---------------------------------------------------
+template <int WS>
+__device__ __forceinline__ int cta_post_process(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int& nv, int wslot) {
+    const Params& p = cp.p;
+    const int tid = threadIdx.x;
+    if (nv < p.min_image_num) return -1;                                                                // :261
+    if (tid < 32) {
+        const int m = warp_get_mask(p, X, tid);                                                         // :265
+        int n2 = nv;
+        if (m != 0) n2 = warp_add_images(p, X, N, ws.images, nv, CAND_MAXV, ws.mark, tid);               // :268
+        if (tid == 0) { cs.bi[0] = n2; cs.bi[1] = m; }
+    }
+    __syncthreads();
+    nv = cs.bi[0];
+    const int masked = cs.bi[1];
+    __syncthreads();
+    if (masked == 0) return -1;
+    cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // :269
+    if (tid < 32) {
+        int n2 = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, tid);
+        __syncwarp();
+        n2 = warp_filter_by_angle(p, X, N, ws.images, n2, tid);                                         // :270
+        if (tid == 0) cs.bi[0] = n2;
+    }
+    __syncthreads();
+    nv = cs.bi[0];
+    __syncthreads();
+    if (nv < p.min_image_num) return -1;                                                                // :272
+    cta_set_ref_image<WS>(cp, ws, cs, tex, X, N, nv, wslot);                                            // :277
+    cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // :279
+    if (tid < 32) {
+        const int n2 = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, tid);
+        if (tid == 0) cs.bi[0] = n2;
+    }
+    __syncthreads();
+    nv = cs.bi[0];
+    __syncthreads();
+    if (nv < p.min_image_num) return -1;                                                                // :281
+    return 0;
+}
+
+// ---- Filter::computeGain (filter.cpp:108-146) by the CTA: one warp per registration, lanes over the cell's slots --------------------
+// The maximum over a cell does not depend on the order; the subtractions run in list order like the reference.
+__device__ __forceinline__ float cta_compute_gain(const StoreParams& sp, CellCta& cs, const PGeo& me, float ncc, const PatchLists& pl, const Overlay& ov) {
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tot = pl.nimg + pl.nvimg;
+    for (int i = warp; i < tot; i += CELL_WARPS) {
+        const bool isv = i >= pl.nimg;
+        const int img = isv ? pl.vimages[i - pl.nimg] : pl.images[i], pc = isv ? pl.vcells[i - pl.nimg] : pl.cells[i];
+        const float pdepth = isv ? dot4(ld4(p.views[img].oaxis), me.X) : 0.0f;
+        const int c = cell_global(sp, img, cell_x(pc), cell_y(pc));
+        const bool local = (c == ov.cell);
+        const int n = local ? ov.n : min(st.ccount[c], st.cell_cap);
+        float mp = 0.0f;
+        for (int s = lane; s < n; s += 32) {
+            const int e = local ? ov.ids[s] : st.cslots[(size_t)c * st.cell_cap + s];
+            if (e == SLOT_TOMB || e < 0 || (!local && overlay_removed(ov, e))) continue;
+            const PGeo q = load_geo(st, e);
+            if (isv && !(pdepth < dot4(ld4(p.views[img].oaxis), q.X))) continue;                   // Camera::computeDepth (camera.cpp:339-346)
+            if (!is_neighbor(sp, me, q, sp.neighbor_threshold1)) mp = max_std(mp, xsub(st.scal[e].x, p.ncc_threshold));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mp = max_std(mp, __shfl_xor_sync(0xffffffffu, mp, o));
+        if (lane == 0) cs.mp[i] = mp;
+    }
+    __syncthreads();
+    float gain = xmul(max_std(0.0f, xsub(ncc, p.ncc_threshold)), (float)pl.nimg);                 // score2 (patch.cpp:27-29)
+    for (int i = 0; i < tot; ++i) gain = xsub(gain, cs.mp[i]);
+    __syncthreads();
+    return gain;
+}
+
+// ---- PatchManager::findNeighbors (patch_manager.cpp:671-728) by the CTA: one warp per view of m_images ----------------------------------
+// Same cells, same tests, same (sorted) result as warp_find_neighbors; the (token, id) table and the output list are shared by the warps.
+__device__ __forceinline__ int cta_find_neighbors(const StoreParams& sp, CellCta& cs, const PGeo& me, const PatchLists& pl, float scale, int margin,
+                                                  const Overlay& ov, int* out) {
+    const StoreDev& st = sp.st;
+    const Params& p = sp.cp.p;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float u1 = __int_as_float(0x7f800000), u2 = u1;
+    float usum = 0.0f;
+    for (int i = 0; i < pl.nimg; ++i) {                                 // Propagate::computeRadius (propagate.cpp:474-481)
+        const ViewConst& vc = p.views[pl.images[i]];
+        const float gu = get_unit(vc, me.X, p.level_scale);
+        usum = xadd(usum, gu);
+        V4 ray = sub4(ld4(vc.center), me.X);
+        ray = div4(ray, norm4(ray));
+        const float d = dot4(ray, me.N);
+        const float u = (0.0f < d) ? xdiv(gu, d) : 1073741824.0f;
+        if (u < u1) { u2 = u1; u1 = u; } else if (u < u2) u2 = u;
+    }
+    const float rad0 = xmul(u2, (float)p.csize);
+    const float radius = __double2float_rn(__dmul_rn(1.5 * (double)margin, (double)rad0));
+    const float unit = xmul(xdiv(usum, (float)pl.nimg), (float)p.csize);
+    const float thr = xmul(sp.neighbor_threshold, scale);
+    unsigned long long* table = reinterpret_cast<unsigned long long*>(out + 2 * NB_CAP);
+    unsigned int* tokp = reinterpret_cast<unsigned int*>(table + NB_HASH);
+    if (tid == 0) {
+        unsigned int token = *tokp + 1;
+        if (token == 0) token = 1;
+        *tokp = token;
+        cs.nb_token = token; cs.nb_count = 0; cs.nb_over = 0;
+    }
+    __syncthreads();
+    const unsigned int token = cs.nb_token;
+    bool overflow = false;
+    const int side = 2 * margin + 1, ncell = side * side;
+    for (int i = warp; i < pl.nimg; i += CELL_WARPS) {
+        const int img = pl.images[i];
+        const ViewConst& vc = p.views[img];
+        const int ix = cell_x(pl.cells[i]), iy = cell_y(pl.cells[i]);
+        int myc = -1, myn = 0, mynslot = 0;
+        if (lane < ncell) {
+            const int yt = iy + lane / side - margin, xt = ix + lane % side - margin;
+            if (!(yt < 0 || vc.gh <= yt || xt < 0 || vc.gw <= xt)) {
+                myc = cell_global(sp, img, xt, yt);
+                mynslot = min(st.ccount[myc], st.cell_cap);
+                myn = mynslot + (myc == ov.cell ? ov.n : 0);
+            }
+        }
+        int incl = myn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int base = 0; base < total; base += 32) {
+            const int f = min(base + lane, total - 1);
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, j + step - 1); if (v <= f) j += step; }
+            const int c = __shfl_sync(0xffffffffu, myc, j), nslot = __shfl_sync(0xffffffffu, mynslot, j);
+            const int slot = f - (__shfl_sync(0xffffffffu, incl, j) - __shfl_sync(0xffffffffu, myn, j));
+            int id = -1;
+            if (base + lane < total && c >= 0) {
+                if (slot < nslot) {
+                    const int e = st.cslots[(size_t)c * st.cell_cap + slot];
+                    if ((e & 0x7fffffff) != SLOT_TOMB) {
+                        const bool isv = e < 0;
+                        const int q = e & 0x7fffffff;
+                        if (!(c == ov.cell && !isv) && !overlay_removed(ov, q)) id = q;
+                    }
+                } else id = ov.ids[slot - nslot];
+            }
+            bool hit = false;
+            if (id >= 0 && nb_insert(table, token, id, overflow)) hit = is_neighbor_radius(sp, me, load_geo(st, id), unit, thr, radius) != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            int wbase = 0;
+            if (m != 0 && lane == 0) wbase = atomicAdd(&cs.nb_count, __popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (hit) { const int pos = wbase + __popc(m & ((1u << lane) - 1u)); if (pos < NB_CAP) out[pos] = id; }
+        }
+    }
+    if (overflow) cs.nb_over = 1;
+    __syncthreads();
+    int nuni = cs.nb_count;
+    if (nuni > NB_CAP) { nuni = NB_CAP; if (tid == 0) cs.nb_over = 1; }
+    // ascending id order, as warp_find_neighbors leaves it (the quadric fit sums over the neighbours in this order)
+    int* tmp = out + NB_CAP;
+    for (int k = tid; k < nuni; k += CELL_WARPS * 32) {
+        const int id = out[k];
+        int rank = 0;
+        for (int j = 0; j < nuni; ++j) rank += out[j] < id ? 1 : 0;
+        tmp[rank] = id;
+    }
+    __syncthreads();
+    for (int k = tid; k < nuni; k += CELL_WARPS * 32) out[k] = tmp[k];
+    if (tid == 0 && cs.nb_over) atomicAdd(st.counters + SC_NBOVER, 1);
+    __syncthreads();
+    return nuni;
+}
+
+// warp-0 pieces kept out of line so that their registers (double-precision normal equations, the sorted cell lists) do not set
+// the budget of the whole kernel
+__device__ __noinline__ int quad_out_of_line(const StoreParams& sp, const PGeo& me, const PatchLists& pl, const int* nb, int n, int lane) {
+    return warp_filter_quad(sp, me, pl, nb, n, nullptr, lane);
+}
+__device__ __noinline__ int topk_trim_out_of_line(const StoreParams& sp, int c, int keep, int* id, float* ncc, unsigned int* birth, int* removed, int* nremoved,
+                                                  int* rem_list, int* ntrim, int lane) {
+    return warp_load_cell_topk<true>(sp, c, keep, id, ncc, birth, removed, nremoved, rem_list, ntrim, lane);
+}
+__device__ __noinline__ int topk_out_of_line(const StoreParams& sp, int c, int keep, int* id, float* ncc, unsigned int* birth, int lane) {
+    return warp_load_cell_topk<false>(sp, c, keep, id, ncc, birth, nullptr, nullptr, nullptr, nullptr, lane);
+}
+
+// =====================================================================================================================================
+// the kernel: dest cells of one wavefront step, handed out longest-first through a counter; one CTA per cell at a time
+// =====================================================================================================================================
+template <int WS>
+__global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const StoreParams sp, const SweepArgs sa) {
+    typedef CellGeom<WS> Gm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& ws = *reinterpret_cast<WarpScratch*>(smem_raw);
+    SweepScratch& ss = *reinterpret_cast<SweepScratch*>(smem_raw + sizeof(WarpScratch));
+    CellCta& cs = *reinterpret_cast<CellCta*>(smem_raw + sizeof(WarpScratch) + sizeof(SweepScratch));
+    float* tex = reinterpret_cast<float*>(smem_raw + ((sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellCta) + 15) & ~(size_t)15));
+    const CandParams& cp = sp.cp;
+    const Params& p = cp.p;
+    const StoreDev& st = sp.st;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wslot = sa.wslot_base + blockIdx.x;              // this CTA's slice of the pairwise / findNeighbors scratch
+    const int inc = sa.inc;
+    const int maxp = sp.max_patches_cell;
+    if (tid < SS_COUNT) cs.stat[tid] = 0;
+    __syncthreads();
+#define PMK_STAT(slot, v) do { if (tid == 0) cs.stat[slot] += (v); } while (0)
+    // profiling only: thread 0 closes the phase that ends here
+#define PMK_PHASE(slot)                                                                                    \
+    if (sa.phase_ns != nullptr && tid == 0) {                                                              \
+        unsigned long long now_;                                                                           \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                                           \
+        if ((slot) >= 0) atomicAdd(sa.phase_ns + (slot), now_ - cs.ph_t);                                  \
+        cs.ph_t = now_;                                                                                    \
+    }
+
+    for (;;) {
+        if (tid == 0) cs.task = atomicAdd(st.counters + SC_NEXT, 1);
+        __syncthreads();
+        const int tslot = cs.task;
+        if (tslot >= sa.ntasks) break;
+        const int task = sa.order[tslot];
+        int g = 0;
+        while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+        const int img = sa.g_img[g];
+        const ViewConst& vimgc = p.views[img];
+        const int gw = vimgc.gw, gh = vimgc.gh;
+        const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
+        const int cD = st.cell_base[img] + y * gw + x;
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cs.t_begin));
+        // ================= preamble: sortPatches' recomputation of negative m_ncc (patch_manager.cpp:411-415), by the CTA =================
+        {
+            const int n = min(st.ccount[cD], st.cell_cap);
+            for (int base = 0; base < n; base += 32) {
+                if (warp == 0) {
+                    const int s2 = base + lane;
+                    int e = SLOT_TOMB;
+                    if (s2 < n) e = st.cslots[(size_t)cD * st.cell_cap + s2];
+                    const bool neg = e != SLOT_TOMB && e >= 0 && st.state[e] == 1 && st.scal[e].x < 0.0f;
+                    const unsigned msk = __ballot_sync(0xffffffffu, neg);
+                    if (neg) cs.negs[__popc(msk & ((1u << lane) - 1u))] = e;
+                    if (lane == 0) cs.nneg = __popc(msk);
+                }
+                __syncthreads();
+                const int nneg = cs.nneg;
+                for (int j = 0; j < nneg; ++j) {
+                    const int el = cs.negs[j];
+                    const int nv = min(st.nimg[el], CAND_MAXV);
+                    for (int k = tid; k < nv; k += CELL_WARPS * 32) ws.images[k] = st.images[(size_t)el * st.maxv + k];
+                    __syncthreads();
+                    const float v = cta_compute_ncc<WS>(p, ws, cs, tex, f4v(st.coord[el]), f4v(st.normal[el]), nv);
+                    if (tid == 0) st.scal[el].x = v;
+                }
+                __syncthreads();
+            }
+        }
+        // ================= preamble (warp 0): D's list, trim, sources (propagate.cpp:88-99,123-134) =================
+        if (warp == 0) {
+            int nrem = 0, ntrim = 0;
+            const int nl = topk_trim_out_of_line(sp, cD, maxp, cs.l_id, cs.l_ncc, cs.l_birth, cs.removed, &nrem, sa.rem_list, &ntrim, lane);
+            if (lane == 0) cs.stat[SS_TRIMMED] += ntrim;
+            int nsrc = 0;
+            for (int side = 0; side < 2; ++side) {              // (x, y - inc) first, then (x - inc, y); sorted top-maxp, reference view == img
+                const int sx = side == 0 ? x : x - inc, sy = side == 0 ? y - inc : y;
+                if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
+                int* tid_ = ss.vimg; float* tncc = reinterpret_cast<float*>(ss.vcell);       // scratch, free until stage B
+                unsigned int* tbirth = reinterpret_cast<unsigned int*>(ss.cells);
+                const int m = topk_out_of_line(sp, st.cell_base[img] + sy * gw + sx, maxp, tid_, tncc, tbirth, lane);
+                for (int i = 0; i < m && nsrc < SRC_MAX; ++i) {
+                    const int e = tid_[i];
+                    if (st.images[(size_t)e * st.maxv] == img) { if (lane == 0) cs.src_id[nsrc] = e; ++nsrc; }
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { cs.nl = nl; cs.nrem = nrem; cs.nnew = 0; cs.nsrc = nsrc; }
+        }
+        __syncthreads();
+        const int ntries = 2 * cs.nsrc;                                                    // MAX_NUM_OF_PROPAG tries per call
+        // ================= the propagatePatch tries (propagate.cpp:122-218), in order, each one spread over the CTA =================
+#pragma unroll 1
+        for (int t = 0; t < ntries; ++t) {
+            const int call = t >> 1, k = t & 1;
+            const int src = cs.src_id[call];
+            const V4 sX = f4v(st.coord[src]), sN = f4v(st.normal[src]);
+            const int sref = st.images[(size_t)src * st.maxv];
+            const int snv = min(st.nimg[src], CAND_MAXV);
+            // one PMR1 stream per call: (iter, view, dest cell, call ordinal)
+            const uint64_t stream = ((uint64_t)(unsigned)sa.iter << 56) ^ ((uint64_t)(unsigned)img << 40) ^ ((uint64_t)(unsigned)(y * gw + x) << 8) ^ (uint64_t)call;
+            const int np = cs.nl;
+            const int wid = np >= maxp ? cs.l_id[maxp - 1] : -1;
+            const float wncc = np >= maxp ? cs.l_ncc[maxp - 1] : 0.0f;
+            PMK_PHASE(-1)
+            if (sa.phase_ns != nullptr && tid == 0) atomicAdd(sa.phase_ns + 6, 1ull);
+            Cand cd;
+            cd.nv = 0; cd.nvv = 0; cd.ncc = 0.f; cd.dscale = 0.f; cd.ascale = 0.f; cd.tmp = 0.f;
+            cd.X = V4{0.f, 0.f, 0.f, 1.f}; cd.N = sN;
+            int outcome = TRY_GEN_NULL;
+            {
+                V3 ic;
+                if (np < maxp) {
+                    float jx = sa.jitter[2 * k], jy = sa.jitter[2 * k + 1];
+                    if (sa.jitter_mode == 1) {
+                        uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), 0x4a495454u, (uint32_t)k};
+                        philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
+                        jx = (float)(0.5 * uniform_pm1(ctr[0])); jy = (float)(0.5 * uniform_pm1(ctr[1]));
+                    }
+                    const float cxf = (float)(p.csize * (2 * x + 1) - 1) / 2.0f, cyf = (float)(p.csize * (2 * y + 1) - 1) / 2.0f;
+                    ic = V3{xadd(cxf, xmul(jx, (float)p.csize)), xadd(cyf, xmul(jy, (float)p.csize)), xadd(1.0f, 0.0f)};
+                } else ic = project(vimgc.P, f4v(st.coord[wid]));
+                // ---- generatePatch (propagate.cpp:220-237) ----
+                const ViewConst& vr = p.views[sref];
+                const float depth = dot4(ld4(vr.oaxis), sX);
+                const float b0 = xsub(xmul(depth, ic.x), vr.P[3]), b1 = xsub(xmul(depth, ic.y), vr.P[7]), b2 = xsub(xmul(depth, ic.z), vr.P[11]);
+                V4 X, N = sN;                                                              // Camera::unproject (camera.cpp:329-337)
+                X.x = xadd(xadd(xmul(vr.Minv[0], b0), xmul(vr.Minv[1], b1)), xmul(vr.Minv[2], b2));
+                X.y = xadd(xadd(xmul(vr.Minv[4], b0), xmul(vr.Minv[5], b1)), xmul(vr.Minv[6], b2));
+                X.z = xadd(xadd(xmul(vr.Minv[8], b0), xmul(vr.Minv[9], b1)), xmul(vr.Minv[10], b2));
+                X.w = 1.0f;
+                if (warp == 0) {                                                           // setGridsImages (patch_manager.cpp:223-239)
+                    int nv0 = 0;
+                    for (int base = 0; base < snv; base += 32) {
+                        const int i = base + lane;
+                        bool keep = false;
+                        int v = 0;
+                        if (i < snv) {
+                            v = st.images[(size_t)src * st.maxv + i];
+                            const V3 q = project(p.views[v].P, X);
+                            const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
+                            keep = 0 <= ix && ix < p.views[v].gw && 0 <= iy && iy < p.views[v].gh;
+                        }
+                        const unsigned msk = __ballot_sync(0xffffffffu, keep);
+                        if (keep) ws.images[nv0 + __popc(msk & ((1u << lane) - 1u))] = v;
+                        nv0 += __popc(msk);
+                    }
+                    if (lane == 0) cs.bi[0] = nv0;
+                }
+                __syncthreads();
+                int nv = cs.bi[0];
+                __syncthreads();
+                if (nv > 0) {
+                    float ncc = cta_compute_ncc<WS>(p, ws, cs, tex, X, N, nv);
+                    PMK_PHASE(0)
+                    if (np >= maxp && ncc < wncc) outcome = TRY_LOSE;
+                    else {
+                        // ---- patch optimisation (propagate.cpp:176-193) ----
+                        float dscale, ascale;
+                        const int pre = cta_pre_process<WS>(cp, ws, cs, tex, X, N, nv, dscale, ascale);
+                        PMK_PHASE(1)
+                        if (pre == -1) outcome = TRY_FAIL0;
+                        else {
+                            if (sa.phase_ns != nullptr && tid == 0) atomicAdd(sa.phase_ns + 7, 1ull);
+                            ncc = cta_refine<WS>(cp, ws, cs, tex, X, N, nv, dscale, stream);
+                            PMK_PHASE(2)
+                            const int r = cta_post_process<WS>(cp, ws, cs, tex, X, N, nv, wslot);
+                            PMK_PHASE(3)
+                            outcome = r == 0 ? TRY_ACCEPT : TRY_FAIL1;
+                            cd.X = X; cd.N = N; cd.nv = nv; cd.ncc = ncc; cd.dscale = dscale; cd.ascale = ascale;
+                            if (r == 0) {
+                                bool outside = false;
+                                for (int i = tid; i < nv; i += CELL_WARPS * 32) {                  // setGrids (optim.cpp:285)
+                                    const V3 q = project(p.views[ws.images[i]].P, X);
+                                    const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
+                                    outside |= ix < 0 || p.views[ws.images[i]].gw <= ix || iy < 0 || p.views[ws.images[i]].gh <= iy;
+                                    ss.cells[i] = pack_cell(ix, iy);
+                                }
+                                // Views inherited from the source patch are not re-checked by addImages, and the refinement moves
+                                // the patch: a view can end up seeing it outside its grid.  The reference then writes m_pgrids out of
+                                // bounds (addPatch, patch_manager.cpp:164-170); here the candidate is rejected like any postProcess failure.
+                                if (__syncthreads_or(outside ? 1 : 0)) outcome = TRY_FAIL1;
+                            }
+                        }
+                    }
+                }
+            }
+            // ---------------- postProcess's store-reading tail: setVImagesVGrids, check (optim.cpp:288-296) ----------------
+            if (outcome == TRY_ACCEPT) {
+                cd.tmp = xmul(max_std(0.0f, xsub(cd.ncc, p.ncc_threshold)), (float)cd.nv);      // m_tmp = score2
+                cd.nvv = 0;
+                if (p.depth) {
+                    if (warp == 0) {
+                        const int nvv = warp_set_vimages(sp, ws, cd.X, cd.N, ws.images, cd.nv, ss.vimg, ss.vcell, 0, lane);
+                        if (lane == 0) cs.bi[0] = nvv;
+                    }
+                    __syncthreads();
+                    cd.nvv = cs.bi[0];
+                    __syncthreads();
+                }
+                if (2 <= p.depth) {                                                    // Optim::check (optim.cpp:300-323)
+                    PGeo me; me.X = cd.X; me.N = cd.N; me.dscale = cd.dscale; me.ref = ws.images[0];
+                    const PatchLists pl{ws.images, ss.cells, cd.nv, ss.vimg, ss.vcell, cd.nvv};
+                    const Overlay ov{cD, cs.l_id, min(cs.nl, LKEEP), cs.removed, cs.nrem};
+                    const float gain = cta_compute_gain(sp, cs, me, cd.ncc, pl, ov);
+                    cd.tmp = gain;
+                    if (gain < 0.0f) outcome = TRY_FAIL1;
+                    else {
+                        int* nb = sp.nb_scratch + (size_t)wslot * NB_STRIDE;
+                        const int nn = cta_find_neighbors(sp, cs, me, pl, 4.0f, 2, ov, nb);
+                        if (6 < nn) {
+                            if (warp == 0) { const int rej = quad_out_of_line(sp, me, pl, nb, nn, lane); if (lane == 0) cs.bi[0] = rej; }
+                            __syncthreads();
+                            if (cs.bi[0]) outcome = TRY_FAIL1;
+                            __syncthreads();
+                        }
+                    }
+                }
+                PMK_PHASE(4)
+            }
+            // ================= commit =================
+            PMK_STAT(SS_CALLS, (k == 0) ? 1 : 0);
+            PMK_STAT(SS_TRIES, 1);
+            if (outcome != TRY_GEN_NULL) PMK_STAT(SS_EVALS, 1);
+            if (outcome == TRY_FAIL1 || outcome == TRY_ACCEPT) PMK_STAT(SS_EVALS, PMR1_EVALS + 1);
+            if (outcome == TRY_GEN_NULL) PMK_STAT(SS_GEN_NULL, 1);
+            else if (outcome == TRY_LOSE) PMK_STAT(SS_NCC_LOSE, 1);
+            else if (outcome == TRY_FAIL0) PMK_STAT(SS_FAIL0, 1);
+            else if (outcome == TRY_FAIL1) PMK_STAT(SS_FAIL1, 1);
+            else if (warp == 0) {
+                // ---- removePatch(worst) / addPatch(new) (propagate.cpp:195-207); grid updates are staged ----
+                int nl = cs.nl;
+                if (nl == maxp) {
+                    const int w = cs.l_id[maxp - 1];
+                    if (w >= st.cap) { if (lane == 0) st.state[w] = 0; }                       // staged this step: never reaches the grids
+                    else if (lane == 0) { cs.removed[cs.nrem] = w; cs.nrem = cs.nrem + 1; }
+                    --nl;
+                    if (lane == 0) cs.stat[SS_REPLACED] += 1;
+                } else if (lane == 0) cs.stat[SS_ADDED] += 1;
+                __syncwarp();
+                const int sid = st.cap + task * NEW_MAX + cs.nnew;
+                __syncwarp();
+                if (lane == 0) {
+                    cs.nnew = cs.nnew + 1;
+                    st.coord[sid] = v4f(cd.X); st.normal[sid] = v4f(cd.N);
+                    st.scal[sid] = make_float4(cd.ncc, cd.dscale, cd.ascale, cd.tmp);
+                    st.nimg[sid] = cd.nv; st.nvimg[sid] = cd.nvv; st.state[sid] = 1;
+                    st.birth[sid] = 0xffffffffu;
+                }
+                bool inD = false;
+                for (int i = lane; i < cd.nv; i += 32) {
+                    st.images[(size_t)sid * st.maxv + i] = ws.images[i];
+                    st.cells[(size_t)sid * st.maxv + i] = ss.cells[i];
+                    if (ws.images[i] == img && cell_x(ss.cells[i]) == x && cell_y(ss.cells[i]) == y) inD = true;
+                }
+                for (int i = lane; i < cd.nvv; i += 32) {
+                    st.vimages[(size_t)sid * st.maxv + i] = ss.vimg[i];
+                    st.vcells[(size_t)sid * st.maxv + i] = ss.vcell[i];
+                }
+                inD = __any_sync(0xffffffffu, inD);
+                if (lane == 0) {
+                    if (inD) { cs.l_id[nl] = sid; cs.l_ncc[nl] = cd.ncc; ++nl; swap_sort_desc(cs.l_id, cs.l_ncc, nl); }
+                    cs.nl = nl;
+                }
+            }
+            PMK_PHASE(5)
+            __syncthreads();
+        }
+        // ---- hand the step's mutations to k4_apply ----
+        if (warp == 0) {
+            const int nrem = cs.nrem;
+            if (lane == 0) sa.task_new[task] = cs.nnew;
+            if (nrem > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(st.counters + SC_REM, nrem);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int i = lane; i < nrem; i += 32) sa.rem_list[base + i] = cs.removed[i];
+            }
+            if (lane == 0) {
+                unsigned long long t_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+                atomicAdd(sa.stats + SS_CELL_NS, t_end - cs.t_begin);
+                atomicMax(sa.step_max, t_end - cs.t_begin);
+                if (sa.cell_ns) sa.cell_ns[cD] = (float)(t_end - cs.t_begin);
+            }
+        }
+        __syncthreads();
+    }
+#undef PMK_PHASE
+#undef PMK_STAT
+    if (tid < SS_COUNT && cs.stat[tid]) atomicAdd(sa.stats + tid, (unsigned long long)cs.stat[tid]);
+}
+
+}  // namespace pmk

@@ -11,7 +11,7 @@
 //                                            breadth-first labelling in m_ppatches order (host, order-dependent in the reference)
 #pragma once
 
-#include "pmk_sweep.cuh"
+#include "pmk_cell.cuh"
 
 namespace pmk {
 

@@ -155,6 +155,7 @@ int store_init(pmk_ctx* ctx) {
     }
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, SC_COUNT * sizeof(int), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(d.ccount, 0, (size_t)d.total_cells * sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d.cslots, 0xff, (size_t)d.total_cells * d.cell_cap * sizeof(int), ctx->stream));   // SLOT_FREE everywhere, once
     CUDA_TRY(cudaMemsetAsync(d.dmap, 0xff, (size_t)d.total_cells * sizeof(unsigned long long), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(d.state, 0, tot * sizeof(int), ctx->stream));
     s->n = 0;
@@ -248,8 +249,8 @@ int store_rebuild(pmk_ctx* ctx, int additive) {
     }
     s->n = nalive;
     CUDA_TRY(cudaMemcpyAsync(d.counters + SC_N, &s->n, sizeof(int), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(d.ccount, 0, (size_t)d.total_cells * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(d.dmap, 0xff, (size_t)d.total_cells * sizeof(unsigned long long), st));
+    k_reset_cells<<<(d.total_cells + 255) / 256, 256, 0, st>>>(d);
+    ctx->launches++;
     if (nalive > 0) {
         const int blocks = std::min(ctx->sm_count * 8, (nalive + 3) / 4);
         k5_register<<<blocks, 128, 0, st>>>(sp, nalive, 0, 0, 0);
@@ -407,7 +408,28 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + cpc - 1) / cpc));
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(s->step_max, 0, sizeof(unsigned long long), st));
-    if (sa.ntasks > 0) {
+    static const int use_v1 = getenv("PMK_SWEEP_V1") ? 1 : 0;      // A/B switch while the CTA-per-cell kernel is being validated
+    if (sa.ntasks > 0 && !use_v1) {
+        // one CTA per dest cell, handed out longest-first through SC_NEXT (pmk_cell.cuh)
+        SweepArgs a = sa;
+        a.heavy_slot = s->max_tasks;
+        a.wslot_base = 0;
+        a.range_sel = 0;
+        k4_plan<<<1, 1024, 0, st>>>(sp, a, s->order);
+        CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_NEXT, 0, sizeof(int), st));
+        typedef CellGeom<WS> Gm;
+        const size_t csmem = ((sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellCta) + 15) & ~(size_t)15) +
+                             (size_t)Gm::nslots(ctx->params.tau) * Gm::SLOT * sizeof(float);
+        static int per_sm = 0;
+        if (!per_sm) {
+            CUDA_TRY(cudaFuncSetAttribute(k4_cells<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cells<WS>, CELL_WARPS * 32, csmem));
+            if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k4_cells does not fit on an SM");
+        }
+        const int cgrid = std::max(1, std::min(sa.ntasks, std::min(ctx->sm_count * per_sm, ctx->cand_grid * CAND_WARPS)));
+        k4_cells<WS><<<cgrid, CELL_WARPS * 32, csmem, st>>>(sp, a);
+        ctx->launches += 2;
+    } else if (sa.ntasks > 0) {
         SweepArgs a = sa;
         a.heavy_slot = s->max_tasks;
         a.wslot_base = 0;

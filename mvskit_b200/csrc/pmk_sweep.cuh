@@ -825,6 +825,23 @@ __global__ void k4_apply_remove(const StoreParams sp, const int* __restrict__ re
     }
 }
 
+// Slots that were never written hold SLOT_FREE, which no scan takes for an erased slot: an appender reserves slot s with
+// atomicAdd(ccount) and stores it afterwards, and a concurrent insert into the same cell already sees s < ccount -- a stale
+// SLOT_TOMB left there by an earlier epoch would be claimed by its CAS and then overwritten by the appender's store (one
+// registration lost, silently).  k_reset_cells restores SLOT_FREE wherever ccount is zeroed.
+constexpr int SLOT_FREE = -1;          // 0xffffffff: reads as an erased m_vpgrids entry, so readers skip it too
+
+// PatchManager::init's empty grids (patch_manager.cpp:38-51): every used slot back to SLOT_FREE, count 0, depth map = m_MAXDEPTH
+__global__ void k_reset_cells(const StoreDev st) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= st.total_cells) return;
+    const int n = min(st.ccount[c], st.cell_cap);
+    int* slots = st.cslots + (size_t)c * st.cell_cap;
+    for (int s = 0; s < n; ++s) slots[s] = SLOT_FREE;
+    st.ccount[c] = 0;
+    st.dmap[c] = ~0ull;
+}
+
 // register `entry` in cell c: reuse an erased slot, else append
 __device__ __forceinline__ void insert_into_cell(const StoreDev& st, int c, int entry) {
     int* slots = st.cslots + (size_t)c * st.cell_cap;

@@ -65,6 +65,31 @@ class PatchBatch:
                        _p(self.vimages), _p(self.nvimages), _p(self.vgrids), self.maxv)
 
 
+class TraceIO(C.Structure):
+    _fields_ = [("cap", C.c_int), ("code", C.c_void_p), ("ncc0", C.c_void_p), ("post_ret", C.c_void_p), ("decision", C.c_void_p),
+                ("branch_full", C.c_void_p), ("mid", PatchIO), ("fin", PatchIO)]
+
+
+class Trace:
+    """Per-try record of pmref_trace_dest (oracle/ref_harness.cpp): code 0 generatePatch NULL / 1 lost to the worst patch /
+    2 preProcess == -1 / 3 refined; mid = the patch as refinePatch left it, fin = as postProcess left it; decision 0 / 1 added /
+    2 replaced the worst."""
+
+    def __init__(self, cap: int, maxv: int):
+        self.cap = cap
+        self.code = np.zeros(cap, np.int32)
+        self.ncc0 = np.zeros(cap, np.float32)
+        self.post_ret = np.zeros(cap, np.int32)
+        self.decision = np.zeros(cap, np.int32)
+        self.branch_full = np.zeros(cap, np.int32)
+        self.mid = PatchBatch(cap, maxv)
+        self.fin = PatchBatch(cap, maxv)
+        self.n = 0
+
+    def io(self) -> TraceIO:
+        return TraceIO(self.cap, _p(self.code), _p(self.ncc0), _p(self.post_ret), _p(self.decision), _p(self.branch_full), self.mid.io(), self.fin.io())
+
+
 class RefLib:
     """The compiled reference.  One scene per process (the reference keeps a static Optim::m_inst)."""
 
@@ -301,6 +326,14 @@ class RefLib:
     # -- schedule PMS1 through the reference's propagatePatch; Filter::run stage by stage -----------------
     def propagate_dest(self, image: int, x: int, y: int, inc: int, it: int) -> int:
         return int(self.L.pmref_propagate_dest(image, x, y, inc, it))
+
+    def trace_dest(self, image: int, x: int, y: int, inc: int, it: int, cap: int = 64) -> Trace:
+        """propagate_dest with every try recorded (teacher forcing); the store ends up exactly as after propagate_dest."""
+        tr = Trace(cap, self.nviews)
+        io = tr.io()
+        tr.n = int(self.L.pmref_trace_dest(image, x, y, inc, it, C.byref(io)))
+        assert tr.n <= cap, (tr.n, cap)
+        return tr
 
     def propagate_diag(self, image: int, diag: int, inc: int, it: int) -> int:
         return int(self.L.pmref_propagate_diag(image, diag, inc, it))

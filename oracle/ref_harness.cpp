@@ -22,6 +22,7 @@
 #include <memory>
 #include <numeric>
 #include <queue>
+#include <random>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -514,6 +515,93 @@ int pmref_propagate_dest(int image, int x, int y, int inc, int iter) {
         g_pm->m_propagate.propagatePatch(sources[call], image, index);
     }
     return (int)sources.size();
+}
+
+// ---- teacher forcing: Propagate::propagatePatch replayed with every intermediate recorded ---------------------------------------
+// pmref_trace_dest does for one dest cell what pmref_propagate_dest does, but instead of calling the reference's propagatePatch
+// it walks that function's control flow (propagate.cpp:126-218) through the reference's OWN member functions -- sortPatches,
+// removePatch, generatePatch, preProcess, refinePatch, postProcess, addPatch -- and records, per try: where the try ended, the
+// candidate's m_ncc out of generatePatch, the patch as refinePatch left it (the "hypothesis" a teacher-forced device run starts
+// from), postProcess' return value and the patch as postProcess left it, and what happened to the cell.
+// tests/test_trace_cpu.py pins this walk to the real propagatePatch: both leave bit-identical stores from the same state.
+//   code:     0 generatePatch returned NULL, 1 lost against the worst patch's m_ncc, 2 preProcess == -1, 3 refined
+//   decision: 0 nothing stored, 1 added into free room, 2 replaced the worst patch
+struct TraceIO {
+    int cap;
+    int* code; float* ncc0; int* post_ret; int* decision; int* branch_full;
+    PatchIO mid;         // after refinePatch (m_images as preProcess left them, m_ncc / m_dscale / m_ascale in scal4)
+    PatchIO fin;         // after postProcess (lists, grids, visible lists, m_tmp)
+};
+
+int pmref_trace_dest(int image, int x, int y, int inc, int iter, TraceIO* io) {
+    PatchManager& pm = g_pm->m_patchManager;
+    Propagate& pr = g_pm->m_propagate;
+    const int gw = pm.m_gwidths[image], gh = pm.m_gheights[image];
+    const int maxp = pr.MAX_NUM_OF_PATCHES;
+    const int index = y * gw + x;
+    {
+        std::vector<Ppatch> cur = pm.m_pgrids[image][index];
+        pm.sortPatches(cur, 0);
+        for (int i = (int)cur.size() - 1; i >= maxp; --i) pm.removePatch(cur[i]);
+    }
+    std::vector<Ppatch> sources;
+    for (int side = 0; side < 2; ++side) {
+        const int sx = side == 0 ? x : x - inc, sy = side == 0 ? y - inc : y;
+        if (sx < 0 || gw <= sx || sy < 0 || gh <= sy) continue;
+        std::vector<Ppatch> src = pm.m_pgrids[image][sy * gw + sx];
+        pm.sortPatches(src, 0);
+        if ((int)src.size() > maxp) src.resize(maxp);
+        for (size_t n = 0; n < src.size(); ++n) if (src[n]->m_images[0] == image) sources.push_back(src[n]);
+    }
+    int ntry = 0;
+    for (size_t call = 0; call < sources.size(); ++call) {
+        pmr1::state().stream = ((unsigned long long)(unsigned)iter << 56) ^ ((unsigned long long)(unsigned)image << 40) ^
+                               ((unsigned long long)(unsigned)index << 8) ^ (unsigned long long)call;
+        const Ppatch& ppatch = sources[call];
+        // ---- propagate.cpp:126-136 ----
+        std::vector<Ppatch>& ppatches = pm.m_pgrids[image][index];
+        pm.sortPatches(ppatches, 0);
+        int npatches = (int)ppatches.size();
+        if (npatches > maxp) { for (int i = npatches - 1; i >= maxp; --i) pm.removePatch(ppatches[i]); }
+        // ---- :138-150 ----
+        std::default_random_engine generator;
+        std::uniform_real_distribution<float> distribution(-0.5, 0.5);
+        const int cx = index % gw, cy = index / gw;
+        Vector3f icoord;
+        icoord << (g_pm->m_csize * (2 * cx + 1) - 1) / 2.0f, (g_pm->m_csize * (2 * cy + 1) - 1) / 2.0f, 1.0f;
+        for (int it = 0; it < pr.MAX_NUM_OF_PROPAG; ++it, ++ntry) {                          // :153
+            const bool rec = ntry < io->cap;
+            if (rec) { io->code[ntry] = 0; io->ncc0[ntry] = 0.0f; io->post_ret[ntry] = -2; io->decision[ntry] = 0; }
+            npatches = (int)ppatches.size();
+            if (rec) io->branch_full[ntry] = npatches < maxp ? 0 : 1;
+            Ppatch newppatch;
+            if (npatches < maxp) {                                                           // :156-165
+                Vector3f d;
+                d << distribution(generator) * g_pm->m_csize, distribution(generator) * g_pm->m_csize, 0.0f;
+                const Vector3f nic = icoord + d;
+                newppatch = pr.generatePatch(ppatch, nic);
+                if (!newppatch) continue;
+                if (rec) io->ncc0[ntry] = newppatch->m_ncc;
+            } else {                                                                          // :166-173
+                pm.sortPatches(ppatches, 0);
+                const Vector3f ic = g_pm->m_photoSet.project(image, ppatches[maxp - 1]->m_coord, g_pm->m_level);
+                newppatch = pr.generatePatch(ppatch, ic);
+                if (newppatch && rec) io->ncc0[ntry] = newppatch->m_ncc;
+                if (!newppatch) continue;
+                if (newppatch->m_ncc < ppatches[maxp - 1]->m_ncc) { if (rec) io->code[ntry] = 1; continue; }
+            }
+            if (g_pm->m_optim.preProcess(*newppatch) == -1) { if (rec) io->code[ntry] = 2; continue; }   // :183-187
+            g_pm->m_optim.refinePatch(*newppatch, 100);                                                  // :190
+            if (rec) { io->code[ntry] = 3; patch_out(*newppatch, io->mid, ntry); }
+            const int pr_ret = g_pm->m_optim.postProcess(*newppatch);                                     // :193
+            if (rec) { io->post_ret[ntry] = pr_ret; patch_out(*newppatch, io->fin, ntry); }
+            if (pr_ret == -1) continue;
+            if (npatches == maxp) { pm.removePatch(ppatches[maxp - 1]); if (rec) io->decision[ntry] = 2; }   // :199-202
+            else if (rec) io->decision[ntry] = 1;
+            pm.addPatch(newppatch);                                                                       // :209
+        }
+    }
+    return ntry;
 }
 
 // one wavefront step: every dest cell of anti-diagonal `diag` of `image`

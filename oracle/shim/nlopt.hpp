@@ -7,7 +7,7 @@
 // north_star the refinement is re-defined as a seeded, counter-based random search over the
 // same three encoded variables, with the same bounds and the same objective (Optim::cost_func,
 // which IS reference source and is pinned by the oracle).  This shim is the CPU definition of
-// that schedule ("PMR1"); mvskit_b200/csrc/pmk_refine.cuh is the CUDA one.
+// that schedule ("PMR1"); warp_refine / k3_refine in mvskit_b200/csrc/pmk_cand.cuh is the CUDA one.
 //
 // PMR1 (batch-synchronous halving random search):
 //   best = clamp(x0); fbest = f(best)

@@ -120,6 +120,51 @@ def test_sweep_wavefront_steps_match_reference_propagate_patch(ctx, reflib, smal
     assert matched >= 0.95 * tot_new_gpu and close >= 0.95 * matched, (matched, close, tot_new_gpu)
 
 
+def _recount(g, nviews, dims):
+    """m_pgrids / m_vpgrids sizes recomputed from the patches' own lists (what cslots must hold)."""
+    pg = [np.zeros((gh, gw), np.int64) for gw, gh in dims]
+    vg = [np.zeros((gh, gw), np.int64) for gw, gh in dims]
+    for i in range(g.n):
+        for k in range(g.nimages[i]):
+            x, y = g.grids[i, k]
+            pg[g.images[i, k]][y, x] += 1
+        for k in range(g.nvimages[i]):
+            x, y = g.vgrids[i, k]
+            vg[g.vimages[i, k]][y, x] += 1
+    return pg, vg
+
+
+def test_cell_slots_hold_exactly_the_registrations_of_the_patch_lists(ctx, reflib):
+    """Round-1 advisor finding: a stale erased-slot marker from an earlier epoch could swallow a concurrent registration
+    (insert_into_cell).  Epochs are cycled here -- sweep, rebuild, sweep, clear, reload, sweep -- and after each one the
+    registrations recounted from the patch lists must equal the live slots of every cell of every view."""
+    pb = _ref_seeds(reflib)
+    dims = [ctx.grid_dims(v) for v in range(reflib.nviews)]
+
+    def check(tag):
+        g = ctx.store_get()
+        pg, vg = _recount(g, reflib.nviews, dims)
+        for v in range(reflib.nviews):
+            assert np.array_equal(ctx.store_cell_counts(v, 0), pg[v]), (tag, "m_pgrids", v)
+            assert np.array_equal(ctx.store_cell_counts(v, 1), vg[v]), (tag, "m_vpgrids", v)
+        return g.n
+
+    _load(ctx, pb, 1)
+    gw, gh = dims[0]
+    ctx.propagate_diagonals(0, 0, 0, gw + gh - 1, SEED)
+    n1 = check("sweep of view 0")
+    assert n1 > pb.n
+    ctx.filter_rebuild(0)
+    check("rebuild")
+    ctx.propagate_diagonals(1, 1, 0, gw + gh - 1, SEED)
+    check("reverse sweep of view 1 after the rebuild")
+    ctx.filter_rebuild(1)
+    check("additive rebuild")
+    _load(ctx, pb, 1)                                        # store_clear: a new epoch over slots full of old entries
+    ctx.propagate_diagonals(0, 2, 0, gw + gh - 1, SEED)
+    check("sweep of view 2 after store_clear")
+
+
 @pytest.fixture(scope="module")
 def populated(ctx, reflib):
     """A store with a few thousand patches: the CUDA sweep grows it from the seeds (two views, all diagonals), then BOTH

@@ -58,7 +58,9 @@ def main():
     for it in range(a.iters):
         t = time.time(); st = ctx.propagate(it, 0x5EED0001); ctx.sync(); t1 = time.time() - t
         nprop = ctx.store_count()
+        ck_prop = ctx.store_checksum()
         t = time.time(); c = ctx.filter(); ctx.sync(); t2 = time.time() - t
+        print(f"iter {it}: checksum after propagate {ck_prop}, after filter {ctx.store_checksum()}", flush=True)
         ctx.update_threshold()
         g = ctx.store_get()
         q = None
