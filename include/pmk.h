@@ -194,6 +194,25 @@ int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16);
 /* the same for wavefront steps [diag_first, diag_first + diag_count) of one view (parity tests step the sweep) */
 int pmk_propagate_diagonals(pmk_ctx* ctx, int iter, int image, int diag_first, int diag_count, uint64_t seed, uint64_t* stats16);
 
+/* Teacher-forced replay of ONE dest cell (x, y) of `image` (parity tests; BASELINE north_star: "accept/reject decisions given identical
+ * hypotheses").  The sweep kernel runs exactly as in pmk_propagate_diagonals for that cell, except that try t does not generate and
+ * refine its own hypothesis but starts from record t -- the patch as the reference's Optim::refinePatch left it (pmmvps/propagate.cpp:190)
+ * -- and then decides everything that follows on the device: the m_ncc test against the cell's worst patch (:170), Optim::postProcess
+ * (optim.cpp:260-298) with setVImagesVGrids and check, removePatch(worst) / addPatch(new) (:199-209).
+ *   in : code[t] 0 generatePatch NULL / 1 lost to the worst patch / 2 preProcess == -1 / 3 refined; ncc0[t] = m_ncc out of
+ *        generatePatch; for code 3: coord4, normal4, scal4 = {m_ncc, m_dscale, m_ascale, -}, images[t][stride] + nimages[t]
+ *   out: ntries_out = tries the device's own sources give (must equal ntries), outcome[t] 0 NULL / 1 lost / 2 preProcess failed /
+ *        3 postProcess or check failed / 4 stored / 5 diverged (the record says "lost" but the device's worst patch does not beat
+ *        it); branch_full[t]; post_ret[t] = postProcess' store-independent return (0 / -1, -2 = not reached); for post_ret 0 the
+ *        lists as stored: images_out / grids_out (ix, iy pairs) / vimages_out / vgrids_out [t][stride], counts, tmp_out = m_tmp. */
+typedef struct pmk_forced_io {
+    int ntries, stride;
+    const int* code; const float* ncc0; const float* coord4; const float* normal4; const float* scal4; const int* nimages; const int* images;
+    int* ntries_out; int* outcome; int* branch_full; int* post_ret;
+    int* nimages_out; int* images_out; int* grids_out; int* nvimages_out; int* vimages_out; int* vgrids_out; float* tmp_out;
+} pmk_forced_io;
+int pmk_propagate_forced(pmk_ctx* ctx, int iter, int image, int x, int y, const pmk_forced_io* io, uint64_t* stats16);
+
 /* K5 -- PatchManager::collectPatches + Filter::setDepthMapsVGridsVPGridsAddPatchV(additive) (filter.cpp:628-655): patch ids become
  * the reference's m_ppatches indices; depth maps, m_vimages / m_vgrids and m_vpgrids are rebuilt. */
 int pmk_filter_rebuild(pmk_ctx* ctx, int additive, int* n_out);
@@ -241,11 +260,12 @@ int pmk_probe_check(pmk_ctx* ctx, int n, const float* coord4, const float* norma
  * (out may be NULL) switches the recording on; every later call returns and clears the times. */
 int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells);
 
-/* Profiling aid: nanoseconds of warp time the sweeps spent in each phase of a propagatePatch try, summed over all warps since the last
- * call: [0] generatePatch + computeNcc, [1] preProcess, [2] refinePatch, [3] postProcess (store-independent part), [4] its store-reading
- * tail (setVImagesVGrids, check), [5] waiting for the try's turn, [6] tries, [7] tries that reached refinePatch.  The first call (out8 may
- * be NULL) switches the recording on; every later call returns and clears the sums. */
-int pmk_debug_phase_times(pmk_ctx* ctx, uint64_t* out8);
+/* Profiling aid: nanoseconds of CTA time the sweeps spent in each phase of a propagatePatch try, summed over all dest cells since the
+ * last call; out16 holds 16 words: [0] generatePatch + computeNcc, [1] preProcess, [2] refinePatch, [3] postProcess (store-independent
+ * part), [4] its store-reading tail (setVImagesVGrids, check), [5] commit, [6] tries, [7] tries that reached refinePatch, [8..15] the
+ * steps of one cost evaluation inside refinePatch (builds with -DPMK_SUBPHASE only, else 0).  The first call (out16 may be NULL)
+ * switches the recording on; every later call returns and clears the sums. */
+int pmk_debug_phase_times(pmk_ctx* ctx, uint64_t* out16);
 
 /* Stream control / timing helpers for bench.py (no reference counterpart). */
 int pmk_sync(pmk_ctx* ctx);

@@ -1270,6 +1270,73 @@ int pmk_propagate_diagonals(pmk_ctx* ctx, int iter, int image, int diag_first, i
     return store_check_overflow(ctx);
 }
 
+int pmk_propagate_forced(pmk_ctx* ctx, int iter, int image, int x, int y, const pmk_forced_io* io, uint64_t* stats16) {
+    if (!ctx || !io) return fail(PMK_ERR_ARG, "pmk_propagate_forced: null argument");
+    if (image < 0 || image >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_propagate_forced: image out of range");
+    const int T = io->ntries, S = io->stride;
+    if (T < 0 || T > 2 * SRC_MAX || S < ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_propagate_forced: bad ntries / stride (stride must hold every view)");
+    if (!io->code || !io->ncc0 || !io->coord4 || !io->normal4 || !io->scal4 || !io->nimages || !io->images || !io->ntries_out || !io->outcome ||
+        !io->branch_full || !io->post_ret || !io->nimages_out || !io->images_out || !io->grids_out || !io->nvimages_out || !io->vimages_out ||
+        !io->vgrids_out || !io->tmp_out)
+        return fail(PMK_ERR_ARG, "pmk_propagate_forced: null buffer");
+    for (int t = 0; t < T; ++t) {
+        if (io->code[t] < 0 || io->code[t] > 3) return fail(PMK_ERR_ARG, "pmk_propagate_forced: bad code");
+        if (io->code[t] != 3) continue;
+        if (io->nimages[t] < 1 || io->nimages[t] > S) return fail(PMK_ERR_ARG, "pmk_propagate_forced: bad image count");
+        for (int k = 0; k < io->nimages[t]; ++k)
+            if (io->images[(size_t)t * S + k] < 0 || io->images[(size_t)t * S + k] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_propagate_forced: image index out of range");
+    }
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    const ViewConst& vc = ctx->h_views[image];
+    if (x < 0 || x >= vc.gw || y < 0 || y >= vc.gh) return fail(PMK_ERR_ARG, "pmk_propagate_forced: dest cell outside the grid");
+    if (ctx->store->nranks > 1) return fail(PMK_ERR_STATE, "pmk_propagate_forced: single-GPU contexts only");
+    const size_t Tn = (size_t)std::max(T, 1);
+    void *d_code, *d_ncc0, *d_coord, *d_normal, *d_scal, *d_nimg, *d_images, *d_oi, *d_of, *d_ol;
+    // o_i: ntries, outcome[T], full[T], post[T], nimg[T], nvimg[T]; o_l: images, cells, vimages, vcells [T][S] each
+    if ((rc = stage_in(ctx, 0, io->code, Tn * 4, &d_code)) || (rc = stage_in(ctx, 1, io->ncc0, Tn * 4, &d_ncc0)) || (rc = stage_in(ctx, 2, io->coord4, Tn * 16, &d_coord)) ||
+        (rc = stage_in(ctx, 3, io->normal4, Tn * 16, &d_normal)) || (rc = stage_in(ctx, 4, io->scal4, Tn * 16, &d_scal)) || (rc = stage_in(ctx, 5, io->nimages, Tn * 4, &d_nimg)) ||
+        (rc = stage_in(ctx, 6, io->images, Tn * S * 4, &d_images)) || (rc = stage_in(ctx, 7, nullptr, (1 + 5 * Tn) * 4, &d_oi)) || (rc = stage_in(ctx, 8, nullptr, Tn * 4, &d_of)) ||
+        (rc = stage_in(ctx, 9, nullptr, 4 * Tn * S * 4, &d_ol)))
+        return rc;
+    CUDA_TRY(cudaMemsetAsync(d_oi, 0xff, (1 + 5 * Tn) * 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_of, 0, Tn * 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_ol, 0xff, 4 * Tn * S * 4, ctx->stream));
+    ForceIO f;
+    f.ntries = T; f.stride = S;
+    f.code = (const int*)d_code; f.ncc0 = (const float*)d_ncc0; f.coord = (const float4*)d_coord; f.normal = (const float4*)d_normal; f.scal = (const float4*)d_scal;
+    f.nimg = (const int*)d_nimg; f.images = (const int*)d_images;
+    int* oi = (int*)d_oi;
+    f.o_ntries = oi; f.o_outcome = oi + 1; f.o_full = oi + 1 + Tn; f.o_post = oi + 1 + 2 * Tn; f.o_nimg = oi + 1 + 3 * Tn; f.o_nvimg = oi + 1 + 4 * Tn;
+    f.o_tmp = (float*)d_of;
+    int* ol = (int*)d_ol;
+    f.o_images = ol; f.o_cells = ol + Tn * S; f.o_vimages = ol + 2 * Tn * S; f.o_vcells = ol + 3 * Tn * S;
+    CUDA_TRY(cudaMemsetAsync(ctx->store->stats, 0, SS_COUNT * sizeof(uint64_t), ctx->stream));
+    const int inc = (iter % 2 == 1) ? -1 : 1, ndiag = vc.gw + vc.gh - 1, d = x + y;
+    const int step = inc > 0 ? d : ndiag - 1 - d;
+    if ((rc = sweep_views(ctx, iter, image, 1, step, 1, 0, x, &f))) return rc;
+    std::vector<int> hi(1 + 5 * Tn), hl(4 * Tn * S);
+    CUDA_TRY(cudaMemcpyAsync(hi.data(), d_oi, hi.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hl.data(), d_ol, hl.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(io->tmp_out, d_of, Tn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *io->ntries_out = hi[0];
+    for (int t = 0; t < T; ++t) {
+        io->outcome[t] = hi[1 + t]; io->branch_full[t] = hi[1 + Tn + t]; io->post_ret[t] = hi[1 + 2 * Tn + t];
+        io->nimages_out[t] = std::max(0, hi[1 + 3 * Tn + t]); io->nvimages_out[t] = std::max(0, hi[1 + 4 * Tn + t]);
+        for (int k = 0; k < S; ++k) {
+            const size_t o = (size_t)t * S + k;
+            io->images_out[o] = hl[o]; io->vimages_out[o] = hl[2 * Tn * S + o];
+            const int c = hl[Tn * S + o], vcell = hl[3 * Tn * S + o];
+            io->grids_out[2 * o] = c == -1 ? -1 : (c & 0xffff); io->grids_out[2 * o + 1] = c == -1 ? -1 : (int)((unsigned)c >> 16);
+            io->vgrids_out[2 * o] = vcell == -1 ? -1 : (vcell & 0xffff); io->vgrids_out[2 * o + 1] = vcell == -1 ? -1 : (int)((unsigned)vcell >> 16);
+        }
+    }
+    if ((rc = read_stats(ctx, stats16))) return rc;
+    return store_check_overflow(ctx);
+}
+
 int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16) {
     if (!ctx) return fail(PMK_ERR_ARG, "pmk_propagate: null ctx");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
@@ -1463,20 +1530,20 @@ int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells) {
     return PMK_OK;
 }
 
-int pmk_debug_phase_times(pmk_ctx* ctx, uint64_t* out8) {
+int pmk_debug_phase_times(pmk_ctx* ctx, uint64_t* out8) {       // out8: 16 words (8 try phases, 8 sub-phases of PMK_SUBPHASE builds)
     if (!ctx) return fail(PMK_ERR_ARG, "pmk_debug_phase_times: null ctx");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     int rc = store_init(ctx);
     if (rc) return rc;
     pmk_store* s = ctx->store;
     if (!s->phase_ns) {
-        if ((rc = dalloc(ctx, &s->phase_ns, 8))) return rc;
-        CUDA_TRY(cudaMemsetAsync(s->phase_ns, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        if ((rc = dalloc(ctx, &s->phase_ns, 16))) return rc;
+        CUDA_TRY(cudaMemsetAsync(s->phase_ns, 0, 16 * sizeof(unsigned long long), ctx->stream));
     }
     if (out8) {
-        CUDA_TRY(cudaMemcpyAsync(out8, s->phase_ns, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(out8, s->phase_ns, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(s->phase_ns, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(s->phase_ns, 0, 16 * sizeof(unsigned long long), ctx->stream));
     }
     return PMK_OK;
 }

@@ -21,23 +21,30 @@
 
 namespace pmk {
 
-#ifndef PMK_CELL_WARPS
-#define PMK_CELL_WARPS 8
-#endif
 #ifndef PMK_CELL_MINB
 #define PMK_CELL_MINB 3
 #endif
-constexpr int CELL_WARPS = PMK_CELL_WARPS;
 constexpr int EVAL_SLOTS = PMR1_CANDS * PMK_MAX_TAU;      // (candidate, view) items of one PMR1 level
+constexpr int FRAME_SLOTS = EVAL_SLOTS > CAND_MAXV ? EVAL_SLOTS : CAND_MAXV;
 
-template <int WS>
+template <int WS, int NW>
 struct CellGeom {
     static constexpr int GW = WS <= 8 ? 8 : 16;              // lanes of an evaluator group
     static constexpr int G = 32 / GW;                         // groups per warp
-    static constexpr int TG = CELL_WARPS * G;                 // groups per CTA
+    static constexpr int TG = NW * G;                         // groups per CTA
+    static constexpr int NT = NW * 32;                        // threads per CTA
     static constexpr int SLOT = WS * 3 * GW;                  // floats of one texture slot: [row][channel][column]
     __host__ __device__ static constexpr int nslots(int tau) { return (PMR1_CANDS * tau > TG + 1) ? PMR1_CANDS * tau : TG + 1; }
 };
+
+#ifdef PMK_SUBPHASE
+#define PMK_SUBT(slot) do { if (threadIdx.x == 0) { unsigned long long n_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n_)); if ((slot) >= 0) cs.sub[slot] += n_ - cs.sub_t; cs.sub_t = n_; } } while (0)
+#else
+#define PMK_SUBT(slot) do { } while (0)
+#endif
+
+struct CandGeo { V4 X, N, px, py; };                     // a candidate's decoded point and its patch axes (Optim::getPAxes)
+struct ItemFrame { float tlx, tly, dxx, dxy, dyx, dyy; int level, view; };    // what Optim::getTex decides before it samples
 
 struct CellCta {                       // one per CTA, shared memory
     int l_id[LKEEP];                   // the dest cell's m_pgrids list, sorted (sortPatches)
@@ -48,9 +55,13 @@ struct CellCta {                       // one per CTA, shared memory
     int nl, nrem, nnew, nsrc;
     int bi[8];                         // small broadcasts from warp 0
     float bf[8];
-    int lvl[EVAL_SLOTS + 4];           // per texture slot: pyramid level sampled, or -1 (getTex == -1)
-    float inv[EVAL_SLOTS + 4];         //                   1 / msd of Optim::normalize
-    float val[EVAL_SLOTS + 4];         //                   robustincc(1 - dot(reference, view))
+    RefineCtx rc;                      // Optim::m_center / m_ray / m_dscale of the refinement in flight
+    CandGeo cg[PMR1_CANDS];
+    ItemFrame fr[FRAME_SLOTS];         // per item: the sampling frame (level < 0: getTex == -1)
+    float inv[FRAME_SLOTS];            //           1 / msd of Optim::normalize
+    float val[EVAL_SLOTS];             //           robustincc(1 - dot(reference, view))
+    int wl[FRAME_SLOTS];               // setINCCs: work list of views whose frame is valid
+    int nwl;
     float mp[2 * CAND_MAXV];           // computeGain: per registration, the strongest non-neighbour of its cell
     int negs[32];                      // preamble: list entries whose m_ncc has to be recomputed
     int nneg;
@@ -59,32 +70,29 @@ struct CellCta {                       // one per CTA, shared memory
     int task;
     unsigned int stat[SS_COUNT];
     unsigned long long t_begin, ph_t;
+    unsigned long long sub_t, sub[8];  // PMK_SUBPHASE builds: time between the barriers of cta_costs (profiling)
 };
 
-// ---- one texture grab by one evaluator group, into a shared-memory slot -------------------------------------------------------
-// Optim::getTex + Optim::normalize for (X, N, px, py) in `view` (optim.cpp:790-844, 917-940).  Arithmetic identical to
-// group_grab (pmk_cand.cuh); the centred, masked lattice column of each lane goes to slot[(row * 3 + channel) * GW + col].
-// Returns the pyramid level or -1 (then nothing is sampled or written); *inv_msd = 1 / sqrt(ssd / (3 n)) (1 when ssd == 0).
+// ---- the sampling half of a texture grab, by one evaluator group, into a shared-memory slot -------------------------------------
+// Optim::getTex's 49 samples + Optim::normalize (optim.cpp:835-842, 917-940) for a frame make_frame accepted.  Arithmetic identical
+// to group_grab (pmk_cand.cuh); the centred, masked lattice column of each lane goes to slot[(row * 3 + channel) * GW + col].
+// Returns 1 / sqrt(ssd / (3 n)) (1 when ssd == 0).
 template <int WS, int GW>
-__device__ __noinline__ int grab_slot(const Params& p, int view, V4 X, V4 N, V4 px, V4 py, int col, unsigned gm, float* __restrict__ slot,
-                                      float* __restrict__ inv_msd) {
+__device__ __noinline__ float sample_slot(const Params& p, const ItemFrame& f, int col, unsigned gm, float* __restrict__ slot) {
     constexpr int NSAMP = WS * WS;
     constexpr float INV_NSAMP = 1.0f / (float)NSAMP, INV_3NSAMP = 1.0f / (float)(3 * NSAMP);
-    if (view < 0 || view >= p.nviews) return -1;
-    const ViewConst& vc = p.views[view];
-    const Frame f = make_frame(p, vc, X, N, px, py);
-    const int level = f.level;
-    if (level < 0) return -1;
+    const ViewConst& vc = p.views[f.view];
     const float cmask = col < WS ? 1.0f : 0.0f;
-    const Texel* img = vc.img[level];
-    const int W = vc.w[level];
+    const Texel* img = vc.img[f.level];
+    const int W = vc.w[f.level];
     const float fcol = (float)(col < WS ? col : WS - 1);
+    const float dyx = f.dyx, dyy = f.dyy;
     const float bx = fmaf(f.dxx, fcol, f.tlx), by = fmaf(f.dxy, fcol, f.tly);
     float t[WS][3];
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int y = 0; y < WS; ++y) {
-        bilinear(img, W, fmaf(f.dyx, (float)y, bx), fmaf(f.dyy, (float)y, by), t[y][0], t[y][1], t[y][2]);
+        bilinear(img, W, fmaf(dyx, (float)y, bx), fmaf(dyy, (float)y, by), t[y][0], t[y][1], t[y][2]);
         s0 = fmaf(t[y][0], cmask, s0); s1 = fmaf(t[y][1], cmask, s1); s2 = fmaf(t[y][2], cmask, s2);
     }
     const float m0 = -group_sum<GW>(s0, gm) * INV_NSAMP * cmask, m1 = -group_sum<GW>(s1, gm) * INV_NSAMP * cmask, m2 = -group_sum<GW>(s2, gm) * INV_NSAMP * cmask;
@@ -96,8 +104,20 @@ __device__ __noinline__ int grab_slot(const Params& p, int view, V4 X, V4 N, V4 
         slot[(y * 3 + 0) * GW + col] = t[y][0]; slot[(y * 3 + 1) * GW + col] = t[y][1]; slot[(y * 3 + 2) * GW + col] = t[y][2];
     }
     const float var = group_sum<GW>(ssd, gm) * INV_3NSAMP;
-    *inv_msd = var > 0.0f ? rsqrtf(var) : 1.0f;
-    return level;
+    return var > 0.0f ? rsqrtf(var) : 1.0f;
+}
+
+// the deciding half (optim.cpp:790-833 + getTexSafe :895-915), by ONE thread per (candidate, view) item
+__device__ __noinline__ void frame_item(const Params& p, int view, const CandGeo& cg, ItemFrame* out) {
+    ItemFrame fr;
+    fr.level = -1; fr.view = 0;
+    fr.tlx = fr.tly = fr.dxx = fr.dxy = fr.dyx = fr.dyy = 0.0f;
+    if (view >= 0 && view < p.nviews) {
+        const Frame f = make_frame(p, p.views[view], cg.X, cg.N, cg.px, cg.py);
+        fr.level = f.level; fr.view = view;
+        fr.tlx = f.tlx; fr.tly = f.tly; fr.dxx = f.dxx; fr.dxy = f.dxy; fr.dyx = f.dyx; fr.dyy = f.dyy;
+    }
+    *out = fr;
 }
 
 // Optim::dot (optim.cpp:601-609) of two slots; same order of operations as group_dot(a = reference, b = view)
@@ -112,69 +132,75 @@ __device__ __forceinline__ float dot_slots(const float* __restrict__ a, float in
 }
 
 // per-thread coordinates inside the CTA
-template <int WS>
+template <int WS, int NW>
 struct CellLane {
     int tid, warp, lane, col, g;
     unsigned gm;
     __device__ __forceinline__ CellLane() {
-        constexpr int GW = CellGeom<WS>::GW;
+        constexpr int GW = CellGeom<WS, NW>::GW;
         tid = threadIdx.x; warp = tid >> 5; lane = tid & 31; col = lane % GW;
-        g = warp * CellGeom<WS>::G + lane / GW;
+        g = warp * CellGeom<WS, NW>::G + lane / GW;
         gm = group_mask<GW>(lane);
     }
 };
 
-// ---- Optim::setINCCs 1-vs-all (optim.cpp:708-746) by the CTA: one group per view -----------------------------------------------
-// images / inccs live in shared memory; every thread holds the same X, N, n.  Ends with a CTA barrier.
-template <int WS>
-__device__ __forceinline__ void cta_set_inccs(const Params& p, CellCta& cs, float* tex, V4 X, V4 N, const int* images, int n, int robust, float* inccs) {
-    typedef CellGeom<WS> Gm;
-    const CellLane<WS> L;
-    V4 px, py;
-    get_paxes(p.views[images[0]], X, N, p.level_scale, px, py);
-    float* mine = tex + (size_t)(1 + L.g) * Gm::SLOT;             // slot 0: the reference view; slot 1 + g: this group's view
-    int lv = -1;
-    float inv = 1.0f;
-    if (L.g < n) {
-        lv = grab_slot<WS, Gm::GW>(p, images[L.g], X, N, px, py, L.col, L.gm, L.g == 0 ? tex : mine, &inv);
-        if (L.g == 0 && L.col == 0) { cs.lvl[0] = lv; cs.inv[0] = inv; }
+// ---- Optim::setINCCs 1-vs-all (optim.cpp:708-746) by the CTA ---------------------------------------------------------------------
+// One THREAD per view decides the frame (projections, pyramid level, getTexSafe), one GROUP per accepted view samples, then the
+// dots against the reference slot.  images / inccs live in shared memory; every thread holds the same X, N, n.  Ends with a barrier.
+template <int WS, int NW>
+__device__ __noinline__ void cta_set_inccs(const Params& p, CellCta& cs, float* tex, V4 X, V4 N, const int* images, int n, int robust, float* inccs) {
+    typedef CellGeom<WS, NW> Gm;
+    const CellLane<WS, NW> L;
+    if (L.tid == 0) cs.nwl = 1;                                   // work list entry 0 = the reference view
+    if (L.tid < ((n + 31) & ~31)) {                              // the warps that hold a view compute the patch axes (no barrier needed)
+        CandGeo cg;
+        cg.X = X; cg.N = N;
+        get_paxes(p.views[images[0]], X, N, p.level_scale, cg.px, cg.py);
+        if (L.tid < n) frame_item(p, images[L.tid], cg, &cs.fr[L.tid]);
     }
     __syncthreads();
-    const int l0 = cs.lvl[0];
-    const float inv0 = cs.inv[0];
-    if (l0 < 0) {
-        for (int k = L.tid; k < n; k += CELL_WARPS * 32) inccs[k] = 2.0f;
+    if (cs.fr[0].level < 0) {
+        for (int k = L.tid; k < n; k += Gm::NT) inccs[k] = 2.0f;
         __syncthreads();
         return;
     }
-    if (L.tid == 0) inccs[0] = 0.0f;
+    for (int i = L.tid; i < n; i += Gm::NT) {
+        if (i == 0) { inccs[0] = 0.0f; cs.wl[0] = 0; }
+        else if (cs.fr[i].level < 0) inccs[i] = 2.0f;
+        else cs.wl[atomicAdd(&cs.nwl, 1)] = i;
+    }
+    __syncthreads();
+    const int nw = cs.nwl;
 #pragma unroll 1
-    for (int base = 0; base < n; base += Gm::TG) {
-        const int i = base + L.g;
-        if (i >= n) break;
-        if (base > 0) lv = grab_slot<WS, Gm::GW>(p, images[i], X, N, px, py, L.col, L.gm, mine, &inv);
-        if (i == 0) continue;
-        float r = 2.0f;
-        if (lv >= 0) {
-            __syncwarp(L.gm);
-            const float d = dot_slots<WS, Gm::GW>(tex, inv0, mine, inv, L.col, L.gm);
-            r = xsub(1.0f, d);
-            if (robust) r = robustincc(r);
+    for (int base = 0; base < nw; base += Gm::TG) {
+        const int k = base + L.g;
+        float* mine = tex + (size_t)(k == 0 ? 0 : 1 + L.g) * Gm::SLOT;       // slot 0: the reference view; slot 1 + g: this group's view
+        float inv = 1.0f;
+        if (k < nw) {
+            inv = sample_slot<WS, Gm::GW>(p, cs.fr[cs.wl[k]], L.col, L.gm, mine);
+            if (k == 0 && L.col == 0) cs.inv[0] = inv;
         }
-        if (L.col == 0) inccs[i] = r;
+        __syncthreads();
+        if (k >= 1 && k < nw) {
+            const float d = dot_slots<WS, Gm::GW>(tex, cs.inv[0], mine, inv, L.col, L.gm);
+            float r = xsub(1.0f, d);
+            if (robust) r = robustincc(r);
+            if (L.col == 0) inccs[cs.wl[k]] = r;
+        }
+        if (base + Gm::TG < nw) __syncthreads();                  // the next round overwrites the slots
     }
     __syncthreads();
 }
 
 // PatchManager::computeNcc (patch_manager.cpp:401-404) on {X, N, ws.images[0..nv)}: every thread returns m_ncc
-template <int WS>
-__device__ __forceinline__ float cta_compute_ncc(const Params& p, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int nv) {
+template <int WS, int NW>
+__device__ __noinline__ float cta_compute_ncc(const Params& p, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int nv) {
     const int tid = threadIdx.x;
     if (tid < 32) compute_weights(p, X, N, ws.images, nv, ws.units, tid);
     float incc = 2.0f;
     if (nv >= 2) {
         const int sz = min(p.tau, nv);
-        cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, sz, 1, ws.inccs);
+        cta_set_inccs<WS, NW>(p, cs, tex, X, N, ws.images, sz, 1, ws.inccs);
         float score = 0.0f, tw = 0.0f;
         for (int i = 1; i < sz; ++i) {
             const float v = ws.inccs[i];
@@ -187,46 +213,11 @@ __device__ __forceinline__ float cta_compute_ncc(const Params& p, WarpScratch& w
 }
 
 // ---- Optim::cost_func (optim.cpp:401-468) for `ncand` encoded points at once -------------------------------------------------------
-// item = (candidate c, view i): grab into slot c * sz + i, then the dots against the candidate's reference slot.  gen(c, x) yields
-// candidate c's encoded point.  On return (after a CTA barrier) cs.lvl / cs.val hold what eval_cost needs.
-template <int WS, typename Gen>
-__device__ __forceinline__ void cta_costs(const CandParams& cp, const RefineCtx& rc, CellCta& cs, float* tex, const int* images, int sz, int ncand, Gen gen) {
-    typedef CellGeom<WS> Gm;
-    const Params& p = cp.p;
-    const CellLane<WS> L;
-    const int nitems = ncand * sz;
-#pragma unroll 1
-    for (int item = L.g; item < nitems; item += Gm::TG) {
-        const int c = item / sz, i = item - c * sz;
-        double xc[3];
-        gen(c, xc);
-        V4 coord, normal, px, py;
-        decode(cp, rc, xc, coord, normal);
-        get_paxes(p.views[rc.ref], coord, normal, p.level_scale, px, py);
-        float inv = 1.0f;
-        const int lv = grab_slot<WS, Gm::GW>(p, images[i], coord, normal, px, py, L.col, L.gm, tex + (size_t)item * Gm::SLOT, &inv);
-        if (L.col == 0) { cs.lvl[item] = lv; cs.inv[item] = inv; }
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int item = L.g; item < nitems; item += Gm::TG) {
-        const int c = item / sz, i = item - c * sz;
-        if (i == 0 || cs.lvl[c * sz] < 0 || cs.lvl[item] < 0) continue;
-        const float d = dot_slots<WS, Gm::GW>(tex + (size_t)(c * sz) * Gm::SLOT, cs.inv[c * sz], tex + (size_t)item * Gm::SLOT, cs.inv[item], L.col, L.gm);
-        if (L.col == 0) cs.val[item] = robustincc(__double2float_rn(1.0 - (double)d));
-    }
-    __syncthreads();
-}
-// the cost of candidate c from the per-view terms, summed in view order as cost_func does
-__device__ __forceinline__ double eval_cost(const CellCta& cs, int c, int sz, int minimum) {
-    if (cs.lvl[c * sz] < 0) return 2.0;
-    double ans = 0.0;
-    int denom = 0;
-    for (int i = 1; i < sz; ++i) if (cs.lvl[c * sz + i] >= 0) { ans += (double)cs.val[c * sz + i]; ++denom; }
-    if (denom < minimum - 1) return 2.0;
-    return ans / (double)denom;
-}
-
+// (1) one thread per candidate: its point, decode + getPAxes; (2) one thread per (candidate c, view i) item: the frame; (3) one group
+// per accepted item: sample into slot c * sz + i; (4) the dots against the candidate's reference slot.  The points: level < 0 -> the
+// single point `best`; else candidate c of PMR1 level `level` around `best` with radii `r` (pmr1_point).  best / r only need to be
+// valid in warp 0.  On return (after a CTA barrier) cs.fr[].level / cs.val hold what eval_cost needs.  One copy, out of line: the
+// sweep kernel is instruction-cache bound.
 __device__ __forceinline__ void pmr1_point(const CandParams& cp, uint64_t stream, int level, int cnd, const double best[3], const double r[3], double xc[3]) {
     const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
     const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
@@ -236,86 +227,158 @@ __device__ __forceinline__ void pmr1_point(const CandParams& cp, uint64_t stream
     for (int i = 0; i < 3; ++i) xc[i] = fmax(fmin(__dadd_rn(best[i], __dmul_rn(r[i], uniform_pm1(ctr[i]))), ub[i]), lb[i]);
 }
 
+template <int WS, int NW>
+__device__ __noinline__ void cta_costs(const CandParams& cp, CellCta& cs, float* tex, const int* images, int sz, int ncand, uint64_t stream, int level,
+                                       double b0, double b1, double b2, double r0, double r1, double r2) {
+    typedef CellGeom<WS, NW> Gm;
+    const Params& p = cp.p;
+    const CellLane<WS, NW> L;
+    const int nitems = ncand * sz;
+    PMK_SUBT(-1);
+    if (L.tid < ncand) {
+        const double best[3] = {b0, b1, b2}, r[3] = {r0, r1, r2};
+        double xc[3] = {b0, b1, b2};
+        if (level >= 0) pmr1_point(cp, stream, level, L.tid, best, r, xc);
+        CandGeo cg;
+        decode(cp, cs.rc, xc, cg.X, cg.N);
+        get_paxes(p.views[cs.rc.ref], cg.X, cg.N, p.level_scale, cg.px, cg.py);
+        cs.cg[L.tid] = cg;
+    }
+    __syncthreads();
+    PMK_SUBT(0);
+    for (int item = L.tid; item < nitems; item += Gm::NT) {
+        const int c = item / sz, i = item - c * sz;
+        frame_item(p, images[i], cs.cg[c], &cs.fr[item]);
+    }
+    __syncthreads();
+    PMK_SUBT(1);
+#pragma unroll 1
+    for (int item = L.g; item < nitems; item += Gm::TG) {
+        if (cs.fr[item].level < 0) continue;
+        const float inv = sample_slot<WS, Gm::GW>(p, cs.fr[item], L.col, L.gm, tex + (size_t)item * Gm::SLOT);
+        if (L.col == 0) cs.inv[item] = inv;
+    }
+    __syncthreads();
+    PMK_SUBT(2);
+#pragma unroll 1
+    for (int item = L.g; item < nitems; item += Gm::TG) {
+        const int c = item / sz, i = item - c * sz;
+        if (i == 0 || cs.fr[c * sz].level < 0 || cs.fr[item].level < 0) continue;
+        const float d = dot_slots<WS, Gm::GW>(tex + (size_t)(c * sz) * Gm::SLOT, cs.inv[c * sz], tex + (size_t)item * Gm::SLOT, cs.inv[item], L.col, L.gm);
+        if (L.col == 0) cs.val[item] = robustincc(__double2float_rn(1.0 - (double)d));
+    }
+    __syncthreads();
+    PMK_SUBT(3);
+}
+// the cost of candidate c from the per-view terms, summed in view order as cost_func does
+__device__ __forceinline__ double eval_cost(const CellCta& cs, int c, int sz, int minimum) {
+    if (cs.fr[c * sz].level < 0) return 2.0;
+    double ans = 0.0;
+    int denom = 0;
+    for (int i = 1; i < sz; ++i) if (cs.fr[c * sz + i].level >= 0) { ans += (double)cs.val[c * sz + i]; ++denom; }
+    if (denom < minimum - 1) return 2.0;
+    return ans / (double)denom;
+}
+
 // ---- Optim::refinePatch (optim.cpp:470-547), schedule PMR1, by the CTA ------------------------------------------------------------------
-// Same points, same costs, same argmin as warp_refine (pmk_cand.cuh).  Every thread returns the same X, N and m_ncc.
-template <int WS>
+// Same points, same costs, same argmin as warp_refine (pmk_cand.cuh).  The search state (best point, its cost, the radii) lives in
+// warp 0 only: its first lanes decode the level's candidates (cta_costs step 1) and it alone reads the costs back; the other warps
+// only supply frames, samples and dots.  Every thread returns the same X, N and m_ncc (broadcast through shared memory).
+template <int WS, int NW>
 __device__ __forceinline__ float cta_refine(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4& X, V4& N, int nv, float dscale, uint64_t stream) {
     const Params& p = cp.p;
     const int tid = threadIdx.x;
-    const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
-    const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
-    RefineCtx rc;
-    rc.center = X;
-    rc.ref = ws.images[0];
-    rc.ray = sub4(X, ld4(p.views[rc.ref].center));
-    rc.ray = div4(rc.ray, norm4(rc.ray));
-    rc.dscale = dscale;
-    if (tid < 32) compute_weights(p, X, N, ws.images, nv, ws.units, tid);          // m_weights of the UNREFINED patch (optim.cpp:490)
-    double best[3];
-    encode(cp, rc, X, N, best);
+    const bool w0 = tid < 32;
+    double best[3] = {0.0, 0.0, 0.0}, fbest = 0.0;
+    double r[3] = {4.0, 4.0, 4.0};
+    if (w0) {
+        const double lb[3] = {-(double)__int_as_float(0x7f800000), -23.99999, -23.99999};
+        const double ub[3] = {(double)__int_as_float(0x7f800000), 23.99999, 23.99999};
+        RefineCtx rc;
+        rc.center = X;
+        rc.ref = ws.images[0];
+        rc.ray = sub4(X, ld4(p.views[rc.ref].center));
+        rc.ray = div4(rc.ray, norm4(rc.ray));
+        rc.dscale = dscale;
+        if (tid == 0) cs.rc = rc;
+        compute_weights(p, X, N, ws.images, nv, ws.units, tid);                   // m_weights of the UNREFINED patch (optim.cpp:490)
+        encode(cp, rc, X, N, best);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) best[i] = fmax(fmin(best[i], ub[i]), lb[i]);
+        for (int i = 0; i < 3; ++i) best[i] = fmax(fmin(best[i], ub[i]), lb[i]);
+    }
     const int sz = min(p.tau, nv);
     const int minimum = min(p.min_image_num, sz);
-    cta_costs<WS>(cp, rc, cs, tex, ws.images, sz, 1, [&](int, double* x) { x[0] = best[0]; x[1] = best[1]; x[2] = best[2]; });
-    double fbest = eval_cost(cs, 0, sz, minimum);
-    double r[3] = {4.0, 4.0, 4.0};
+    cta_costs<WS, NW>(cp, cs, tex, ws.images, sz, 1, stream, -1, best[0], best[1], best[2], 0.0, 0.0, 0.0);
+    if (w0) fbest = eval_cost(cs, 0, sz, minimum);
 #pragma unroll 1
     for (int level = 0; level < PMR1_LEVELS; ++level) {
-        __syncthreads();                                                           // eval_cost readers of the previous level are done
-        cta_costs<WS>(cp, rc, cs, tex, ws.images, sz, PMR1_CANDS, [&](int c, double* x) { pmr1_point(cp, stream, level, c, best, r, x); });
-        // argmin over the level's candidates in index order, lowest index on ties (strict <)
-        double fwin = eval_cost(cs, 0, sz, minimum);
-        int cwin = 0;
-        for (int c = 1; c < PMR1_CANDS; ++c) { const double fc = eval_cost(cs, c, sz, minimum); if (fc < fwin) { fwin = fc; cwin = c; } }
-        if (fwin < fbest) { fbest = fwin; double xw[3]; pmr1_point(cp, stream, level, cwin, best, r, xw); best[0] = xw[0]; best[1] = xw[1]; best[2] = xw[2]; }
+        cta_costs<WS, NW>(cp, cs, tex, ws.images, sz, PMR1_CANDS, stream, level, best[0], best[1], best[2], r[0], r[1], r[2]);
+        if (w0) {
+            // argmin over the level's candidates in index order, lowest index on ties (strict <)
+            const double mine = eval_cost(cs, tid < PMR1_CANDS ? tid : 0, sz, minimum);        // lane c: the cost of candidate c
+            double fwin = __shfl_sync(0xffffffffu, mine, 0);
+            int cwin = 0;
+            for (int c = 1; c < PMR1_CANDS; ++c) { const double fc = __shfl_sync(0xffffffffu, mine, c); if (fc < fwin) { fwin = fc; cwin = c; } }
+            if (fwin < fbest) { fbest = fwin; double xw[3]; pmr1_point(cp, stream, level, cwin, best, r, xw); best[0] = xw[0]; best[1] = xw[1]; best[2] = xw[2]; }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = __dmul_rn(r[i], 0.6);
+            for (int i = 0; i < 3; ++i) r[i] = __dmul_rn(r[i], 0.6);
+        }
+        PMK_SUBT(4);
     }
-    __syncthreads();
     // optim.cpp:534-541: decode, normal.w = 0, ncc = 1.0 - unrobustincc(computeINCC(...)) with the stale weights
-    V4 Xf, Nf;
-    decode(cp, rc, best, Xf, Nf);
-    float incc = 2.0f;
-    if (nv >= 2) {
-        cta_costs<WS>(cp, rc, cs, tex, ws.images, sz, 1, [&](int, double* x) { x[0] = best[0]; x[1] = best[1]; x[2] = best[2]; });
-        if (cs.lvl[0] >= 0) {
+    if (nv >= 2) cta_costs<WS, NW>(cp, cs, tex, ws.images, sz, 1, stream, -1, best[0], best[1], best[2], 0.0, 0.0, 0.0);
+    if (tid == 0) {
+        // the final point was decoded by cta_costs' first step (candidate 0); with fewer than two views nothing was evaluated
+        V4 Xf, Nf;
+        decode(cp, cs.rc, best, Xf, Nf);
+        float incc = 2.0f;
+        if (nv >= 2 && cs.fr[0].level >= 0) {
             float score = 0.0f, tw = 0.0f;
             for (int i = 1; i < sz; ++i)
-                if (cs.lvl[i] >= 0) { tw = xadd(tw, ws.units[i]); score = xadd(score, xmul(cs.val[i], ws.units[i])); }
+                if (cs.fr[i].level >= 0) { tw = xadd(tw, ws.units[i]); score = xadd(score, xmul(cs.val[i], ws.units[i])); }
             incc = (tw == 0.0f) ? 2.0f : xdiv(score, tw);
         }
+        cs.bf[0] = Xf.x; cs.bf[1] = Xf.y; cs.bf[2] = Xf.z; cs.bf[3] = Xf.w;
+        cs.bf[4] = Nf.x; cs.bf[5] = Nf.y; cs.bf[6] = Nf.z;
+        cs.bf[7] = __double2float_rn(1.0 - (double)unrobustincc(incc));
     }
     __syncthreads();
-    X = Xf;
-    N = V4{Nf.x, Nf.y, Nf.z, 0.0f};
-    return __double2float_rn(1.0 - (double)unrobustincc(incc));
+    X = V4{cs.bf[0], cs.bf[1], cs.bf[2], cs.bf[3]};
+    N = V4{cs.bf[4], cs.bf[5], cs.bf[6], 0.0f};
+    const float ncc = cs.bf[7];
+    __syncthreads();
+    return ncc;
 }
 
 // ---- Optim::setRefImage (optim.cpp:348-383) by the CTA; same arithmetic as warp_set_ref_image ------------------------------------------
-template <int WS>
-__device__ __forceinline__ void cta_set_ref_image(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int nv, int wslot) {
-    typedef CellGeom<WS> Gm;
+template <int WS, int NW>
+__device__ __noinline__ void cta_set_ref_image(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int nv, int wslot) {
+    typedef CellGeom<WS, NW> Gm;
     constexpr int TEXW = WS * WS * 3;
     const Params& p = cp.p;
-    const CellLane<WS> L;
+    const CellLane<WS, NW> L;
     float* gtex = cp.tex_scratch + (size_t)wslot * p.nviews * (TEXW + 4);
     float* mat = cp.mat_scratch + (size_t)wslot * p.nviews * p.nviews;
-    V4 px, py;
-    get_paxes(p.views[ws.images[0]], X, N, p.level_scale, px, py);
+    if (L.tid < ((nv + 31) & ~31)) {
+        CandGeo cg;
+        cg.X = X; cg.N = N;
+        get_paxes(p.views[ws.images[0]], X, N, p.level_scale, cg.px, cg.py);
+        if (L.tid < nv) frame_item(p, ws.images[L.tid], cg, &cs.fr[L.tid]);
+    }
+    __syncthreads();
     float* mine = tex + (size_t)L.g * Gm::SLOT;
 #pragma unroll 1
-    for (int base = 0; base < nv; base += Gm::TG) {
-        const int i = base + L.g;
-        if (i >= nv) break;
-        float inv = 1.0f;
-        const int lv = grab_slot<WS, Gm::GW>(p, ws.images[i], X, N, px, py, L.col, L.gm, mine, &inv);
+    for (int i = L.g; i < nv; i += Gm::TG) {
+        const int lv = cs.fr[i].level;
         float* dst = gtex + (size_t)i * (TEXW + 4);
-        if (lv >= 0 && L.col < WS) {
+        if (lv >= 0) {
+            const float inv = sample_slot<WS, Gm::GW>(p, cs.fr[i], L.col, L.gm, mine);
+            if (L.col < WS) {
 #pragma unroll
-            for (int y = 0; y < WS; ++y) {
-                float* q = dst + (y * WS + L.col) * 3;
-                q[0] = mine[(y * 3 + 0) * Gm::GW + L.col] * inv; q[1] = mine[(y * 3 + 1) * Gm::GW + L.col] * inv; q[2] = mine[(y * 3 + 2) * Gm::GW + L.col] * inv;
+                for (int y = 0; y < WS; ++y) {
+                    float* q = dst + (y * WS + L.col) * 3;
+                    q[0] = mine[(y * 3 + 0) * Gm::GW + L.col] * inv; q[1] = mine[(y * 3 + 1) * Gm::GW + L.col] * inv; q[2] = mine[(y * 3 + 2) * Gm::GW + L.col] * inv;
+                }
             }
         }
         if (L.col == 0) dst[TEXW] = lv >= 0 ? 1.0f : 0.0f;
@@ -323,7 +386,7 @@ __device__ __forceinline__ void cta_set_ref_image(const CandParams& cp, WarpScra
     }
     __syncthreads();
 #pragma unroll 1
-    for (int q = L.tid; q < nv * nv; q += CELL_WARPS * 32) {
+    for (int q = L.tid; q < nv * nv; q += Gm::NT) {
         const int i = q / nv, j = q % nv;
         if (j < i) continue;
         float v = 0.0f;
@@ -360,7 +423,7 @@ __device__ __forceinline__ void cta_set_ref_image(const CandParams& cp, WarpScra
 }
 
 // ---- Optim::preProcess (optim.cpp:137-163) by the CTA; every thread gets the same return value, nv, dscale, ascale ------------------
-template <int WS>
+template <int WS, int NW>
 __device__ __forceinline__ int cta_pre_process(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int& nv, float& dscale, float& ascale) {
     const Params& p = cp.p;
     const int tid = threadIdx.x;
@@ -372,7 +435,7 @@ __device__ __forceinline__ int cta_pre_process(const CandParams& cp, WarpScratch
     }
     __syncthreads();
     nv = cs.bi[0];
-    cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // constraintImages, :141
+    cta_set_inccs<WS, NW>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // constraintImages, :141
     if (tid < 32) {
         int n2 = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold_before, tid);
         __syncwarp();
@@ -395,7 +458,7 @@ __device__ __forceinline__ int cta_pre_process(const CandParams& cp, WarpScratch
 }
 
 // ---- Optim::postProcess (optim.cpp:260-290), the store-independent part, by the CTA ---------------------------------------------------
-template <int WS>
+template <int WS, int NW>
 __device__ __forceinline__ int cta_post_process(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int& nv, int wslot) {
     const Params& p = cp.p;
     const int tid = threadIdx.x;
@@ -411,7 +474,7 @@ __device__ __forceinline__ int cta_post_process(const CandParams& cp, WarpScratc
     const int masked = cs.bi[1];
     __syncthreads();
     if (masked == 0) return -1;
-    cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // :269
+    cta_set_inccs<WS, NW>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // :269
     if (tid < 32) {
         int n2 = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, tid);
         __syncwarp();
@@ -422,8 +485,8 @@ __device__ __forceinline__ int cta_post_process(const CandParams& cp, WarpScratc
     nv = cs.bi[0];
     __syncthreads();
     if (nv < p.min_image_num) return -1;                                                                // :272
-    cta_set_ref_image<WS>(cp, ws, cs, tex, X, N, nv, wslot);                                            // :277
-    cta_set_inccs<WS>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // :279
+    cta_set_ref_image<WS, NW>(cp, ws, cs, tex, X, N, nv, wslot);                                            // :277
+    cta_set_inccs<WS, NW>(p, cs, tex, X, N, ws.images, nv, 0, ws.inccs);                                    // :279
     if (tid < 32) {
         const int n2 = warp_constraint(ws.images, ws.inccs, nv, p.ncc_threshold, tid);
         if (tid == 0) cs.bi[0] = n2;
@@ -437,12 +500,13 @@ __device__ __forceinline__ int cta_post_process(const CandParams& cp, WarpScratc
 
 // ---- Filter::computeGain (filter.cpp:108-146) by the CTA: one warp per registration, lanes over the cell's slots --------------------
 // The maximum over a cell does not depend on the order; the subtractions run in list order like the reference.
+template <int NW>
 __device__ __forceinline__ float cta_compute_gain(const StoreParams& sp, CellCta& cs, const PGeo& me, float ncc, const PatchLists& pl, const Overlay& ov) {
     const StoreDev& st = sp.st;
     const Params& p = sp.cp.p;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tot = pl.nimg + pl.nvimg;
-    for (int i = warp; i < tot; i += CELL_WARPS) {
+    for (int i = warp; i < tot; i += NW) {
         const bool isv = i >= pl.nimg;
         const int img = isv ? pl.vimages[i - pl.nimg] : pl.images[i], pc = isv ? pl.vcells[i - pl.nimg] : pl.cells[i];
         const float pdepth = isv ? dot4(ld4(p.views[img].oaxis), me.X) : 0.0f;
@@ -470,6 +534,7 @@ __device__ __forceinline__ float cta_compute_gain(const StoreParams& sp, CellCta
 
 // ---- PatchManager::findNeighbors (patch_manager.cpp:671-728) by the CTA: one warp per view of m_images ----------------------------------
 // Same cells, same tests, same (sorted) result as warp_find_neighbors; the (token, id) table and the output list are shared by the warps.
+template <int NW>
 __device__ __forceinline__ int cta_find_neighbors(const StoreParams& sp, CellCta& cs, const PGeo& me, const PatchLists& pl, float scale, int margin,
                                                   const Overlay& ov, int* out) {
     const StoreDev& st = sp.st;
@@ -503,7 +568,7 @@ __device__ __forceinline__ int cta_find_neighbors(const StoreParams& sp, CellCta
     const unsigned int token = cs.nb_token;
     bool overflow = false;
     const int side = 2 * margin + 1, ncell = side * side;
-    for (int i = warp; i < pl.nimg; i += CELL_WARPS) {
+    for (int i = warp; i < pl.nimg; i += NW) {
         const int img = pl.images[i];
         const ViewConst& vc = p.views[img];
         const int ix = cell_x(pl.cells[i]), iy = cell_y(pl.cells[i]);
@@ -553,14 +618,14 @@ __device__ __forceinline__ int cta_find_neighbors(const StoreParams& sp, CellCta
     if (nuni > NB_CAP) { nuni = NB_CAP; if (tid == 0) cs.nb_over = 1; }
     // ascending id order, as warp_find_neighbors leaves it (the quadric fit sums over the neighbours in this order)
     int* tmp = out + NB_CAP;
-    for (int k = tid; k < nuni; k += CELL_WARPS * 32) {
+    for (int k = tid; k < nuni; k += NW * 32) {
         const int id = out[k];
         int rank = 0;
         for (int j = 0; j < nuni; ++j) rank += out[j] < id ? 1 : 0;
         tmp[rank] = id;
     }
     __syncthreads();
-    for (int k = tid; k < nuni; k += CELL_WARPS * 32) out[k] = tmp[k];
+    for (int k = tid; k < nuni; k += NW * 32) out[k] = tmp[k];
     if (tid == 0 && cs.nb_over) atomicAdd(st.counters + SC_NBOVER, 1);
     __syncthreads();
     return nuni;
@@ -582,9 +647,9 @@ __device__ __noinline__ int topk_out_of_line(const StoreParams& sp, int c, int k
 // =====================================================================================================================================
 // the kernel: dest cells of one wavefront step, handed out longest-first through a counter; one CTA per cell at a time
 // =====================================================================================================================================
-template <int WS>
-__global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const StoreParams sp, const SweepArgs sa) {
-    typedef CellGeom<WS> Gm;
+template <int WS, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) k4_cells(const __grid_constant__ StoreParams sp, const __grid_constant__ SweepArgs sa) {
+    typedef CellGeom<WS, NW> Gm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch& ws = *reinterpret_cast<WarpScratch*>(smem_raw);
     SweepScratch& ss = *reinterpret_cast<SweepScratch*>(smem_raw + sizeof(WarpScratch));
@@ -598,6 +663,7 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
     const int inc = sa.inc;
     const int maxp = sp.max_patches_cell;
     if (tid < SS_COUNT) cs.stat[tid] = 0;
+    if (tid < 8) cs.sub[tid] = 0;
     __syncthreads();
 #define PMK_STAT(slot, v) do { if (tid == 0) cs.stat[slot] += (v); } while (0)
     // profiling only: thread 0 closes the phase that ends here
@@ -641,9 +707,9 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
                 for (int j = 0; j < nneg; ++j) {
                     const int el = cs.negs[j];
                     const int nv = min(st.nimg[el], CAND_MAXV);
-                    for (int k = tid; k < nv; k += CELL_WARPS * 32) ws.images[k] = st.images[(size_t)el * st.maxv + k];
+                    for (int k = tid; k < nv; k += NW * 32) ws.images[k] = st.images[(size_t)el * st.maxv + k];
                     __syncthreads();
-                    const float v = cta_compute_ncc<WS>(p, ws, cs, tex, f4v(st.coord[el]), f4v(st.normal[el]), nv);
+                    const float v = cta_compute_ncc<WS, NW>(p, ws, cs, tex, f4v(st.coord[el]), f4v(st.normal[el]), nv);
                     if (tid == 0) st.scal[el].x = v;
                 }
                 __syncthreads();
@@ -671,6 +737,9 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
         }
         __syncthreads();
         const int ntries = 2 * cs.nsrc;                                                    // MAX_NUM_OF_PROPAG tries per call
+        const bool forced = sa.force.code != nullptr;
+        bool fill0 = false;                                                                // try 0 of the current call drew its jitter
+        if (forced && tid == 0) *sa.force.o_ntries = ntries;
         // ================= the propagatePatch tries (propagate.cpp:122-218), in order, each one spread over the CTA =================
 #pragma unroll 1
         for (int t = 0; t < ntries; ++t) {
@@ -690,10 +759,15 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
             cd.nv = 0; cd.nvv = 0; cd.ncc = 0.f; cd.dscale = 0.f; cd.ascale = 0.f; cd.tmp = 0.f;
             cd.X = V4{0.f, 0.f, 0.f, 1.f}; cd.N = sN;
             int outcome = TRY_GEN_NULL;
-            {
+            int post_r = -2;                                                           // postProcess' return once it has run
+            bool refined = false;                                                      // cd holds the patch as refinePatch left it
+            if (!forced) {
                 V3 ic;
                 if (np < maxp) {
-                    float jx = sa.jitter[2 * k], jy = sa.jitter[2 * k + 1];
+                    // the reference draws from an engine it re-constructs per propagatePatch call (propagate.cpp:139-141): the
+                    // first fill-branch try of a call gets draws 0, 1 and the second one draws 2, 3
+                    const int dr = (k == 1 && fill0) ? 2 : 0;
+                    float jx = sa.jitter[dr], jy = sa.jitter[dr + 1];
                     if (sa.jitter_mode == 1) {
                         uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), 0x4a495454u, (uint32_t)k};
                         philox4x32_10((uint32_t)cp.seed, (uint32_t)(cp.seed >> 32), ctr);
@@ -733,40 +807,64 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
                 int nv = cs.bi[0];
                 __syncthreads();
                 if (nv > 0) {
-                    float ncc = cta_compute_ncc<WS>(p, ws, cs, tex, X, N, nv);
+                    float ncc = cta_compute_ncc<WS, NW>(p, ws, cs, tex, X, N, nv);
                     PMK_PHASE(0)
                     if (np >= maxp && ncc < wncc) outcome = TRY_LOSE;
                     else {
                         // ---- patch optimisation (propagate.cpp:176-193) ----
                         float dscale, ascale;
-                        const int pre = cta_pre_process<WS>(cp, ws, cs, tex, X, N, nv, dscale, ascale);
+                        const int pre = cta_pre_process<WS, NW>(cp, ws, cs, tex, X, N, nv, dscale, ascale);
                         PMK_PHASE(1)
                         if (pre == -1) outcome = TRY_FAIL0;
                         else {
                             if (sa.phase_ns != nullptr && tid == 0) atomicAdd(sa.phase_ns + 7, 1ull);
-                            ncc = cta_refine<WS>(cp, ws, cs, tex, X, N, nv, dscale, stream);
+                            ncc = cta_refine<WS, NW>(cp, ws, cs, tex, X, N, nv, dscale, stream);
                             PMK_PHASE(2)
-                            const int r = cta_post_process<WS>(cp, ws, cs, tex, X, N, nv, wslot);
-                            PMK_PHASE(3)
-                            outcome = r == 0 ? TRY_ACCEPT : TRY_FAIL1;
+                            refined = true;
                             cd.X = X; cd.N = N; cd.nv = nv; cd.ncc = ncc; cd.dscale = dscale; cd.ascale = ascale;
-                            if (r == 0) {
-                                bool outside = false;
-                                for (int i = tid; i < nv; i += CELL_WARPS * 32) {                  // setGrids (optim.cpp:285)
-                                    const V3 q = project(p.views[ws.images[i]].P, X);
-                                    const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
-                                    outside |= ix < 0 || p.views[ws.images[i]].gw <= ix || iy < 0 || p.views[ws.images[i]].gh <= iy;
-                                    ss.cells[i] = pack_cell(ix, iy);
-                                }
-                                // Views inherited from the source patch are not re-checked by addImages, and the refinement moves
-                                // the patch: a view can end up seeing it outside its grid.  The reference then writes m_pgrids out of
-                                // bounds (addPatch, patch_manager.cpp:164-170); here the candidate is rejected like any postProcess failure.
-                                if (__syncthreads_or(outside ? 1 : 0)) outcome = TRY_FAIL1;
-                            }
                         }
                     }
                 }
+            } else {
+                // ---- teacher forcing (tests): the try starts from a recorded hypothesis instead of generating and refining one ----
+                const int fcode = t < sa.force.ntries ? sa.force.code[t] : 0;
+                if (fcode != 0) {
+                    if (np >= maxp && sa.force.ncc0[t] < wncc) outcome = TRY_LOSE;       // propagate.cpp:170, on the recorded m_ncc
+                    else if (fcode == 1) outcome = TRY_DIVERGED;                          // the recorded run lost here; nothing to continue from
+                    else if (fcode == 2) outcome = TRY_FAIL0;
+                    else {
+                        const float4 sc = sa.force.scal[t];
+                        cd.X = f4v(sa.force.coord[t]); cd.N = f4v(sa.force.normal[t]);
+                        cd.ncc = sc.x; cd.dscale = sc.y; cd.ascale = sc.z;
+                        cd.nv = min(sa.force.nimg[t], CAND_MAXV);
+                        for (int i = tid; i < cd.nv; i += NW * 32) ws.images[i] = sa.force.images[(size_t)t * sa.force.stride + i];
+                        __syncthreads();
+                        refined = true;
+                    }
+                }
             }
+            if (refined) {
+                int nv = cd.nv;
+                const int r = cta_post_process<WS, NW>(cp, ws, cs, tex, cd.X, cd.N, nv, wslot);
+                PMK_PHASE(3)
+                post_r = r;
+                outcome = r == 0 ? TRY_ACCEPT : TRY_FAIL1;
+                cd.nv = nv;
+                if (r == 0) {
+                    bool outside = false;
+                    for (int i = tid; i < nv; i += NW * 32) {                          // setGrids (optim.cpp:285)
+                        const V3 q = project(p.views[ws.images[i]].P, cd.X);
+                        const int ix = cell_of(q.x, p.csize), iy = cell_of(q.y, p.csize);
+                        outside |= ix < 0 || p.views[ws.images[i]].gw <= ix || iy < 0 || p.views[ws.images[i]].gh <= iy;
+                        ss.cells[i] = pack_cell(ix, iy);
+                    }
+                    // Views inherited from the source patch are not re-checked by addImages, and the refinement moves
+                    // the patch: a view can end up seeing it outside its grid.  The reference then writes m_pgrids out of
+                    // bounds (addPatch, patch_manager.cpp:164-170); here the candidate is rejected like any postProcess failure.
+                    if (__syncthreads_or(outside ? 1 : 0)) outcome = TRY_FAIL1;
+                }
+            }
+            if (k == 0) fill0 = np < maxp;
             // ---------------- postProcess's store-reading tail: setVImagesVGrids, check (optim.cpp:288-296) ----------------
             if (outcome == TRY_ACCEPT) {
                 cd.tmp = xmul(max_std(0.0f, xsub(cd.ncc, p.ncc_threshold)), (float)cd.nv);      // m_tmp = score2
@@ -784,12 +882,12 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
                     PGeo me; me.X = cd.X; me.N = cd.N; me.dscale = cd.dscale; me.ref = ws.images[0];
                     const PatchLists pl{ws.images, ss.cells, cd.nv, ss.vimg, ss.vcell, cd.nvv};
                     const Overlay ov{cD, cs.l_id, min(cs.nl, LKEEP), cs.removed, cs.nrem};
-                    const float gain = cta_compute_gain(sp, cs, me, cd.ncc, pl, ov);
+                    const float gain = cta_compute_gain<NW>(sp, cs, me, cd.ncc, pl, ov);
                     cd.tmp = gain;
                     if (gain < 0.0f) outcome = TRY_FAIL1;
                     else {
                         int* nb = sp.nb_scratch + (size_t)wslot * NB_STRIDE;
-                        const int nn = cta_find_neighbors(sp, cs, me, pl, 4.0f, 2, ov, nb);
+                        const int nn = cta_find_neighbors<NW>(sp, cs, me, pl, 4.0f, 2, ov, nb);
                         if (6 < nn) {
                             if (warp == 0) { const int rej = quad_out_of_line(sp, me, pl, nb, nn, lane); if (lane == 0) cs.bi[0] = rej; }
                             __syncthreads();
@@ -800,6 +898,18 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
                 }
                 PMK_PHASE(4)
             }
+            if (forced && t < sa.force.ntries) {
+                // what the try decided, for the comparison with the recorded run
+                const ForceIO& fo = sa.force;
+                if (tid == 0) {
+                    fo.o_outcome[t] = outcome; fo.o_full[t] = np >= maxp ? 1 : 0; fo.o_post[t] = post_r;
+                    fo.o_nimg[t] = post_r == 0 ? cd.nv : 0; fo.o_nvimg[t] = outcome == TRY_ACCEPT || post_r == 0 ? cd.nvv : 0; fo.o_tmp[t] = cd.tmp;
+                }
+                if (post_r == 0) {
+                    for (int i = tid; i < cd.nv; i += NW * 32) { fo.o_images[(size_t)t * fo.stride + i] = ws.images[i]; fo.o_cells[(size_t)t * fo.stride + i] = ss.cells[i]; }
+                    for (int i = tid; i < cd.nvv; i += NW * 32) { fo.o_vimages[(size_t)t * fo.stride + i] = ss.vimg[i]; fo.o_vcells[(size_t)t * fo.stride + i] = ss.vcell[i]; }
+                }
+            }
             // ================= commit =================
             PMK_STAT(SS_CALLS, (k == 0) ? 1 : 0);
             PMK_STAT(SS_TRIES, 1);
@@ -809,7 +919,7 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
             else if (outcome == TRY_LOSE) PMK_STAT(SS_NCC_LOSE, 1);
             else if (outcome == TRY_FAIL0) PMK_STAT(SS_FAIL0, 1);
             else if (outcome == TRY_FAIL1) PMK_STAT(SS_FAIL1, 1);
-            else if (warp == 0) {
+            else if (outcome == TRY_ACCEPT && warp == 0) {
                 // ---- removePatch(worst) / addPatch(new) (propagate.cpp:195-207); grid updates are staged ----
                 int nl = cs.nl;
                 if (nl == maxp) {
@@ -871,6 +981,9 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, PMK_CELL_MINB) k4_cells(const
 #undef PMK_PHASE
 #undef PMK_STAT
     if (tid < SS_COUNT && cs.stat[tid]) atomicAdd(sa.stats + tid, (unsigned long long)cs.stat[tid]);
+#ifdef PMK_SUBPHASE
+    if (sa.phase_ns != nullptr && tid < 8 && cs.sub[tid]) atomicAdd(sa.phase_ns + 8 + tid, cs.sub[tid]);
+#endif
 }
 
 }  // namespace pmk

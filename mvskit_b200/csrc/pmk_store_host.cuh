@@ -399,6 +399,24 @@ NcclApi* nccl_api() {
     return (api.handle && api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather) ? &api : nullptr;
 }
 
+// one CTA of NW warps per dest cell (pmk_cell.cuh)
+template <int WS, int NW, int MINB>
+int launch_cells(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& a) {
+    typedef CellGeom<WS, NW> Gm;
+    const size_t csmem = ((sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellCta) + 15) & ~(size_t)15) +
+                         (size_t)Gm::nslots(ctx->params.tau) * Gm::SLOT * sizeof(float);
+    static int per_sm = 0;
+    if (!per_sm) {
+        CUDA_TRY(cudaFuncSetAttribute(k4_cells<WS, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cells<WS, NW, MINB>, NW * 32, csmem));
+        if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k4_cells does not fit on an SM");
+        if (getenv("PMK_CELL_MAXCTA")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("PMK_CELL_MAXCTA"))));    // experiment: unloaded latency
+    }
+    const int cgrid = std::max(1, std::min(a.ntasks, std::min(ctx->sm_count * per_sm, ctx->cand_grid * CAND_WARPS)));
+    k4_cells<WS, NW, MINB><<<cgrid, NW * 32, csmem, ctx->stream>>>(sp, a);
+    return PMK_OK;
+}
+
 template <int WS>
 int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     pmk_store* s = ctx->store;
@@ -408,6 +426,7 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + cpc - 1) / cpc));
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(s->step_max, 0, sizeof(unsigned long long), st));
+    int rc_cells = 0;
     static const int use_v1 = getenv("PMK_SWEEP_V1") ? 1 : 0;      // A/B switch while the CTA-per-cell kernel is being validated
     if (sa.ntasks > 0 && !use_v1) {
         // one CTA per dest cell, handed out longest-first through SC_NEXT (pmk_cell.cuh)
@@ -417,17 +436,14 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
         a.range_sel = 0;
         k4_plan<<<1, 1024, 0, st>>>(sp, a, s->order);
         CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_NEXT, 0, sizeof(int), st));
-        typedef CellGeom<WS> Gm;
-        const size_t csmem = ((sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellCta) + 15) & ~(size_t)15) +
-                             (size_t)Gm::nslots(ctx->params.tau) * Gm::SLOT * sizeof(float);
-        static int per_sm = 0;
-        if (!per_sm) {
-            CUDA_TRY(cudaFuncSetAttribute(k4_cells<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cells<WS>, CELL_WARPS * 32, csmem));
-            if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k4_cells does not fit on an SM");
-        }
-        const int cgrid = std::max(1, std::min(sa.ntasks, std::min(ctx->sm_count * per_sm, ctx->cand_grid * CAND_WARPS)));
-        k4_cells<WS><<<cgrid, CELL_WARPS * 32, csmem, st>>>(sp, a);
+        static const int nw_env = getenv("PMK_CELL_WARPS") ? atoi(getenv("PMK_CELL_WARPS")) : 8;
+        static const int minb_env = getenv("PMK_CELL_MINB") ? atoi(getenv("PMK_CELL_MINB")) : 3;
+        if (nw_env == 12) rc_cells = launch_cells<WS, 12, 2>(ctx, sp, a);
+        else if (nw_env == 4) rc_cells = minb_env >= 6 ? launch_cells<WS, 4, 6>(ctx, sp, a) : launch_cells<WS, 4, 4>(ctx, sp, a);
+        else if (minb_env == 4) rc_cells = launch_cells<WS, 8, 4>(ctx, sp, a);
+        else if (minb_env == 5) rc_cells = launch_cells<WS, 8, 5>(ctx, sp, a);
+        else rc_cells = launch_cells<WS, 8, 3>(ctx, sp, a);
+        if (rc_cells) return rc_cells;
         ctx->launches += 2;
     } else if (sa.ntasks > 0) {
         SweepArgs a = sa;
@@ -484,7 +500,7 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
 // Wavefront steps [step_first, step_first + step_count) of Propagate::propagatePmImage for views [img_first, img_first + nimg):
 // step k carries anti-diagonal k (from the far corner on odd iterations, propagate.cpp:80-86) of every view of the group.
 // (rank, nranks): this GPU only takes the dest cells whose row lies in its band of each view's grid (multi-GPU partition).
-int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first, int step_count, uint64_t seed) {
+int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first, int step_count, uint64_t seed, int only_x = -1, const ForceIO* force = nullptr) {
     pmk_store* s = ctx->store;
     StoreParams sp;
     int rc = store_params(ctx, sp, seed);
@@ -496,6 +512,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     sa.inc = inc; sa.iter = iter;
     sa.jitter_mode = ctx->cfg.jitter_mode;
     for (int i = 0; i < 4; ++i) sa.jitter[i] = s->jitter[i];
+    if (force) sa.force = *force;
     sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order; sa.step_max = s->step_max; sa.cell_ns = s->cell_ns; sa.phase_ns = s->phase_ns;
     int max_steps = 0;
     for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
@@ -510,7 +527,8 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
             // rows of this rank's band
             const int ylo = (int)((long long)gh * s->rank / s->nranks), yhi = (int)((long long)gh * (s->rank + 1) / s->nranks);
             const int gxlo = std::max(0, d - gh + 1), gxhi = std::min(gw - 1, d);             // the whole anti-diagonal
-            const int xlo = std::max(gxlo, d - yhi + 1), xhi = std::min(gxhi, d - ylo);       // this rank's band of it
+            int xlo = std::max(gxlo, d - yhi + 1), xhi = std::min(gxhi, d - ylo);             // this rank's band of it
+            if (only_x >= 0) { xlo = std::max(xlo, only_x); xhi = std::min(xhi, only_x); }   // a single dest cell (pmk_propagate_forced)
             const int goff = gtasks;
             gtasks += gxhi - gxlo + 1;
             if (xhi < xlo) continue;

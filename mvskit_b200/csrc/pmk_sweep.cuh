@@ -25,6 +25,16 @@ constexpr int GROUP_MAX = 128;         // views whose wavefronts one step can ca
 constexpr int LKEEP = 40;              // entries of a cell list the sweep keeps (MAX_NUM_OF_PATCHES <= 32, plus slack)
 constexpr int REM_OVERLAY = 128;       // removals of a dest cell that the step's own check() calls can see
 
+// Teacher forcing (tests only, pmk_propagate_forced): the tries of the step's single dest cell start from recorded hypotheses --
+// the patch as the reference's refinePatch left it -- so that everything decided AFTER the hypothesis (the m_ncc test against the
+// worst patch, postProcess, setVImagesVGrids, check, add / replace) can be compared try by try.  code: 0 generatePatch NULL,
+// 1 lost, 2 preProcess == -1, 3 refined (coord / normal / scal = {ncc, dscale, ascale} / images are the refined patch).
+struct ForceIO {
+    int ntries, stride;
+    const int* code; const float* ncc0; const float4* coord; const float4* normal; const float4* scal; const int* nimg; const int* images;
+    int* o_ntries; int* o_outcome; int* o_full; int* o_post; int* o_nimg; int* o_images; int* o_cells; int* o_nvimg; int* o_vimages; int* o_vcells; float* o_tmp;
+};
+
 struct SweepArgs {
     // dest cells of this step: for group member g, view g_img[g], cells (g_xlo[g] + t, g_diag[g] - g_xlo[g] - t),
     // t in [0, g_off[g + 1] - g_off[g]); task index = g_off[g] + t
@@ -49,6 +59,7 @@ struct SweepArgs {
     unsigned long long* stats;             // SweepStat
     unsigned long long* step_max;          // slowest dest cell of this step, ns (one word per step, zeroed by the host)
     float* cell_ns;                        // optional [total_cells]: time spent on each dest cell in its last visit (profiling)
+    ForceIO force;                         // code == nullptr in production
     unsigned long long* phase_ns;          // optional [8]: warp time by phase of a try (profiling, pmk_debug_phase_times): generatePatch + computeNcc,
                                            // preProcess, refinePatch, postProcess, its store-reading tail, waiting for the turn / commit, tries, refined tries
 };
@@ -225,7 +236,7 @@ __device__ __forceinline__ TrySnap take_snapshot(const CellShared& cs, int* my_i
     return sn;
 }
 
-enum TryOutcome { TRY_GEN_NULL = 0, TRY_LOSE, TRY_FAIL0, TRY_FAIL1, TRY_ACCEPT };
+enum TryOutcome { TRY_GEN_NULL = 0, TRY_LOSE, TRY_FAIL0, TRY_FAIL1, TRY_ACCEPT, TRY_DIVERGED };
 
 struct Cand {                    // a candidate after stage A (its image list is in ws.images)
     V4 X, N;

@@ -40,6 +40,13 @@ class Camera(C.Structure):
                 ("yaxis", C.c_float * 3), ("zaxis", C.c_float * 3), ("ipscale", C.c_float)]
 
 
+class ForcedIO(C.Structure):
+    """pmk_forced_io (include/pmk.h)."""
+    _fields_ = [("ntries", C.c_int), ("stride", C.c_int)] + [(n, C.c_void_p) for n in (
+        "code", "ncc0", "coord4", "normal4", "scal4", "nimages", "images", "ntries_out", "outcome", "branch_full", "post_ret",
+        "nimages_out", "images_out", "grids_out", "nvimages_out", "vimages_out", "vgrids_out", "tmp_out")]
+
+
 _lib = None
 
 
@@ -363,6 +370,25 @@ class Context:
         st = np.zeros(16, np.uint64)
         _chk(lib().pmk_propagate_diagonals(self.h, it, image, first, count, C.c_uint64(seed), _p(st)))
         return dict(zip(self.SWEEP_STATS, (int(v) for v in st)))
+
+    def propagate_forced(self, it: int, image: int, x: int, y: int, code, ncc0, coord, normal, scal, images, nimages) -> dict:
+        """pmk_propagate_forced: replay dest cell (x, y) with every try starting from a recorded post-refinePatch hypothesis."""
+        code, nimages = np.ascontiguousarray(code, np.int32), np.ascontiguousarray(nimages, np.int32)
+        ncc0 = np.ascontiguousarray(ncc0, np.float32)
+        coord, normal, scal = (np.ascontiguousarray(a, np.float32) for a in (coord, normal, scal))
+        images = np.ascontiguousarray(images, np.int32)
+        T, S = len(code), images.shape[1]
+        o = dict(ntries=np.zeros(1, np.int32), outcome=np.zeros(T, np.int32), branch_full=np.zeros(T, np.int32), post_ret=np.zeros(T, np.int32),
+                 nimages=np.zeros(T, np.int32), images=np.zeros((T, S), np.int32), grids=np.zeros((T, S, 2), np.int32),
+                 nvimages=np.zeros(T, np.int32), vimages=np.zeros((T, S), np.int32), vgrids=np.zeros((T, S, 2), np.int32), tmp=np.zeros(T, np.float32))
+        io = ForcedIO(T, S, _p(code), _p(ncc0), _p(coord), _p(normal), _p(scal), _p(nimages), _p(images), _p(o["ntries"]), _p(o["outcome"]),
+                      _p(o["branch_full"]), _p(o["post_ret"]), _p(o["nimages"]), _p(o["images"]), _p(o["grids"]), _p(o["nvimages"]), _p(o["vimages"]),
+                      _p(o["vgrids"]), _p(o["tmp"]))
+        st = np.zeros(16, np.uint64)
+        _chk(lib().pmk_propagate_forced(self.h, it, image, x, y, C.byref(io), _p(st)))
+        o["ntries"] = int(o["ntries"][0])
+        o["stats"] = dict(zip(self.SWEEP_STATS, (int(v) for v in st)))
+        return o
 
     def filter_rebuild(self, additive: int) -> int:
         n = C.c_int()

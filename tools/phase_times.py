@@ -28,7 +28,7 @@ def main():
         st = ctx.propagate(it, 0x5EED0001)
         ctx.sync()
         wall = time.perf_counter() - t
-        ph = np.zeros(8, np.uint64)
+        ph = np.zeros(16, np.uint64)
         pmk._chk(pmk.lib().pmk_debug_phase_times(ctx.h, pmk._p(ph)))
         tot = float(ph[:6].sum())
         tries, refined = int(ph[6]), int(ph[7])
@@ -37,6 +37,9 @@ def main():
         for i, name in enumerate(NAMES):
             per = refined if i in (2, 3, 4) else tries
             print(f"  {name:<36s} {float(ph[i]) / 1e9:8.2f} s  {100.0 * float(ph[i]) / max(tot, 1):5.1f} %   {float(ph[i]) / max(per, 1) / 1e3:8.1f} us per {'refined try' if i in (2, 3, 4) else 'try'}")
+        if ph[8:].any():
+            sub = ph[8:].astype(float) / 1e9
+            print("  cta_costs sub-phases (s): candidates %.2f, frames %.2f, sampling %.2f, dots %.2f, argmin %.2f" % tuple(sub[:5]))
         ctx.filter(); ctx.update_threshold()
     ctx.close()
 
