@@ -235,7 +235,7 @@ int cand_params(pmk_ctx* ctx, CandParams& cp, uint64_t seed) {
     const int ws = ctx->cfg.wsize, texw = ws * ws * 3 + 4;
     if (!ctx->cand_grid) {
         ctx->cand_grid = ctx->sm_count * 4;
-        const size_t warps = (size_t)ctx->cand_grid * CAND_WARPS * 2;   // x2: the sweep runs two kernels side by side (heavy / light dest cells)
+        const size_t warps = (size_t)ctx->cand_grid * CAND_WARPS;       // one slice per warp of the candidate kernels / per CTA of the sweep
         CUDA_TRY(cudaMalloc((void**)&ctx->tex_scratch, warps * ctx->cfg.nviews * texw * sizeof(float)));
         CUDA_TRY(cudaMalloc((void**)&ctx->mat_scratch, warps * ctx->cfg.nviews * ctx->cfg.nviews * sizeof(float)));
         ctx->owned.push_back(ctx->tex_scratch);

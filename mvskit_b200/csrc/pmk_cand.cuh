@@ -118,7 +118,7 @@ struct RefineCtx {
     int ref;
 };
 
-__device__ __forceinline__ void decode(const CandParams& cp, const RefineCtx& rc, const double x[3], V4& coord, V4& normal) {
+__device__ __forceinline__ void decode(const CandParams& cp, const ViewConst& vc, const RefineCtx& rc, const double x[3], V4& coord, V4& normal) {
     const float s = __double2float_rn(__dmul_rn((double)rc.dscale, x[0]));        // double scalar narrowed, then Vector4f * float
     coord = add4(rc.center, mul4(rc.ray, s));
     const float angle1 = __double2float_rn(__dmul_rn(x[1], (double)cp.ascale));
@@ -126,12 +126,14 @@ __device__ __forceinline__ void decode(const CandParams& cp, const RefineCtx& rc
     const float fx = xmul(sinf(angle1), cosf(angle2));
     const float fy = sinf(angle2);
     const float fz = xmul(-cosf(angle1), cosf(angle2));
-    const ViewConst& vc = cp.p.views[rc.ref];
     const V4 xa = ld4(vc.xaxis), ya = ld4(vc.yaxis), za = ld4(vc.zaxis);
     normal.x = xadd(xadd(xmul(xa.x, fx), xmul(ya.x, fy)), xmul(za.x, fz));
     normal.y = xadd(xadd(xmul(xa.y, fx), xmul(ya.y, fy)), xmul(za.y, fz));
     normal.z = xadd(xadd(xmul(xa.z, fx), xmul(ya.z, fy)), xmul(za.z, fz));
     normal.w = 0.0f;
+}
+__device__ __forceinline__ void decode(const CandParams& cp, const RefineCtx& rc, const double x[3], V4& coord, V4& normal) {
+    decode(cp, cp.p.views[rc.ref], rc, x, coord, normal);
 }
 
 // ---- Optim::encode (optim.cpp:549-580) -----------------------------------------------------------------------------------

@@ -33,12 +33,12 @@ struct CellGeom {
     static constexpr int G = 32 / GW;                         // groups per warp
     static constexpr int TG = NW * G;                         // groups per CTA
     static constexpr int NT = NW * 32;                        // threads per CTA
-    static constexpr int SLOT = WS * 3 * GW;                  // floats of one texture slot: [row][channel][column]
+    static constexpr int SLOT = WS * 3 * WS;                  // floats of one texture slot: [row][channel][column < WS]
     __host__ __device__ static constexpr int nslots(int tau) { return (PMR1_CANDS * tau > TG + 1) ? PMR1_CANDS * tau : TG + 1; }
 };
 
 #ifdef PMK_SUBPHASE
-#define PMK_SUBT(slot) do { if (threadIdx.x == 0) { unsigned long long n_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n_)); if ((slot) >= 0) cs.sub[slot] += n_ - cs.sub_t; cs.sub_t = n_; } } while (0)
+#define PMK_SUBT(slot) do { if ((int)threadIdx.x == 0) { unsigned long long n_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n_)); if ((slot) >= 0) cs.sub[slot] += n_ - cs.sub_t; cs.sub_t = n_; } } while (0)
 #else
 #define PMK_SUBT(slot) do { } while (0)
 #endif
@@ -56,6 +56,8 @@ struct CellCta {                       // one per CTA, shared memory
     int bi[8];                         // small broadcasts from warp 0
     float bf[8];
     RefineCtx rc;                      // Optim::m_center / m_ray / m_dscale of the refinement in flight
+    int fr_ok[PMK_MAX_TAU];            // view index valid
+    ViewConst vc[PMK_MAX_TAU];         // the refinement's views (m_indexes), copied next to the SM: every cost evaluation starts from them
     CandGeo cg[PMR1_CANDS];
     ItemFrame fr[FRAME_SLOTS];         // per item: the sampling frame (level < 0: getTex == -1)
     float inv[FRAME_SLOTS];            //           1 / msd of Optim::normalize
@@ -75,13 +77,12 @@ struct CellCta {                       // one per CTA, shared memory
 
 // ---- the sampling half of a texture grab, by one evaluator group, into a shared-memory slot -------------------------------------
 // Optim::getTex's 49 samples + Optim::normalize (optim.cpp:835-842, 917-940) for a frame make_frame accepted.  Arithmetic identical
-// to group_grab (pmk_cand.cuh); the centred, masked lattice column of each lane goes to slot[(row * 3 + channel) * GW + col].
+// to group_grab (pmk_cand.cuh); the centred lattice column of each lane (col < WS) goes to slot[(row * 3 + channel) * WS + col].
 // Returns 1 / sqrt(ssd / (3 n)) (1 when ssd == 0).
 template <int WS, int GW>
-__device__ __noinline__ float sample_slot(const Params& p, const ItemFrame& f, int col, unsigned gm, float* __restrict__ slot) {
+__device__ __noinline__ float sample_slot(const ViewConst& vc, const ItemFrame& f, int col, unsigned gm, float* __restrict__ slot) {
     constexpr int NSAMP = WS * WS;
     constexpr float INV_NSAMP = 1.0f / (float)NSAMP, INV_3NSAMP = 1.0f / (float)(3 * NSAMP);
-    const ViewConst& vc = p.views[f.view];
     const float cmask = col < WS ? 1.0f : 0.0f;
     const Texel* img = vc.img[f.level];
     const int W = vc.w[f.level];
@@ -101,33 +102,37 @@ __device__ __noinline__ float sample_slot(const Params& p, const ItemFrame& f, i
     for (int y = 0; y < WS; ++y) {
         t[y][0] = fmaf(t[y][0], cmask, m0); t[y][1] = fmaf(t[y][1], cmask, m1); t[y][2] = fmaf(t[y][2], cmask, m2);
         ssd = fmaf(t[y][0], t[y][0], fmaf(t[y][1], t[y][1], fmaf(t[y][2], t[y][2], ssd)));
-        slot[(y * 3 + 0) * GW + col] = t[y][0]; slot[(y * 3 + 1) * GW + col] = t[y][1]; slot[(y * 3 + 2) * GW + col] = t[y][2];
+        if (col < WS) { slot[(y * 3 + 0) * WS + col] = t[y][0]; slot[(y * 3 + 1) * WS + col] = t[y][1]; slot[(y * 3 + 2) * WS + col] = t[y][2]; }
     }
     const float var = group_sum<GW>(ssd, gm) * INV_3NSAMP;
     return var > 0.0f ? rsqrtf(var) : 1.0f;
 }
 
 // the deciding half (optim.cpp:790-833 + getTexSafe :895-915), by ONE thread per (candidate, view) item
-__device__ __noinline__ void frame_item(const Params& p, int view, const CandGeo& cg, ItemFrame* out) {
+__device__ __noinline__ void frame_item(const Params& p, const ViewConst* vc, int view, const CandGeo& cg, ItemFrame* out) {
     ItemFrame fr;
     fr.level = -1; fr.view = 0;
     fr.tlx = fr.tly = fr.dxx = fr.dxy = fr.dyx = fr.dyy = 0.0f;
-    if (view >= 0 && view < p.nviews) {
-        const Frame f = make_frame(p, p.views[view], cg.X, cg.N, cg.px, cg.py);
+    if (vc != nullptr) {
+        const Frame f = make_frame(p, *vc, cg.X, cg.N, cg.px, cg.py);
         fr.level = f.level; fr.view = view;
         fr.tlx = f.tlx; fr.tly = f.tly; fr.dxx = f.dxx; fr.dxy = f.dxy; fr.dyx = f.dyx; fr.dyy = f.dyy;
     }
     *out = fr;
 }
+__device__ __forceinline__ const ViewConst* view_or_null(const Params& p, int view) { return (view >= 0 && view < p.nviews) ? p.views + view : nullptr; }
 
 // Optim::dot (optim.cpp:601-609) of two slots; same order of operations as group_dot(a = reference, b = view)
 template <int WS, int GW>
 __device__ __forceinline__ float dot_slots(const float* __restrict__ a, float inv_a, const float* __restrict__ b, float inv_b, int col, unsigned gm) {
+    // lanes past the lattice width hold zeros (group_grab masks them): they add nothing but take part in the reduction tree
     float dp = 0.f;
+    if (col < WS) {
 #pragma unroll
-    for (int y = 0; y < WS; ++y)
-        dp = fmaf(a[(y * 3 + 0) * GW + col], b[(y * 3 + 0) * GW + col],
-                  fmaf(a[(y * 3 + 1) * GW + col], b[(y * 3 + 1) * GW + col], fmaf(a[(y * 3 + 2) * GW + col], b[(y * 3 + 2) * GW + col], dp)));
+        for (int y = 0; y < WS; ++y)
+            dp = fmaf(a[(y * 3 + 0) * WS + col], b[(y * 3 + 0) * WS + col],
+                      fmaf(a[(y * 3 + 1) * WS + col], b[(y * 3 + 1) * WS + col], fmaf(a[(y * 3 + 2) * WS + col], b[(y * 3 + 2) * WS + col], dp)));
+    }
     return group_sum<GW>(dp, gm) * inv_a * inv_b * (1.0f / (float)(3 * WS * WS));
 }
 
@@ -138,7 +143,7 @@ struct CellLane {
     unsigned gm;
     __device__ __forceinline__ CellLane() {
         constexpr int GW = CellGeom<WS, NW>::GW;
-        tid = threadIdx.x; warp = tid >> 5; lane = tid & 31; col = lane % GW;
+        tid = (int)threadIdx.x; warp = tid >> 5; lane = tid & 31; col = lane % GW;
         g = warp * CellGeom<WS, NW>::G + lane / GW;
         gm = group_mask<GW>(lane);
     }
@@ -156,7 +161,7 @@ __device__ __noinline__ void cta_set_inccs(const Params& p, CellCta& cs, float* 
         CandGeo cg;
         cg.X = X; cg.N = N;
         get_paxes(p.views[images[0]], X, N, p.level_scale, cg.px, cg.py);
-        if (L.tid < n) frame_item(p, images[L.tid], cg, &cs.fr[L.tid]);
+        if (L.tid < n) frame_item(p, view_or_null(p, images[L.tid]), images[L.tid], cg, &cs.fr[L.tid]);
     }
     __syncthreads();
     if (cs.fr[0].level < 0) {
@@ -177,7 +182,7 @@ __device__ __noinline__ void cta_set_inccs(const Params& p, CellCta& cs, float* 
         float* mine = tex + (size_t)(k == 0 ? 0 : 1 + L.g) * Gm::SLOT;       // slot 0: the reference view; slot 1 + g: this group's view
         float inv = 1.0f;
         if (k < nw) {
-            inv = sample_slot<WS, Gm::GW>(p, cs.fr[cs.wl[k]], L.col, L.gm, mine);
+            inv = sample_slot<WS, Gm::GW>(p.views[cs.fr[cs.wl[k]].view], cs.fr[cs.wl[k]], L.col, L.gm, mine);
             if (k == 0 && L.col == 0) cs.inv[0] = inv;
         }
         __syncthreads();
@@ -195,7 +200,7 @@ __device__ __noinline__ void cta_set_inccs(const Params& p, CellCta& cs, float* 
 // PatchManager::computeNcc (patch_manager.cpp:401-404) on {X, N, ws.images[0..nv)}: every thread returns m_ncc
 template <int WS, int NW>
 __device__ __noinline__ float cta_compute_ncc(const Params& p, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int nv) {
-    const int tid = threadIdx.x;
+    const int tid = (int)threadIdx.x;
     if (tid < 32) compute_weights(p, X, N, ws.images, nv, ws.units, tid);
     float incc = 2.0f;
     if (nv >= 2) {
@@ -240,22 +245,22 @@ __device__ __noinline__ void cta_costs(const CandParams& cp, CellCta& cs, float*
         double xc[3] = {b0, b1, b2};
         if (level >= 0) pmr1_point(cp, stream, level, L.tid, best, r, xc);
         CandGeo cg;
-        decode(cp, cs.rc, xc, cg.X, cg.N);
-        get_paxes(p.views[cs.rc.ref], cg.X, cg.N, p.level_scale, cg.px, cg.py);
+        decode(cp, cs.vc[0], cs.rc, xc, cg.X, cg.N);
+        get_paxes(cs.vc[0], cg.X, cg.N, p.level_scale, cg.px, cg.py);
         cs.cg[L.tid] = cg;
     }
     __syncthreads();
     PMK_SUBT(0);
     for (int item = L.tid; item < nitems; item += Gm::NT) {
         const int c = item / sz, i = item - c * sz;
-        frame_item(p, images[i], cs.cg[c], &cs.fr[item]);
+        frame_item(p, cs.fr_ok[i] ? &cs.vc[i] : nullptr, i, cs.cg[c], &cs.fr[item]);              // ItemFrame::view = index into cs.vc
     }
     __syncthreads();
     PMK_SUBT(1);
 #pragma unroll 1
     for (int item = L.g; item < nitems; item += Gm::TG) {
         if (cs.fr[item].level < 0) continue;
-        const float inv = sample_slot<WS, Gm::GW>(p, cs.fr[item], L.col, L.gm, tex + (size_t)item * Gm::SLOT);
+        const float inv = sample_slot<WS, Gm::GW>(cs.vc[cs.fr[item].view], cs.fr[item], L.col, L.gm, tex + (size_t)item * Gm::SLOT);
         if (L.col == 0) cs.inv[item] = inv;
     }
     __syncthreads();
@@ -287,7 +292,7 @@ __device__ __forceinline__ double eval_cost(const CellCta& cs, int c, int sz, in
 template <int WS, int NW>
 __device__ __forceinline__ float cta_refine(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4& X, V4& N, int nv, float dscale, uint64_t stream) {
     const Params& p = cp.p;
-    const int tid = threadIdx.x;
+    const int tid = (int)threadIdx.x;
     const bool w0 = tid < 32;
     double best[3] = {0.0, 0.0, 0.0}, fbest = 0.0;
     double r[3] = {4.0, 4.0, 4.0};
@@ -308,6 +313,16 @@ __device__ __forceinline__ float cta_refine(const CandParams& cp, WarpScratch& w
     }
     const int sz = min(p.tau, nv);
     const int minimum = min(p.min_image_num, sz);
+    {   // the sz views every cost evaluation of this refinement reads: per-view constants into shared memory, word by word
+        constexpr int VW = sizeof(ViewConst) / 4;
+        for (int w = tid; w < sz * VW; w += NW * 32) {
+            const int i = w / VW, o = w - i * VW, v = ws.images[i];
+            const bool ok = v >= 0 && v < p.nviews;
+            if (o == 0) cs.fr_ok[i] = ok ? 1 : 0;
+            reinterpret_cast<unsigned int*>(&cs.vc[i])[o] = reinterpret_cast<const unsigned int*>(p.views + (ok ? v : 0))[o];
+        }
+    }
+    __syncthreads();
     cta_costs<WS, NW>(cp, cs, tex, ws.images, sz, 1, stream, -1, best[0], best[1], best[2], 0.0, 0.0, 0.0);
     if (w0) fbest = eval_cost(cs, 0, sz, minimum);
 #pragma unroll 1
@@ -330,7 +345,7 @@ __device__ __forceinline__ float cta_refine(const CandParams& cp, WarpScratch& w
     if (tid == 0) {
         // the final point was decoded by cta_costs' first step (candidate 0); with fewer than two views nothing was evaluated
         V4 Xf, Nf;
-        decode(cp, cs.rc, best, Xf, Nf);
+        decode(cp, cs.vc[0], cs.rc, best, Xf, Nf);
         float incc = 2.0f;
         if (nv >= 2 && cs.fr[0].level >= 0) {
             float score = 0.0f, tw = 0.0f;
@@ -363,7 +378,7 @@ __device__ __noinline__ void cta_set_ref_image(const CandParams& cp, WarpScratch
         CandGeo cg;
         cg.X = X; cg.N = N;
         get_paxes(p.views[ws.images[0]], X, N, p.level_scale, cg.px, cg.py);
-        if (L.tid < nv) frame_item(p, ws.images[L.tid], cg, &cs.fr[L.tid]);
+        if (L.tid < nv) frame_item(p, view_or_null(p, ws.images[L.tid]), ws.images[L.tid], cg, &cs.fr[L.tid]);
     }
     __syncthreads();
     float* mine = tex + (size_t)L.g * Gm::SLOT;
@@ -372,12 +387,12 @@ __device__ __noinline__ void cta_set_ref_image(const CandParams& cp, WarpScratch
         const int lv = cs.fr[i].level;
         float* dst = gtex + (size_t)i * (TEXW + 4);
         if (lv >= 0) {
-            const float inv = sample_slot<WS, Gm::GW>(p, cs.fr[i], L.col, L.gm, mine);
+            const float inv = sample_slot<WS, Gm::GW>(p.views[cs.fr[i].view], cs.fr[i], L.col, L.gm, mine);
             if (L.col < WS) {
 #pragma unroll
                 for (int y = 0; y < WS; ++y) {
                     float* q = dst + (y * WS + L.col) * 3;
-                    q[0] = mine[(y * 3 + 0) * Gm::GW + L.col] * inv; q[1] = mine[(y * 3 + 1) * Gm::GW + L.col] * inv; q[2] = mine[(y * 3 + 2) * Gm::GW + L.col] * inv;
+                    q[0] = mine[(y * 3 + 0) * WS + L.col] * inv; q[1] = mine[(y * 3 + 1) * WS + L.col] * inv; q[2] = mine[(y * 3 + 2) * WS + L.col] * inv;
                 }
             }
         }
@@ -426,7 +441,7 @@ __device__ __noinline__ void cta_set_ref_image(const CandParams& cp, WarpScratch
 template <int WS, int NW>
 __device__ __forceinline__ int cta_pre_process(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int& nv, float& dscale, float& ascale) {
     const Params& p = cp.p;
-    const int tid = threadIdx.x;
+    const int tid = (int)threadIdx.x;
     dscale = 0.0f; ascale = 0.0f;
     if (nv < 1) { nv = 0; return -1; }
     if (tid < 32) {
@@ -461,7 +476,7 @@ __device__ __forceinline__ int cta_pre_process(const CandParams& cp, WarpScratch
 template <int WS, int NW>
 __device__ __forceinline__ int cta_post_process(const CandParams& cp, WarpScratch& ws, CellCta& cs, float* tex, V4 X, V4 N, int& nv, int wslot) {
     const Params& p = cp.p;
-    const int tid = threadIdx.x;
+    const int tid = (int)threadIdx.x;
     if (nv < p.min_image_num) return -1;                                                                // :261
     if (tid < 32) {
         const int m = warp_get_mask(p, X, tid);                                                         // :265
@@ -504,7 +519,7 @@ template <int NW>
 __device__ __forceinline__ float cta_compute_gain(const StoreParams& sp, CellCta& cs, const PGeo& me, float ncc, const PatchLists& pl, const Overlay& ov) {
     const StoreDev& st = sp.st;
     const Params& p = sp.cp.p;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tot = pl.nimg + pl.nvimg;
     for (int i = warp; i < tot; i += NW) {
         const bool isv = i >= pl.nimg;
@@ -539,7 +554,7 @@ __device__ __forceinline__ int cta_find_neighbors(const StoreParams& sp, CellCta
                                                   const Overlay& ov, int* out) {
     const StoreDev& st = sp.st;
     const Params& p = sp.cp.p;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float u1 = __int_as_float(0x7f800000), u2 = u1;
     float usum = 0.0f;
     for (int i = 0; i < pl.nimg; ++i) {                                 // Propagate::computeRadius (propagate.cpp:474-481)
@@ -658,7 +673,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_cells(const __grid_constant_
     const CandParams& cp = sp.cp;
     const Params& p = cp.p;
     const StoreDev& st = sp.st;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wslot = sa.wslot_base + blockIdx.x;              // this CTA's slice of the pairwise / findNeighbors scratch
     const int inc = sa.inc;
     const int maxp = sp.max_patches_cell;

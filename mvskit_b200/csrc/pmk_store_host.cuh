@@ -134,8 +134,8 @@ int store_init(pmk_ctx* ctx) {
         return rc;
     CandParams cp;
     if ((rc = cand_params(ctx, cp, 0))) return rc;                       // sizes cand_grid and the pairwise scratch
-    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * 2 * NB_STRIDE))) return rc;
-    CUDA_TRY(cudaMemsetAsync(s->nb_scratch, 0, (size_t)ctx->cand_grid * CAND_WARPS * 2 * NB_STRIDE * sizeof(int), ctx->stream));
+    if ((rc = dalloc(ctx, &s->nb_scratch, (size_t)ctx->cand_grid * CAND_WARPS * NB_STRIDE))) return rc;
+    CUDA_TRY(cudaMemsetAsync(s->nb_scratch, 0, (size_t)ctx->cand_grid * CAND_WARPS * NB_STRIDE * sizeof(int), ctx->stream));
     s->gather_bytes = (size_t)d.cap * d.maxv * sizeof(int);
     s->gather_bytes = std::max(s->gather_bytes, (size_t)d.cap * sizeof(float4));
     CUDA_TRY(cudaMalloc(&s->gather_tmp, s->gather_bytes));
@@ -410,6 +410,7 @@ int launch_cells(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& a) {
         CUDA_TRY(cudaFuncSetAttribute(k4_cells<WS, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cells<WS, NW, MINB>, NW * 32, csmem));
         if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k4_cells does not fit on an SM");
+        if (getenv("PMK_VERBOSE")) fprintf(stderr, "pmk: k4_cells<%d,%d,%d> %zu B smem, %d CTAs/SM\n", WS, NW, MINB, csmem, per_sm);
         if (getenv("PMK_CELL_MAXCTA")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("PMK_CELL_MAXCTA"))));    // experiment: unloaded latency
     }
     const int cgrid = std::max(1, std::min(a.ntasks, std::min(ctx->sm_count * per_sm, ctx->cand_grid * CAND_WARPS)));
@@ -421,55 +422,21 @@ template <int WS>
 int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     pmk_store* s = ctx->store;
     cudaStream_t st = ctx->stream;
-    const size_t smem = CAND_WARPS * (sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellShared));
-    const int cpc = CAND_WARPS / sa.wpc;
-    const int grid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks + cpc - 1) / cpc));
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(s->step_max, 0, sizeof(unsigned long long), st));
-    int rc_cells = 0;
-    static const int use_v1 = getenv("PMK_SWEEP_V1") ? 1 : 0;      // A/B switch while the CTA-per-cell kernel is being validated
-    if (sa.ntasks > 0 && !use_v1) {
-        // one CTA per dest cell, handed out longest-first through SC_NEXT (pmk_cell.cuh)
-        SweepArgs a = sa;
-        a.heavy_slot = s->max_tasks;
-        a.wslot_base = 0;
-        a.range_sel = 0;
-        k4_plan<<<1, 1024, 0, st>>>(sp, a, s->order);
+    if (sa.ntasks > 0) {
+        // longest-first order (k4_plan), then one CTA per dest cell, handed out through SC_NEXT (pmk_cell.cuh)
+        k4_plan<<<1, 1024, 0, st>>>(sp, sa, s->order);
         CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_NEXT, 0, sizeof(int), st));
+        // PMK_CELL_WARPS / PMK_CELL_MINB: tuning knobs (warps per CTA, CTAs per SM the kernel is compiled for); defaults measured best
         static const int nw_env = getenv("PMK_CELL_WARPS") ? atoi(getenv("PMK_CELL_WARPS")) : 8;
         static const int minb_env = getenv("PMK_CELL_MINB") ? atoi(getenv("PMK_CELL_MINB")) : 3;
-        if (nw_env == 12) rc_cells = launch_cells<WS, 12, 2>(ctx, sp, a);
-        else if (nw_env == 4) rc_cells = minb_env >= 6 ? launch_cells<WS, 4, 6>(ctx, sp, a) : launch_cells<WS, 4, 4>(ctx, sp, a);
-        else if (minb_env == 4) rc_cells = launch_cells<WS, 8, 4>(ctx, sp, a);
-        else if (minb_env == 5) rc_cells = launch_cells<WS, 8, 5>(ctx, sp, a);
-        else rc_cells = launch_cells<WS, 8, 3>(ctx, sp, a);
+        int rc_cells;
+        if (nw_env == 4) rc_cells = minb_env >= 5 ? launch_cells<WS, 4, 5>(ctx, sp, sa) : launch_cells<WS, 4, 4>(ctx, sp, sa);
+        else if (minb_env == 4) rc_cells = launch_cells<WS, 8, 4>(ctx, sp, sa);
+        else rc_cells = launch_cells<WS, 8, 3>(ctx, sp, sa);
         if (rc_cells) return rc_cells;
         ctx->launches += 2;
-    } else if (sa.ntasks > 0) {
-        SweepArgs a = sa;
-        a.heavy_slot = s->max_tasks;
-        a.wslot_base = 0;
-        k4_plan<<<1, 1024, 0, st>>>(sp, a, s->order);
-        ctx->launches++;
-        if (a.wpc > 1 || sa.split == 0) {                 // narrow step (or splitting disabled): one launch
-            a.range_sel = 0;
-            k4_sweep<WS><<<grid, CAND_WARPS * 32, smem, st>>>(sp, a);
-            ctx->launches++;
-        } else {
-            // wide step: the dest cells with many tries (they end the step) get four warps each on the context stream, the rest
-            // one warp each on a second stream; both read the same snapshot and stage into disjoint slots
-            CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
-            CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_fork, 0));
-            a.range_sel = 1; a.wpc = 4;
-            k4_sweep<WS><<<std::max(1, std::min(ctx->cand_grid, sa.ntasks)), CAND_WARPS * 32, smem, st>>>(sp, a);
-            static const int light_wpc = getenv("PMK_LIGHT_WPC") ? atoi(getenv("PMK_LIGHT_WPC")) : 2;
-            a.range_sel = 2; a.wpc = (light_wpc == 2 || light_wpc == 4) ? light_wpc : 1; a.wslot_base = ctx->cand_grid * CAND_WARPS;
-            const int lgrid = std::max(1, std::min(ctx->cand_grid, (sa.ntasks * a.wpc + CAND_WARPS - 1) / CAND_WARPS));
-            k4_sweep<WS><<<lgrid, CAND_WARPS * 32, smem, ctx->s_in>>>(sp, a);
-            CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->s_in));
-            CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-            ctx->launches += 2;
-        }
     }
     k_fold_step<<<1, 1, 0, st>>>(s->stats, s->step_max);
     if (s->nranks <= 1) {
@@ -513,6 +480,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     sa.jitter_mode = ctx->cfg.jitter_mode;
     for (int i = 0; i < 4; ++i) sa.jitter[i] = s->jitter[i];
     if (force) sa.force = *force;
+    sa.wslot_base = 0;
     sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order; sa.step_max = s->step_max; sa.cell_ns = s->cell_ns; sa.phase_ns = s->phase_ns;
     int max_steps = 0;
     for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
@@ -540,19 +508,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
         sa.g_off[sa.ngroup] = sa.ntasks;
         if (sa.ntasks <= 0 && s->nranks <= 1) continue;
         if (sa.ntasks > s->max_tasks) return fail(PMK_ERR_CAPACITY, "pmk: sweep step exceeds the staging capacity");
-        // warps per dest cell: a step ends with its slowest cell, so narrow steps put 4 (or 2) warps on each cell (speculative tries,
-        // in-order commit); wide steps already fill the machine with one warp per cell
         {
-            static const int forced = getenv("PMK_SWEEP_WPC") ? atoi(getenv("PMK_SWEEP_WPC")) : 0;
-            const int resident = ctx->sm_count * PMK_SWEEP_MINB * CAND_WARPS;        // warps in flight
-            sa.wpc = sa.ntasks * 4 <= resident ? 4 : (sa.ntasks * 2 <= resident ? 2 : 1);
-            if (forced == 1 || forced == 2 || forced == 4) sa.wpc = forced;
-            static const int nosplit = getenv("PMK_SWEEP_NOSPLIT") ? 1 : 0;
-            sa.split = nosplit ? 0 : 1;
-            static const int heavy_est = getenv("PMK_HEAVY_EST") ? atoi(getenv("PMK_HEAVY_EST")) : 16;
-            sa.heavy_est = heavy_est;
-            static const int coop = getenv("PMK_SWEEP_COOP") ? atoi(getenv("PMK_SWEEP_COOP")) : 2;
-            sa.coop = coop;
             static const int room_weight = getenv("PMK_ROOM_WEIGHT") ? atoi(getenv("PMK_ROOM_WEIGHT")) : 2;
             sa.room_weight = room_weight;
         }
