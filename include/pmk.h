@@ -243,6 +243,9 @@ int pmk_store_checksum(pmk_ctx* ctx, uint64_t* out2);       /* {order-independen
  *   cell     : PatchManager::setGrids index + in-grid flag (patch_manager.cpp:223-249) -> ixy2, ok */
 int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const float* normal4,
               float* project3, float* unit1, float* px4, float* py4, int* cell_ixy2, int* cell_ok);
+/* Camera::unproject (image/camera.cpp:329-337) at the working level, as Propagate::generatePatch uses it (propagate.cpp:224-226):
+ * icoord3 = depth * (u, v, 1); coord4_out = (M^-1 (icoord - p4), 1). */
+int pmk_probe_unproject(pmk_ctx* ctx, int n, const int* view, const float* icoord3, float* coord4_out);
 
 /* PmMvps::isNeighbor (pmmvps.cpp:117-147; hunit NULL: computed from the two reference views as in :117-121) and isNeighborRadius
  * (:149-180; radius non-NULL) on n free-standing pairs.  A patch is 10 floats: coord4, normal4, m_dscale, (float)m_images[0]. */

@@ -2,6 +2,7 @@
 //
 // Host-side float math in this file (camera constants, level table) follows the same operation order as
 // the reference; the file is compiled with -Xcompiler -ffp-contract=off so x86 never fuses it.
+#include <chrono>
 #include <cmath>
 #include <climits>
 #include <cstdio>
@@ -372,6 +373,8 @@ void pmk_destroy(pmk_ctx* ctx) {
     for (cudaEvent_t e : ctx->ev_k) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->store && ctx->store->adj) cudaFree(ctx->store->adj);
+    if (ctx->store && ctx->store->h_hdr) cudaFreeHost(ctx->store->h_hdr);
     delete ctx->store;
     delete ctx;
 }
@@ -848,6 +851,24 @@ int pmk_probe(pmk_ctx* ctx, int n, const int* view, const float* coord4, const f
 }
 
 // ---- candidate entry points (host pointers in, host pointers out) ----------------------------------------------------
+int pmk_probe_unproject(pmk_ctx* ctx, int n, const int* view, const float* icoord3, float* coord4_out) {
+    if (!ctx || !view || !icoord3 || !coord4_out) return fail(PMK_ERR_ARG, "pmk_probe_unproject: null argument");
+    if (n <= 0) return PMK_OK;
+    for (int i = 0; i < n; ++i) if (view[i] < 0 || view[i] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_unproject: view out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    const size_t N = (size_t)n;
+    void *dv, *di, *dout;
+    if ((rc = stage_in(ctx, 0, view, N * 4, &dv)) || (rc = stage_in(ctx, 1, icoord3, N * 12, &di)) || (rc = stage_in(ctx, 2, nullptr, N * 16, &dout))) return rc;
+    k_probe_unproject<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->params, n, (const int*)dv, (const float*)di, (float4*)dout);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(coord4_out, dout, N * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
 int pmk_set_inccs(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* views, const int* nviews, int stride,
                   int robust, int pairwise, float* out) {
     if (!ctx || !coord4 || !normal4 || !views || !nviews || !out) return fail(PMK_ERR_ARG, "pmk_set_inccs: null argument");
@@ -1344,6 +1365,10 @@ int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16) {
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(ctx->store->stats, 0, SS_COUNT * sizeof(uint64_t), ctx->stream));
     const int group = ctx->store->group;
+    {   // multi-GPU: re-cut the row bands from where the patches are now (no-op on one GPU)
+        StoreParams sp;
+        if ((rc = store_check_overflow(ctx)) || (rc = store_params(ctx, sp, seed)) || (rc = balance_bands(ctx, sp))) return rc;
+    }
     for (int image = 0; image < ctx->cfg.nviews; image += group) {                        // propagate.cpp:73, `group` views at a time
         if ((rc = sweep_views(ctx, iter, image, std::min(group, ctx->cfg.nviews - image), 0, 1 << 30, seed))) return rc;
         if ((rc = store_check_overflow(ctx))) return rc;
@@ -1388,11 +1413,24 @@ int pmk_filter(pmk_ctx* ctx, int* counts6) {
     int rc = store_init(ctx);
     if (rc) return rc;
     int c[6] = {0, 0, 0, 0, 0, 0};
+    static const bool verbose = getenv("PMK_VERBOSE") != nullptr;
+    auto now = [&]() { cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
+    auto t0 = verbose ? now() : std::chrono::steady_clock::time_point();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        const auto t1 = now();
+        fprintf(stderr, "pmk_filter: %-22s %8.2f ms (%d patches)\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count(), ctx->store->n);
+        t0 = t1;
+    };
     if ((rc = store_rebuild(ctx, 0))) return rc;                     // filter.cpp:26
+    lap("rebuild(0)");
     c[0] = ctx->store->n;
+    static const char* names[5] = {"", "filterOutside", "filterExact", "filterNeighbor", "filterSmallGroups"};
     for (int stage = 1; stage <= 4; ++stage) {                       // filterOutside, filterExact, filterNeighbor(1), filterSmallGroups
         if ((rc = filter_stage(ctx, stage, &c[stage]))) return rc;
+        lap(names[stage]);
         if ((rc = store_rebuild(ctx, 1))) return rc;                 // filter.cpp:31,36,41,46
+        lap("rebuild(1)");
     }
     c[5] = ctx->store->n;
     if (counts6) std::memcpy(counts6, c, sizeof(c));
@@ -1427,6 +1465,7 @@ int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128) {
     pmk_store* s = ctx->store;
     if (s->nccl_comm) return fail(PMK_ERR_STATE, "pmk_comm_init: communicator already set");
     s->rank = rank; s->nranks = nranks;
+    s->band.clear();
     if (nranks == 1) return PMK_OK;
     if (!id128) return fail(PMK_ERR_ARG, "pmk_comm_init: null id");
     NcclApi* api = nccl_api();
@@ -1441,8 +1480,10 @@ int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128) {
     s->ml.rec_cap = std::max(1024, std::min(16384, s->max_tasks * 4));
     s->ml.rec_words = 16 + 4 * s->d.maxv;
     if ((rc = dalloc(ctx, &s->msg, s->ml.words())) || (rc = dalloc(ctx, &s->all_msgs, s->ml.words() * nranks)) ||
-        (rc = dalloc(ctx, &s->pack_ids, s->ml.rec_cap)) || (rc = dalloc(ctx, &s->rec_base, 2 * nranks + 4)))
+        (rc = dalloc(ctx, &s->pack_ids, s->ml.rec_cap)) || (rc = dalloc(ctx, &s->rec_base, 2 * nranks + 4)) || (rc = dalloc(ctx, &s->all_hdr, 4 * nranks)))
         return rc;
+    if (!s->h_hdr) CUDA_TRY(cudaMallocHost((void**)&s->h_hdr, 4 * 64 * sizeof(int)));
+    s->ml.stride = s->ml.words();
     const size_t nrec = (size_t)nranks * s->ml.rec_cap;
     if ((rc = dalloc(ctx, &s->mg_keys, nrec)) || (rc = dalloc(ctx, &s->mg_keys2, nrec)) || (rc = dalloc(ctx, &s->mg_vals, nrec)) || (rc = dalloc(ctx, &s->mg_vals2, nrec)))
         return rc;
@@ -1463,6 +1504,7 @@ int pmk_comm_destroy(pmk_ctx* ctx) {
         s->nccl_comm = nullptr;
     }
     s->rank = 0; s->nranks = 1;
+    s->band.clear();
     return PMK_OK;
 }
 

@@ -794,12 +794,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_cells(const __grid_constant_
                 // ---- generatePatch (propagate.cpp:220-237) ----
                 const ViewConst& vr = p.views[sref];
                 const float depth = dot4(ld4(vr.oaxis), sX);
-                const float b0 = xsub(xmul(depth, ic.x), vr.P[3]), b1 = xsub(xmul(depth, ic.y), vr.P[7]), b2 = xsub(xmul(depth, ic.z), vr.P[11]);
-                V4 X, N = sN;                                                              // Camera::unproject (camera.cpp:329-337)
-                X.x = xadd(xadd(xmul(vr.Minv[0], b0), xmul(vr.Minv[1], b1)), xmul(vr.Minv[2], b2));
-                X.y = xadd(xadd(xmul(vr.Minv[4], b0), xmul(vr.Minv[5], b1)), xmul(vr.Minv[6], b2));
-                X.z = xadd(xadd(xmul(vr.Minv[8], b0), xmul(vr.Minv[9], b1)), xmul(vr.Minv[10], b2));
-                X.w = 1.0f;
+                V4 X = unproject_rows(vr.P, vr.Minv, V3{xmul(depth, ic.x), xmul(depth, ic.y), xmul(depth, ic.z)});         // Camera::unproject (camera.cpp:329-337)
+                V4 N = sN;
                 if (warp == 0) {                                                           // setGridsImages (patch_manager.cpp:223-239)
                     int nv0 = 0;
                     for (int base = 0; base < snv; base += 32) {

@@ -120,6 +120,19 @@ __device__ __forceinline__ V3 project(const Proj& P, V4 X) {
     return r;
 }
 
+// ---- Camera::unproject (camera.cpp:329-337) at the working level: M^-1 (icoord - p4), icoord = depth * (u, v, 1) -------------------
+// Minv is the host's adjugate / determinant inverse of P[:, :3] (the definition the oracle's Matrix3f::inverse shim uses).
+struct ViewConst;
+__device__ __forceinline__ V4 unproject_rows(const float* __restrict__ P, const float* __restrict__ Minv, V3 ic) {
+    const float b0 = xsub(ic.x, P[3]), b1 = xsub(ic.y, P[7]), b2 = xsub(ic.z, P[11]);
+    V4 X;
+    X.x = xadd(xadd(xmul(Minv[0], b0), xmul(Minv[1], b1)), xmul(Minv[2], b2));
+    X.y = xadd(xadd(xmul(Minv[4], b0), xmul(Minv[5], b1)), xmul(Minv[6], b2));
+    X.z = xadd(xadd(xmul(Minv[8], b0), xmul(Minv[9], b1)), xmul(Minv[10], b2));
+    X.w = 1.0f;
+    return X;
+}
+
 // ---- Photo::getMask(coord, m_level) (photo.cpp:44-52) -> Image::getMask(fx, fy, level) (image.cpp:749-781) ------------
 // -1: the view has no mask, or the rounded pixel lies outside the image; else the mask value (0 outside / 255 inside).
 // The reference converts floorf(f + 0.5f) to int first (x86: INT_MIN for NaN and out-of-range, i.e. "outside"); comparing the

@@ -228,6 +228,55 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k9_group_edges(const StorePar
     }
 }
 
+// ---- Filter::filterSmallGroups' labelling (filter.cpp:455-473) on the device ------------------------------------------------------------
+// The reference labels breadth-first in m_ppatches order over a DIRECTED relation (a patch's neighbours are looked up in the grid of
+// ITS reference view only): for pid = 0, 1, ...: if unlabelled, start a group and claim everything reachable that is still unlabelled.
+// Reachability is transitive, so the patch that ends up labelling v is m(v) = the smallest id among all patches that can reach v
+// (v included): nobody smaller reaches m(v), hence it is still unlabelled at its turn and starts a group; no earlier group start
+// reaches v.  label(v) = min over ancestors is the fixed point of  L[v] = min(L[v], L[u]) over edges u -> v,  which shortcutting
+// L[v] = L[L[v]] (valid because L[v] reaches v and L[L[v]] reaches L[v]) brings down to a few rounds.  Groups, sizes and therefore
+// the removals are exactly the reference's; only the group numbers differ (seed ids instead of consecutive integers).
+__global__ void k9_label_init(int n, int* __restrict__ L) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) L[q] = q;
+}
+// one warp per source patch u: push L[u] along its out-edges
+__global__ void k9_label_relax(int n, const int* __restrict__ offs, const int* __restrict__ adj, int* __restrict__ L, int* __restrict__ changed) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    bool any = false;
+    for (int u = gwarp; u < n; u += nwarps) {
+        const int lu = L[u];
+        for (int k = offs[u] + lane; k < offs[u + 1]; k += 32) {
+            const int v = adj[k];
+            if (lu < L[v]) { atomicMin(L + v, lu); any = true; }
+        }
+    }
+    if (__any_sync(0xffffffffu, any) && lane == 0) *changed = 1;
+}
+__global__ void k9_label_jump(int n, int* __restrict__ L, int* __restrict__ changed) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int l = L[q];
+    int ll = L[l];
+    if (ll < l) {
+        while (ll < l) { l = ll; ll = L[l]; }
+        L[q] = l;
+        *changed = 1;
+    }
+}
+__global__ void k9_group_sizes(const StoreDev st, int n, const int* __restrict__ L, int* __restrict__ size) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n && st.state[q] == 1) atomicAdd(size + L[q], 1);
+}
+__global__ void k9_group_flags(const StoreDev st, int n, const int* __restrict__ L, const int* __restrict__ size, int threshold, int* __restrict__ flags, int* __restrict__ removed) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int f = (st.state[q] == 1 && size[L[q]] < threshold) ? 1 : 0;
+    flags[q] = f;
+    if (f) atomicAdd(removed, 1);
+}
+
 // PatchManager::writePly colour (patch_manager.cpp:566-581): mean over m_images of Image::getColor at the projection, rounded
 __global__ void k_patch_colors(const StoreParams sp, int n, const int* __restrict__ perm, unsigned char* __restrict__ rgb) {
     const StoreDev& st = sp.st;

@@ -352,4 +352,13 @@ __global__ void k_probe(const Params p, int n, const int* __restrict__ view, con
     }
 }
 
+// Camera::unproject (camera.cpp:329-337) at the working level, one thread per point: the routine Propagate::generatePatch goes through
+__global__ void k_probe_unproject(const Params p, int n, const int* __restrict__ view, const float* __restrict__ icoord3, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ViewConst& vc = p.views[view[i]];
+    const V4 X = unproject_rows(vc.P, vc.Minv, V3{icoord3[3 * i], icoord3[3 * i + 1], icoord3[3 * i + 2]});
+    out[i] = make_float4(X.x, X.y, X.z, X.w);
+}
+
 }  // namespace pmk

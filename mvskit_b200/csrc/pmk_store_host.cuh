@@ -32,15 +32,20 @@ struct pmk_store {
     void* gather_tmp = nullptr; size_t gather_bytes = 0;
     float* f_tmp = nullptr; int* i_tmp = nullptr; int* i_tmp2 = nullptr; int* i_tmp3 = nullptr;
     int* nb_scratch = nullptr;
+    int* adj = nullptr; size_t adj_cap = 0;   // filterSmallGroups: directed neighbour lists (CSR values), grown on demand
     int* small = nullptr;               // a few device ints for results
     float jitter[4];
     // multi-GPU exchange of the step mutations (pmk_comm_init)
     void* nccl_comm = nullptr;
-    pmk::MsgLayout ml = {0, 0, 0};
+    pmk::MsgLayout ml = {0, 0, 0, 0};
     int* msg = nullptr; int* all_msgs = nullptr; int* pack_ids = nullptr; int* rec_base = nullptr;
+    int* all_hdr = nullptr; int* h_hdr = nullptr;      // the ranks' 4-word message headers: device copy, pinned host copy
     unsigned long long* mg_keys = nullptr; unsigned long long* mg_keys2 = nullptr; int* mg_vals = nullptr; int* mg_vals2 = nullptr;
     void* mg_cub = nullptr; size_t mg_cub_bytes = 0;
     bool canonical = false;             // patch ids are the reference's m_ppatches indices (collect order, no holes)
+    std::vector<int> band;              // multi-GPU: band[v * (nranks + 1) + r] = first cell row of rank r in view v (balance_bands)
+    std::vector<int> row_base;          // first entry of view v in the per-row work histogram
+    int* row_base_d = nullptr; int* rows_d = nullptr;
 };
 
 namespace {
@@ -280,7 +285,8 @@ int kill_flagged(pmk_ctx* ctx, const float* gains, const int* flags, int* killed
     return PMK_OK;
 }
 
-// Filter::filterSmallGroups (filter.cpp:432-525): edges on the device, breadth-first labelling on the host in id order
+// Filter::filterSmallGroups (filter.cpp:432-525): directed isNeighbor edges (k9_group_edges), then the reference's order-dependent
+// labelling as a min-ancestor fixed point on the device (k9_label_*, pmk_filter.cuh) -- no adjacency ever leaves the GPU
 int small_groups(pmk_ctx* ctx, const StoreParams& sp, int* flags_dev, int* removed) {
     pmk_store* s = ctx->store;
     const int n = s->n;
@@ -293,45 +299,43 @@ int small_groups(pmk_ctx* ctx, const StoreParams& sp, int* flags_dev, int* remov
     CUDA_TRY(cudaMemsetAsync(s->i_tmp + n, 0, sizeof(int), st));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->cub_tmp, s->cub_bytes, s->i_tmp, s->i_tmp2, n + 1, st));
     ctx->launches++;
-    std::vector<int> offs(n + 1);
-    CUDA_TRY(cudaMemcpyAsync(offs.data(), s->i_tmp2, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int nedges = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nedges, s->i_tmp2 + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    const int nedges = offs[n];
-    int* adj_d = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&adj_d, std::max(nedges, 1) * sizeof(int)));
-    k9_group_edges<<<grid, CAND_WARPS * 32, 0, st>>>(sp, n, 1, nullptr, s->i_tmp2, adj_d);
-    ctx->launches++;
-    std::vector<int> adj(std::max(nedges, 1));
-    cudaError_t e = cudaMemcpyAsync(adj.data(), adj_d, (size_t)nedges * sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(adj_d);
-    if (e != cudaSuccess) return fail(PMK_ERR_CUDA, std::string("small_groups: ") + cudaGetErrorString(e));
-    std::vector<int> label(n, -1), queue;
-    queue.reserve(n);
-    int id = -1;
-    for (int pid = 0; pid < n; ++pid) {
-        if (label[pid] != -1) continue;
-        label[pid] = ++id;
-        queue.clear();
-        queue.push_back(pid);
-        for (size_t h = 0; h < queue.size(); ++h) {
-            const int cur = queue[h];
-            for (int k = offs[cur]; k < offs[cur + 1]; ++k) {
-                const int q = adj[k];
-                if (label[q] != -1) continue;
-                label[q] = id;
-                queue.push_back(q);
-            }
-        }
+    if ((size_t)nedges > s->adj_cap) {                       // adjacency buffer, grown on demand and kept
+        if (s->adj) CUDA_TRY(cudaFree(s->adj));
+        s->adj = nullptr; s->adj_cap = 0;
+        const size_t cap = (size_t)nedges + (size_t)nedges / 4 + 1024;
+        CUDA_TRY(cudaMalloc((void**)&s->adj, cap * sizeof(int)));
+        s->adj_cap = cap;
     }
-    ++id;
-    std::vector<int> size(id, 0);
-    for (int pid = 0; pid < n; ++pid) ++size[label[pid]];
+    k9_group_edges<<<grid, CAND_WARPS * 32, 0, st>>>(sp, n, 1, nullptr, s->i_tmp2, s->adj);
+    ctx->launches++;
+    int* L = s->i_tmp3;                                        // labels; i_tmp (degrees) becomes the group sizes afterwards
+    const int tb = (n + 255) / 256;
+    k9_label_init<<<tb, 256, 0, st>>>(n, L);
+    ctx->launches++;
+    const int rgrid = std::max(1, std::min(ctx->sm_count * 8, (n + 7) / 8));
+    for (int round = 0; round < 4096; ++round) {
+        CUDA_TRY(cudaMemsetAsync(s->small, 0, sizeof(int), st));
+        k9_label_relax<<<rgrid, 256, 0, st>>>(n, s->i_tmp2, s->adj, L, s->small);
+        k9_label_jump<<<tb, 256, 0, st>>>(n, L, s->small);
+        ctx->launches += 2;
+        int changed = 0;
+        CUDA_TRY(cudaMemcpyAsync(&changed, s->small, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (!changed) break;
+    }
     const int threshold = std::max(20, n / 10000);
-    std::vector<int> flags(n, 0);
-    for (int pid = 0; pid < n; ++pid) if (size[label[pid]] < threshold) { flags[pid] = 1; ++*removed; }
-    CUDA_TRY(cudaMemcpyAsync(flags_dev, flags.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(s->i_tmp, 0, (size_t)n * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(s->small, 0, sizeof(int), st));
+    k9_group_sizes<<<tb, 256, 0, st>>>(s->d, n, L, s->i_tmp);
+    k9_group_flags<<<tb, 256, 0, st>>>(s->d, n, L, s->i_tmp, threshold, s->i_tmp2, s->small);
+    ctx->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(flags_dev, s->i_tmp2, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(removed, s->small, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
     return PMK_OK;
 }
 
@@ -405,14 +409,17 @@ int launch_cells(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& a) {
     typedef CellGeom<WS, NW> Gm;
     const size_t csmem = ((sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellCta) + 15) & ~(size_t)15) +
                          (size_t)Gm::nslots(ctx->params.tau) * Gm::SLOT * sizeof(float);
-    static int per_sm = 0;
-    if (!per_sm) {
-        CUDA_TRY(cudaFuncSetAttribute(k4_cells<WS, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cells<WS, NW, MINB>, NW * 32, csmem));
-        if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k4_cells does not fit on an SM");
-        if (getenv("PMK_VERBOSE")) fprintf(stderr, "pmk: k4_cells<%d,%d,%d> %zu B smem, %d CTAs/SM\n", WS, NW, MINB, csmem, per_sm);
-        if (getenv("PMK_CELL_MAXCTA")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("PMK_CELL_MAXCTA"))));    // experiment: unloaded latency
+    // the slot count depends on tau (a context property): opt in to the largest size once, ask the occupancy for the size at hand
+    static bool attr_done = false;
+    if (!attr_done) {
+        const size_t cmax = ((sizeof(WarpScratch) + sizeof(SweepScratch) + sizeof(CellCta) + 15) & ~(size_t)15) + (size_t)Gm::nslots(PMK_MAX_TAU) * Gm::SLOT * sizeof(float);
+        CUDA_TRY(cudaFuncSetAttribute(k4_cells<WS, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmax));
+        attr_done = true;
     }
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cells<WS, NW, MINB>, NW * 32, csmem));
+    if (per_sm < 1) return fail(PMK_ERR_CUDA, "pmk: k4_cells does not fit on an SM");
+    if (getenv("PMK_VERBOSE")) { static bool said = false; if (!said) { said = true; fprintf(stderr, "pmk: k4_cells<%d,%d,%d> %zu B smem, %d CTAs/SM\n", WS, NW, MINB, csmem, per_sm); } }
     const int cgrid = std::max(1, std::min(a.ntasks, std::min(ctx->sm_count * per_sm, ctx->cand_grid * CAND_WARPS)));
     k4_cells<WS, NW, MINB><<<cgrid, NW * 32, csmem, ctx->stream>>>(sp, a);
     return PMK_OK;
@@ -428,13 +435,8 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
         // longest-first order (k4_plan), then one CTA per dest cell, handed out through SC_NEXT (pmk_cell.cuh)
         k4_plan<<<1, 1024, 0, st>>>(sp, sa, s->order);
         CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_NEXT, 0, sizeof(int), st));
-        // PMK_CELL_WARPS / PMK_CELL_MINB: tuning knobs (warps per CTA, CTAs per SM the kernel is compiled for); defaults measured best
-        static const int nw_env = getenv("PMK_CELL_WARPS") ? atoi(getenv("PMK_CELL_WARPS")) : 8;
-        static const int minb_env = getenv("PMK_CELL_MINB") ? atoi(getenv("PMK_CELL_MINB")) : 3;
-        int rc_cells;
-        if (nw_env == 4) rc_cells = minb_env >= 5 ? launch_cells<WS, 4, 5>(ctx, sp, sa) : launch_cells<WS, 4, 4>(ctx, sp, sa);
-        else if (minb_env == 4) rc_cells = launch_cells<WS, 8, 4>(ctx, sp, sa);
-        else rc_cells = launch_cells<WS, 8, 3>(ctx, sp, sa);
+        // 8 warps per CTA, 3 CTAs per SM (80 registers): measured best on config 2 against 4 / 12 / 16 warps and 2 / 4 / 5 CTAs per SM
+        const int rc_cells = launch_cells<WS, 8, 3>(ctx, sp, sa);
         if (rc_cells) return rc_cells;
         ctx->launches += 2;
     }
@@ -448,10 +450,21 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
         // pack this rank's mutations, all-gather over NVLink, apply every rank's in rank order
         NcclApi* api = nccl_api();
         if (!api || !s->nccl_comm) return fail(PMK_ERR_STATE, "pmk: multi-GPU sweep without a communicator (pmk_comm_init)");
-        k4_pack_scan<<<1, 32, 0, st>>>(sp, s->task_new, sa.ntasks, s->rem_list, s->ml, s->msg, s->pack_ids);
+        k4_pack_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->rem_list, s->ml, s->msg, s->pack_ids);
         k4_pack_copy<<<ctx->sm_count, 128, 0, st>>>(sp, sa, s->ml, s->msg, s->pack_ids);
-        const ncclResult_t nr = api->AllGather(s->msg, s->all_msgs, s->ml.words(), ncclInt32, (ncclComm_t)s->nccl_comm, st);
+        k_stamp<<<1, 1, 0, st>>>(s->step_max + 1);
+        // headers first: every rank learns how much the others produced, the payload gather then moves max-over-ranks words
+        ncclResult_t nr = api->AllGather(s->msg, s->all_hdr, 4, ncclInt32, (ncclComm_t)s->nccl_comm, st);
         if (nr != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nr) : "error"));
+        CUDA_TRY(cudaMemcpyAsync(s->h_hdr, s->all_hdr, (size_t)s->nranks * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        size_t need = 4;
+        for (int r = 0; r < s->nranks; ++r) need = std::max(need, (size_t)4 + (size_t)s->h_hdr[4 * r + 1] + (size_t)s->h_hdr[4 * r] * s->ml.rec_words);
+        need = std::min((need + 255) & ~(size_t)255, s->ml.words());
+        s->ml.stride = need;
+        nr = api->AllGather(s->msg, s->all_msgs, need, ncclInt32, (ncclComm_t)s->nccl_comm, st);
+        if (nr != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nr) : "error"));
+        k_fold_exchange<<<1, 1, 0, st>>>(s->stats, s->step_max + 1, (unsigned long long)(need + 4) * 4ull * s->nranks);
         k4_unpack_remove<<<ctx->sm_count, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks);
         const int nrec = s->nranks * s->ml.rec_cap;
         k4_unpack_keys<<<(nrec + 255) / 256, 256, 0, st>>>(s->ml, s->all_msgs, s->nranks, s->mg_keys, s->mg_vals);
@@ -464,6 +477,53 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     return PMK_OK;
 }
 
+// Multi-GPU partition of a sweep: every rank owns a band of cell rows of every view.  Equal bands leave most ranks idle when the
+// surface covers part of the image (round 1: 0.8 % of the calls on rank 0 of 8), so the bands are cut where the cumulative number
+// of live patches per (reference view, row) -- the sources of the propagatePatch calls -- reaches r / nranks of the view's total;
+// half of the weight stays uniform so that empty regions are still spread out.  Every rank holds the same store, hence computes the
+// same cuts; the result of a sweep does not depend on the cuts at all (ids follow the global task order).
+int balance_bands(pmk_ctx* ctx, const StoreParams& sp) {
+    pmk_store* s = ctx->store;
+    const int nv = ctx->cfg.nviews, nr = s->nranks;
+    s->band.assign((size_t)nv * (nr + 1), 0);
+    for (int v = 0; v < nv; ++v)
+        for (int r = 0; r <= nr; ++r) s->band[(size_t)v * (nr + 1) + r] = (int)((long long)ctx->h_views[v].gh * r / nr);
+    static const int balanced = getenv("PMK_EQUAL_BANDS") ? 0 : 1;
+    if (nr <= 1 || !balanced || s->n <= 0) return PMK_OK;
+    if (s->row_base.empty()) {
+        s->row_base.assign(nv + 1, 0);
+        for (int v = 0; v < nv; ++v) s->row_base[v + 1] = s->row_base[v] + ctx->h_views[v].gh;
+        int rc;
+        if ((rc = dalloc(ctx, &s->row_base_d, nv + 1)) || (rc = dalloc(ctx, &s->rows_d, s->row_base[nv]))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s->row_base_d, s->row_base.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int total_rows = s->row_base[nv];
+    CUDA_TRY(cudaMemsetAsync(s->rows_d, 0, (size_t)total_rows * sizeof(int), ctx->stream));
+    k_row_work<<<(s->n + 255) / 256, 256, 0, ctx->stream>>>(sp, s->n, s->row_base_d, s->rows_d);
+    ctx->launches++;
+    std::vector<int> rows(total_rows);
+    CUDA_TRY(cudaMemcpyAsync(rows.data(), s->rows_d, (size_t)total_rows * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int v = 0; v < nv; ++v) {
+        const int gh = ctx->h_views[v].gh;
+        const int* w = rows.data() + s->row_base[v];
+        long long tot = 0;
+        for (int y = 0; y < gh; ++y) tot += w[y];
+        if (tot <= 0) continue;
+        // weight of row y = w[y] / tot / 2 + 1 / gh / 2, in integer arithmetic: 2 * tot * gh units in all
+        const long long unit_u = tot, unit_w = gh;                  // row y carries w[y] * gh + tot units
+        long long acc = 0;
+        int r = 1;
+        for (int y = 0; y < gh && r < nr; ++y) {
+            acc += (long long)w[y] * unit_w + unit_u;
+            while (r < nr && acc * nr >= 2 * tot * gh * (long long)r) { s->band[(size_t)v * (nr + 1) + r] = y + 1; ++r; }
+        }
+        for (; r < nr; ++r) s->band[(size_t)v * (nr + 1) + r] = gh;
+        s->band[(size_t)v * (nr + 1) + nr] = gh;
+    }
+    return PMK_OK;
+}
+
 // Wavefront steps [step_first, step_first + step_count) of Propagate::propagatePmImage for views [img_first, img_first + nimg):
 // step k carries anti-diagonal k (from the far corner on odd iterations, propagate.cpp:80-86) of every view of the group.
 // (rank, nranks): this GPU only takes the dest cells whose row lies in its band of each view's grid (multi-GPU partition).
@@ -473,6 +533,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     int rc = store_params(ctx, sp, seed);
     if (rc) return rc;
     if (nimg > GROUP_MAX) return fail(PMK_ERR_ARG, "pmk: sweep group too large");
+    if (s->band.size() != (size_t)ctx->cfg.nviews * (s->nranks + 1) && (rc = balance_bands(ctx, sp))) return rc;
     const int inc = (iter % 2 == 1) ? -1 : 1;
     SweepArgs sa;
     std::memset(&sa, 0, sizeof(sa));
@@ -493,7 +554,7 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
             if (k >= ndiag) continue;
             const int d = inc > 0 ? k : ndiag - 1 - k;
             // rows of this rank's band
-            const int ylo = (int)((long long)gh * s->rank / s->nranks), yhi = (int)((long long)gh * (s->rank + 1) / s->nranks);
+            const int ylo = s->band[(size_t)(img_first + g) * (s->nranks + 1) + s->rank], yhi = s->band[(size_t)(img_first + g) * (s->nranks + 1) + s->rank + 1];
             const int gxlo = std::max(0, d - gh + 1), gxhi = std::min(gw - 1, d);             // the whole anti-diagonal
             int xlo = std::max(gxlo, d - yhi + 1), xhi = std::min(gxhi, d - ylo);             // this rank's band of it
             if (only_x >= 0) { xlo = std::max(xlo, only_x); xhi = std::min(xhi, only_x); }   // a single dest cell (pmk_propagate_forced)

@@ -19,7 +19,8 @@
 namespace pmk {
 
 enum SweepStat { SS_CALLS = 0, SS_TRIES, SS_GEN_NULL, SS_NCC_LOSE, SS_FAIL0, SS_FAIL1, SS_ADDED, SS_REPLACED, SS_TRIMMED, SS_EVALS,
-                 SS_CELL_NS, SS_STEP_MAX_NS, SS_STEPS, SS_COOP_CELLS, SS_COOP_REFINES, SS_COUNT = 16 };   // ..., summed dest-cell time, summed per-step slowest cell, steps
+                 SS_CELL_NS, SS_STEP_MAX_NS, SS_STEPS, SS_NCCL_NS, SS_MSG_BYTES, SS_COUNT = 16 };   // ..., summed dest-cell time, summed per-step slowest cell,
+                                                                                                 // steps, time inside the step exchanges (multi-GPU), bytes gathered
 
 constexpr int GROUP_MAX = 128;         // views whose wavefronts one step can carry
 constexpr int LKEEP = 40;              // entries of a cell list the sweep keeps (MAX_NUM_OF_PATCHES <= 32, plus slack)
@@ -253,6 +254,15 @@ __global__ void k_fold_step(unsigned long long* stats, const unsigned long long*
     stats[SS_STEPS] += 1;
 }
 
+// multi-GPU: time stamps around a step's exchange (device clock, on the stream) and the bytes it gathered
+__global__ void k_stamp(unsigned long long* t) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*t)); }
+__global__ void k_fold_exchange(unsigned long long* stats, const unsigned long long* t0, unsigned long long bytes) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    stats[SS_NCCL_NS] += now - *t0;
+    stats[SS_MSG_BYTES] += bytes;
+}
+
 // ---- apply: removals ---------------------------------------------------------------------------------------------------------------
 // PatchManager::removePatch (patch_manager.cpp:303-325): erase the patch from every cell it is registered in.  One warp per patch.
 __device__ __forceinline__ void erase_from_cell(const StoreDev& st, int c, int entry) {
@@ -420,9 +430,11 @@ __global__ void k4_apply_add(const StoreParams sp, const int* __restrict__ task_
 // Multi-GPU: the store is replicated, the dest cells of a step are partitioned by row band, and the step's mutations
 // (new patches, removals) travel between the ranks as one fixed-layout message per rank (ncclAllGather over NVLink).
 // Every rank then applies ALL messages in rank order, so ids, creation numbers and grids stay identical everywhere.
-//   message = int hdr[4] {n_new, n_rem, overflow, 0} | int rem[rem_cap] | rec[rec_cap][16 + 4 * maxv]
+//   message = int hdr[4] {n_new, n_rem, overflow, 0} | int rem[n_rem] | rec[n_new][16 + 4 * maxv]      (compact: only what the step produced)
 //   record  = coord4, normal4, scal4 (as int bits), nimg, nvimg, global task index, slot in the task,
 //             images[maxv], cells[maxv], vimages[maxv], vcells[maxv]
+// The ranks first gather their 4-word headers; the host reads them and gathers max-over-ranks words of payload, so a step moves what
+// it produced instead of the worst case (34 MB per rank at 128 views).
 // Final ids and creation numbers are assigned in (global task, slot) order -- the order the single-GPU scan uses -- so an
 // N-GPU run produces the single-GPU store bit for bit.
 // =====================================================================================================================
@@ -430,27 +442,34 @@ namespace pmk {
 
 struct MsgLayout {
     int rem_cap, rec_cap, rec_words;
-    __host__ __device__ size_t words() const { return 4 + (size_t)rem_cap + (size_t)rec_cap * rec_words; }
+    size_t stride;                       // words between two ranks' messages in the gathered buffer (set per step)
+    __host__ __device__ size_t words() const { return 4 + (size_t)rem_cap + (size_t)rec_cap * rec_words; }        // capacity of one message
+    __device__ const int* msg_of(const int* all, int rk) const { return all + (size_t)rk * stride; }
+    __device__ static const int* rec_of(const int* msg, int r, int rec_words) { return msg + 4 + msg[1] + (size_t)r * rec_words; }
 };
 
-// one thread: list the staged patches that survived the step, fill the header
-__global__ void k4_pack_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, const int* __restrict__ rem_list, MsgLayout ml,
-                             int* __restrict__ msg, int* __restrict__ pack_ids) {
+// one block: list the staged patches that survived the step (any order: the receivers sort by (task, slot)), copy the removals, fill the header
+__global__ void __launch_bounds__(1024) k4_pack_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, const int* __restrict__ rem_list, MsgLayout ml,
+                                                     int* __restrict__ msg, int* __restrict__ pack_ids) {
     const StoreDev& st = sp.st;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int n = 0, over = 0;
-    for (int t = 0; t < ntasks; ++t) {
+    __shared__ int s_n, s_over;
+    if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntasks; t += blockDim.x) {
         const int k = task_new[t];
         for (int j = 0; j < k; ++j) {
             const int sid = st.cap + t * NEW_MAX + j;
             if (st.state[sid] != 1) continue;
-            if (n < ml.rec_cap) pack_ids[n++] = sid; else over = 1;
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < ml.rec_cap) pack_ids[pos] = sid; else s_over = 1;
         }
     }
+    __syncthreads();
     int nrem = st.counters[SC_REM];
-    if (nrem > ml.rem_cap) { nrem = ml.rem_cap; over = 1; }
-    msg[0] = n; msg[1] = nrem; msg[2] = over; msg[3] = 0;
-    for (int i = 0; i < nrem; ++i) msg[4 + i] = rem_list[i];
+    if (nrem > ml.rem_cap) { nrem = ml.rem_cap; if (threadIdx.x == 0) s_over = 1; }
+    for (int i = threadIdx.x; i < nrem; i += blockDim.x) msg[4 + i] = rem_list[i];
+    __syncthreads();
+    if (threadIdx.x == 0) { msg[0] = min(s_n, ml.rec_cap); msg[1] = nrem; msg[2] = s_over; msg[3] = 0; }
 }
 
 __global__ void k4_pack_copy(const StoreParams sp, const SweepArgs sa, MsgLayout ml, int* __restrict__ msg, const int* __restrict__ pack_ids) {
@@ -460,7 +479,7 @@ __global__ void k4_pack_copy(const StoreParams sp, const SweepArgs sa, MsgLayout
     const int n = msg[0];
     for (int r = gwarp; r < n; r += nwarps) {
         const int sid = pack_ids[r];
-        int* rec = msg + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
+        int* rec = msg + 4 + msg[1] + (size_t)r * ml.rec_words;
         if (lane == 0) {
             const float4 c = st.coord[sid], m = st.normal[sid], s = st.scal[sid];
             rec[0] = __float_as_int(c.x); rec[1] = __float_as_int(c.y); rec[2] = __float_as_int(c.z); rec[3] = __float_as_int(c.w);
@@ -485,7 +504,7 @@ __global__ void k4_unpack_remove(const StoreParams sp, MsgLayout ml, const int* 
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int rk = 0; rk < nranks; ++rk) {
-        const int* msg = all + (size_t)rk * ml.words();
+        const int* msg = ml.msg_of(all, rk);
         const int nrem = msg[1];
         for (int r = gwarp; r < nrem; r += nwarps) {
             const int id = msg[4 + r];
@@ -509,10 +528,10 @@ __global__ void k4_unpack_keys(MsgLayout ml, const int* __restrict__ all, int nr
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nranks * ml.rec_cap) return;
     const int rk = i / ml.rec_cap, r = i % ml.rec_cap;
-    const int* msg = all + (size_t)rk * ml.words();
+    const int* msg = ml.msg_of(all, rk);
     unsigned long long k = ~0ull;
     if (r < msg[0]) {
-        const int* rec = msg + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
+        const int* rec = MsgLayout::rec_of(msg, r, ml.rec_words);
         k = (unsigned long long)(unsigned int)rec[14] * NEW_MAX + (unsigned int)rec[15];
     }
     keys[i] = k;
@@ -525,7 +544,7 @@ __global__ void k4_unpack_scan(const StoreParams sp, MsgLayout ml, const int* __
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int total = 0;
     for (int rk = 0; rk < nranks; ++rk) {
-        const int* msg = all + (size_t)rk * ml.words();
+        const int* msg = ml.msg_of(all, rk);
         if (msg[2]) atomicAdd(st.counters + SC_OVERFLOW, 1);
         total += msg[0];
     }
@@ -548,7 +567,7 @@ __global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __r
     for (int pos = gwarp; pos < take; pos += nwarps) {
         const int i = sorted_vals[pos];
         const int rk = i / ml.rec_cap, r = i % ml.rec_cap;
-        const int* rec = all + (size_t)rk * ml.words() + 4 + ml.rem_cap + (size_t)r * ml.rec_words;
+        const int* rec = MsgLayout::rec_of(ml.msg_of(all, rk), r, ml.rec_words);
         const int fid = n0 + pos, mv = st.maxv;
         const int ni = rec[12], nv = rec[13];
         if (lane == 0) {
@@ -563,6 +582,17 @@ __global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __r
         warp_register_patch(sp, fid, deep, deep, lane);
         __syncwarp();
     }
+}
+
+// Multi-GPU load balance: propagatePatch calls come from patches whose reference view is the swept view, so the live patches per
+// (reference view, cell row) estimate the work of that row.  rows[row_base[v] + y] += 1 per live patch.
+__global__ void k_row_work(const StoreParams sp, int n, const int* __restrict__ row_base, int* __restrict__ rows) {
+    const StoreDev& st = sp.st;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || st.state[q] != 1 || st.nimg[q] < 1) return;
+    const int v = st.images[(size_t)q * st.maxv];
+    const int y = cell_y(st.cells[(size_t)q * st.maxv]);
+    if (y >= 0 && y < sp.cp.p.views[v].gh) atomicAdd(rows + row_base[v] + y, 1);
 }
 
 // order-independent digest of the live store (replica consistency checks): sum over patches of a hash of coord, ncc and lists

@@ -317,6 +317,13 @@ class Context:
         _chk(lib().pmk_probe(self.h, n, _p(view), _p(coord), _p(normal), _p(proj), _p(unit), _p(px), _p(py), _p(ixy), _p(ok)))
         return dict(project=proj, unit=unit, px=px, py=py, cell=ixy, cell_ok=ok)
 
+    def probe_unproject(self, view, icoord3) -> np.ndarray:
+        """Camera::unproject (camera.cpp:329-337) at the working level."""
+        view, icoord3 = np.ascontiguousarray(view, np.int32), np.ascontiguousarray(icoord3, np.float32)
+        out = np.empty((len(view), 4), np.float32)
+        _chk(lib().pmk_probe_unproject(self.h, len(view), _p(view), _p(icoord3), _p(out)))
+        return out
+
     # -- device patch store, sweep and filters ----------------------------------------------------------------
     def store_clear(self):
         _chk(lib().pmk_store_clear(self.h))
@@ -358,7 +365,7 @@ class Context:
         _chk(lib().pmk_store_colors(self.h, n, _p(out)))
         return out
 
-    SWEEP_STATS = ("calls", "tries", "gen_null", "ncc_lose", "fail0", "fail1", "added", "replaced", "trimmed", "evals", "cell_ns", "step_max_ns", "steps", "coop_cells", "coop_refines")
+    SWEEP_STATS = ("calls", "tries", "gen_null", "ncc_lose", "fail0", "fail1", "added", "replaced", "trimmed", "evals", "cell_ns", "step_max_ns", "steps", "nccl_ns", "msg_bytes")
 
     def propagate(self, it: int, seed: int) -> dict:
         """Propagate::run(iter)."""

@@ -409,13 +409,19 @@ class Scene:
         return coord, normal, vw, nviews
 
     # -- seed patches (ply/00000000.patch) ----------------------------------------------------------
-    def seeds(self, stride: int = 4, seed: int = 42, depth_noise: float = 0.005, normal_noise_deg: float = 10.0, max_images: int = 12):
+    def seeds(self, stride: int = 4, seed: int = 42, depth_noise: float = 0.005, normal_noise_deg: float = 10.0, max_images: int = 12,
+              views: Optional[List[int]] = None):
+        """Seed patches around ground truth, one per `stride`-th cell of every view.  views = None: one random stream over all views
+        in order (configs 1 and 2 as used since round 1).  views = [...]: only those views, each with its OWN stream (seed, view) --
+        what the parallel generator for the big configs uses, so the result does not depend on how the views are split up."""
         rng = np.random.RandomState(seed)
         sc = 1 << self.level
         gw = (self.width // sc + self.csize - 1) // self.csize
         gh = (self.height // sc + self.csize - 1) // self.csize
         recs = []
-        for v in range(self.nviews):
+        for v in (range(self.nviews) if views is None else views):
+            if views is not None:
+                rng = np.random.RandomState((seed * 7919 + 104729 * (v + 1)) % (2 ** 31))
             cx, cy = np.meshgrid(np.arange(6, gw - 6, stride), np.arange(6, gh - 6, stride))
             cx, cy = cx.ravel().astype(np.float64), cy.ravel().astype(np.float64)
             u1 = (self.csize * (2 * cx + 1) - 1) / 2.0
@@ -439,9 +445,51 @@ class Scene:
         return recs
 
 
-def seed_arrays(scene: "Scene", **kw):
+def _render_job(args):
+    config, scale, nviews, views = args
+    sc = make_scene(config, scale=scale, nviews=nviews)
+    sc.render(views=views)
+    return [(v, sc.images[v]) for v in views]
+
+
+def _seed_job(args):
+    config, scale, nviews, views, kw = args
+    return make_scene(config, scale=scale, nviews=nviews).seeds(views=views, **kw)
+
+
+def _pool_map(fn, jobs, procs):
+    if procs <= 1 or len(jobs) <= 1:
+        return [fn(j) for j in jobs]
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(min(procs, len(jobs))) as pool:
+        return pool.map(fn, jobs)
+
+
+def render_views(config: int, scale: float, views: List[int], procs: int, nviews: Optional[int] = None):
+    """[(view, image)] for `views`, rendered by `procs` processes (every view renders independently and deterministically)."""
+    procs = max(1, min(procs, len(views)))
+    jobs = [(config, scale, nviews, views[i::procs]) for i in range(procs)]
+    return [vi for part in _pool_map(_render_job, jobs, procs) for vi in part]
+
+
+def seed_records(config: int, scale: float, views: List[int], procs: int, nviews: Optional[int] = None, **kw):
+    """Scene.seeds(views=...) over `procs` processes; records come back grouped by view in ascending view order."""
+    procs = max(1, min(procs, len(views)))
+    chunks = [views[i::procs] for i in range(procs)]
+    parts = _pool_map(_seed_job, [(config, scale, nviews, ch, kw) for ch in chunks], procs)
+    # each chunk's records are in its own view order; regroup into ascending view order
+    by_view = {}
+    for ch, recs in zip(chunks, parts):
+        ref_of = [r[3][0] for r in recs]
+        for v in ch:
+            by_view[v] = [r for r, rv in zip(recs, ref_of) if rv == v]
+    return [r for v in sorted(by_view) for r in by_view[v]]
+
+
+def seed_arrays(scene: "Scene", recs=None, **kw):
     """scene.seeds() as the record arrays pmk_store_add takes: coord4, normal4, scal4 = (ncc 1, dscale, 0, 0), images, nimages."""
-    recs = scene.seeds(**kw)
+    if recs is None:
+        recs = scene.seeds(**kw)
     n, V = len(recs), scene.nviews
     coord, normal, scal = np.ones((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
     images, nimg = np.zeros((n, V), np.int32), np.zeros(n, np.int32)

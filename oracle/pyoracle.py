@@ -105,6 +105,7 @@ class RefLib:
         L.pmref_init(prefix.encode(), option.encode())
         self.nviews, self.level, self.csize, self.wsize, self.tau, self.min_image_num = (L.pmref_info(i) for i in range(6))
         self.nlevels = L.pmref_info(7)
+        self.init_thresholds = [float(L.pmref_threshold(i)) for i in range(9)]      # as PmMvps::init left them (pmmvps.cpp:52-67)
 
     # -- scalars ---------------------------------------------------------------------------------
     def threshold(self, what: int) -> float:
@@ -112,6 +113,9 @@ class RefLib:
 
     def set_depth(self, d: int):
         self.L.pmref_set_depth(d)
+
+    def update_threshold(self):
+        self.L.pmref_update_threshold()
 
     def set_ncc_thresholds(self, ncc: float, before: float):
         self.L.pmref_set_ncc_thresholds(C.c_float(ncc), C.c_float(before))

@@ -120,6 +120,8 @@ float pmref_threshold(int what) {
 }
 
 void pmref_set_depth(int depth) { g_pm->m_depth = depth; }
+// PmMvps::updateThreshold (pmmvps.cpp:70-74), the reference's own
+void pmref_update_threshold(void) { g_pm->updateThreshold(); }
 void pmref_set_ncc_thresholds(float ncc, float before) { g_pm->m_nccThreshold = ncc; g_pm->m_nccThresholdBefore = before; }
 
 void pmref_image_dims(int view, int level, int* w, int* h) {

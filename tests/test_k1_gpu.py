@@ -64,6 +64,23 @@ def test_building_blocks_bit_exact(ctx, coracle, hyps):
     assert np.array_equal(got["cell_ok"], ok)
 
 
+def test_unproject_bit_exact(ctx, coracle, reflib, hyps, small_scene):
+    """Camera::unproject (camera.cpp:329-337) as Propagate::generatePatch drives it (propagate.cpp:224-226): depth * (u, v, 1) of a
+    pixel of the reference view back to 3-D -- against the C restatement AND against the compiled reference itself."""
+    c, n, vw, nv = hyps
+    v0 = vw[:, 0].copy()
+    rng = np.random.RandomState(11)
+    depth = rng.uniform(1.0, 6.0, len(v0)).astype(np.float32)
+    uv = np.stack([rng.uniform(-20, small_scene.width // 2 + 20, len(v0)), rng.uniform(-20, small_scene.height // 2 + 20, len(v0)), np.ones(len(v0))], 1).astype(np.float32)
+    ic = (uv * depth[:, None]).astype(np.float32)                     # float32 products, as `depth * icoord` in the reference
+    got = ctx.probe_unproject(v0, ic)
+    assert_bits_equal(got, coracle.unproject(v0, ic), "unproject vs the C restatement")
+    assert_bits_equal(got, reflib.unproject(v0, ic), "unproject vs libpmref.so")
+    # round trip: the projection of the unprojected point is the pixel again (float32 tolerance)
+    back = ctx.probe(v0, got)["project"]
+    assert np.abs(back[:, :2] - uv[:, :2]).max() < 2e-2
+
+
 def test_cells_behind_camera_and_negative(ctx, coracle, small_scene):
     # points behind the camera hit the (-65535,-65535,-1) sentinel; points just left of the image exercise the
     # truncating integer division quirk (patch_manager.cpp:230-233): x in (-csize-0.5, -0.5) -> cell 0

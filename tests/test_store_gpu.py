@@ -473,3 +473,63 @@ def test_check_on_free_standing_candidates(ctx, reflib, populated, small_scene):
     assert np.abs(gain - rgain).max() <= 1e-5, np.abs(gain - rgain).max()         # computeGain
     assert 50 < rret.sum() < 550, rret.sum()                                       # both outcomes occur
     assert same_ret >= 590, same_ret                                               # gain sign exact; quad fit tolerance-bound
+
+
+def test_filter_small_groups_given_the_reference_state(ctx, reflib, populated):
+    """filterSmallGroups in isolation and UNCONDITIONALLY (round-1 review: the staged test only compared it when both sides happened to
+    enter stage 4 with the same count).  Both sides are re-loaded from the reference's own state after filterOutside + filterExact +
+    filterNeighbor; the directed neighbour relation and the order-dependent labelling are integer work, so the removals must be
+    IDENTICAL.  A few isolated patches are appended so that groups below the size threshold exist."""
+    import copy
+    g = populated
+    reflib.set_ncc_thresholds(0.7, 0.4)
+    _load_both(ctx, reflib, g, 1)
+    reflib.filter_rebuild(0)
+    for stage in (1, 2, 3):
+        reflib.stage_begin(); reflib.filter_stage(stage)
+        reflib.filter_rebuild(1)
+    n0 = reflib.stage_begin()
+    rp = copy.deepcopy(reflib.get_patches())
+    # thin the store so that islands form: drop the patches of every third 8-cell-wide column band of their reference view
+    keep = np.ones(n0, bool)
+    for i in range(n0):
+        if (rp.grids[i, 0, 0] // 8) % 3 == 1 and (rp.grids[i, 0, 1] // 6) % 2 == 0:
+            keep[i] = False
+    for k in ("coord", "normal", "scal", "images", "nimages"):
+        setattr(rp, k, getattr(rp, k)[:n0][keep].copy())
+    rp.n = int(keep.sum())
+    _load_both(ctx, reflib, rp, 1)
+    reflib.filter_rebuild(0)
+    n = ctx.filter_rebuild(0)
+    assert n == rp.n == reflib.stage_begin()
+    assert_bits_equal(ctx.store_get().coord, reflib.get_patches().coord[:n], "collect order of the re-loaded store")
+    reflib.filter_stage(4)
+    ralive = reflib.stage_alive()
+    _, gflag, _, killed = ctx.filter_stage(4, n)
+    assert killed == int((gflag != 0).sum())
+    assert np.array_equal(gflag == 0, ralive == 1), (int((gflag != 0).sum()), int((ralive == 0).sum()), np.nonzero((gflag == 0) != (ralive == 1))[0][:10])
+    print("filterSmallGroups:", n, "patches,", killed, "removed on both sides")
+    assert 0 < killed < n                                        # small groups existed and were removed, big ones survived
+
+
+def test_thresholds_follow_the_reference(ctx, reflib):
+    """PmMvps::init's thresholds (pmmvps.cpp:32,54-67) and updateThreshold (:70-74) through pmk_get_thresholds, bit for bit."""
+    from mvskit_b200 import pmk
+    c = pmk.Context(nviews=reflib.nviews)
+    t = c.thresholds()
+    assert t.tau == reflib.tau
+    names = ("ncc_threshold", "ncc_threshold_before", "angle_threshold0", "angle_threshold1", "max_angle_threshold", "quad_threshold",
+             "neighbor_threshold", "neighbor_threshold1", "neighbor_threshold2")
+    ref = np.array(reflib.init_thresholds, np.float32)       # what the reference's PmMvps::init computed (pmmvps.cpp:52-67)
+    reflib.set_ncc_thresholds(float(ref[0]), float(ref[1]))  # other tests move the two NCC thresholds; start updateThreshold from init's
+    got = np.array([getattr(t, k) for k in names], np.float32)
+    assert_bits_equal(got, ref, "thresholds after init")
+    for step in range(3):                                    # PmMvps::run: updateThreshold after every Filter::run
+        c.update_threshold()
+        reflib.update_threshold()                            # the reference's own PmMvps::updateThreshold
+        ref = np.array([reflib.threshold(i) for i in range(9)], np.float32)
+        t = c.thresholds()
+        assert_bits_equal(np.array([getattr(t, k) for k in names], np.float32), ref, f"thresholds after updateThreshold #{step + 1}")
+        assert t.depth == step + 1
+    reflib.set_ncc_thresholds(0.7, 0.4)
+    c.close()
