@@ -259,6 +259,28 @@ int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs
 int pmk_probe_check(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages, int stride,
                     int* ret, float* gain, int* nneighbors, int* vimages_out, int* nvimages_out);
 
+/* ---- the rest of PatchManager's / Camera's public surface, for the host mirror's pass-throughs (mvskit_b200/host) ----------------
+ * Camera::setProjection for "CONTOUR2" camera files: 6 intrinsics {fx, fy, skew, cx, cy, -} and 6 extrinsics {Euler angles in degrees,
+ * translation} -> the level-0 3 x 4 projection K [R | t] (image/camera.cpp:116-131, quat2proj :241-261).  Host arithmetic only. */
+int pmk_contour2_to_projection(const float* intrinsics6, const float* extrinsics6, float* P12);
+/* PatchManager::isVisible0 (cell_ixy == NULL; the cells come back in cell_ixy_out) / isVisible (patch_manager.cpp:327-376) of n
+ * free-standing points {coord4, normal4} in view image[i], against the store's depth maps, with the given strictness. */
+int pmk_probe_visible(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* image, const int* cell_ixy, float strict,
+                      int* out, int* cell_ixy_out);
+/* PatchManager::setScales (patch_manager.cpp:378-399) for fresh patches: m_dscale, m_ascale from {coord4, images[n][stride], nimages}. */
+int pmk_probe_scales(pmk_ctx* ctx, int n, const float* coord4, const int* images, const int* nimages, int stride, float* dscale, float* ascale);
+/* PatchManager::findNeighbors(patch, neighbors, scale, margin) (patch_manager.cpp:671-728) for free-standing patches (scal4 = {ncc,
+ * dscale, ascale, -}): the neighbours' store ids in ascending order (ids_out[n][cap], first min(count, cap)) and their number. */
+int pmk_probe_neighbors(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages,
+                        int stride, float scale, int margin, int cap, int* ids_out, int* count_out);
+/* PatchManager::removePatch (patch_manager.cpp:303-325) for stored patches (ids in collect order, as pmk_store_get returns them). */
+int pmk_store_remove(pmk_ctx* ctx, int n, const int* ids);
+/* PatchManager::updateDepthMaps (patch_manager.cpp:191-221) for stored patches. */
+int pmk_store_update_depth_maps(pmk_ctx* ctx, int n, const int* ids);
+/* m_pgrids (which = 0) / m_vpgrids (1) of one view as CSR: offsets[cells + 1] and the patch ids of every cell in slot order.  ids may be
+ * NULL to ask for the total only (total_out). */
+int pmk_store_cell_ids(pmk_ctx* ctx, int view, int which, int* offsets, int* ids, int ids_cap, int* total_out);
+
 /* Profiling aid: nanoseconds the last sweep spent on every dest cell (all views, view-major, row-major cells).  The first call
  * (out may be NULL) switches the recording on; every later call returns and clears the times. */
 int pmk_debug_cell_times(pmk_ctx* ctx, float* out_total_cells);

@@ -383,7 +383,7 @@ static int set_view_impl(pmk_ctx* ctx, int view, const float* P, const uint8_t* 
     if (!ctx || !P || (!rgb && !on_device)) return fail(PMK_ERR_ARG, "pmk_set_view: null argument");
     if (view < 0 || view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_set_view: view out of range");
     const int nlevels = ctx->cfg.level + 3, level = ctx->cfg.level;
-    if (width < (16 << nlevels) / 2 || height < (16 << nlevels) / 2) return fail(PMK_ERR_ARG, "pmk_set_view: image too small for the pyramid");
+    if ((width >> (nlevels - 1)) < 8 || (height >> (nlevels - 1)) < 8) return fail(PMK_ERR_ARG, "pmk_set_view: image too small for the pyramid (the coarsest level must keep 8 pixels per side)");
     if (ctx->view_set[view]) return fail(PMK_ERR_STATE, "pmk_set_view: view already uploaded");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     ViewConst& vc = ctx->h_views[view];
@@ -1364,6 +1364,12 @@ int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16) {
     int rc = store_init(ctx);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(ctx->store->stats, 0, SS_COUNT * sizeof(uint64_t), ctx->stream));
+    if (getenv("PMK_VERBOSE") && !ctx->store->laps) {
+        if ((rc = dalloc(ctx, &ctx->store->laps, 17))) return rc;
+    }
+    if (ctx->store->laps) CUDA_TRY(cudaMemsetAsync(ctx->store->laps, 0, 17 * sizeof(unsigned long long), ctx->stream));
+    ctx->store->host_wait_s = 0.0; ctx->store->host_waits = 0;
+    const auto t_prop0 = std::chrono::steady_clock::now();
     const int group = ctx->store->group;
     {   // multi-GPU: re-cut the row bands from where the patches are now (no-op on one GPU)
         StoreParams sp;
@@ -1372,6 +1378,16 @@ int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16) {
     for (int image = 0; image < ctx->cfg.nviews; image += group) {                        // propagate.cpp:73, `group` views at a time
         if ((rc = sweep_views(ctx, iter, image, std::min(group, ctx->cfg.nviews - image), 0, 1 << 30, seed))) return rc;
         if ((rc = store_check_overflow(ctx))) return rc;
+    }
+    if (ctx->store->laps) {
+        unsigned long long l[16];
+        CUDA_TRY(cudaMemcpyAsync(l, ctx->store->laps, sizeof(l), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_prop0).count();
+        fprintf(stderr, "pmk_propagate[rank %d/%d] iter %d: wall %.3f s; stream laps (s): plan+sweep %.3f, apply %.3f, pack %.3f, header gather(+wait for ranks) %.3f, "
+                        "host trip + payload gather %.3f, removals %.3f, keys+sort %.3f, scan+add %.3f; host blocked %.3f s in %lld syncs\n",
+                ctx->store->rank, ctx->store->nranks, iter, wall, l[0] / 1e9, l[1] / 1e9, l[2] / 1e9, l[3] / 1e9, l[4] / 1e9, l[5] / 1e9, l[6] / 1e9, l[7] / 1e9,
+                ctx->store->host_wait_s, ctx->store->host_waits);
     }
     return read_stats(ctx, stats16);
 }
@@ -1458,7 +1474,7 @@ int pmk_comm_unique_id(char* id128) {
 }
 
 int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128) {
-    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return fail(PMK_ERR_ARG, "pmk_comm_init: bad argument");
+    if (!ctx || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return fail(PMK_ERR_ARG, "pmk_comm_init: bad argument (1 <= nranks <= 64)");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     int rc = store_init(ctx);
     if (rc) return rc;
@@ -1476,14 +1492,23 @@ int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128) {
     const ncclResult_t r = api->CommInitRank(&comm, nranks, id, rank);
     if (r != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
     s->nccl_comm = comm;
-    s->ml.rem_cap = 16384;
-    s->ml.rec_cap = std::max(1024, std::min(16384, s->max_tasks * 4));
+    // capacities of one rank's step message (the gather itself only moves what a step produced): a dest cell rarely stores more than
+    // two patches per step and trims a handful; 2 x / 8 x the widest step, bounded so that (1 + nranks) buffers stay below ~10 GB
+    s->ml.rec_cap = std::max(4096, std::min(1 << 18, s->max_tasks * 2));
+    s->ml.rem_cap = std::max(16384, std::min(1 << 20, s->max_tasks * 8));
     s->ml.rec_words = 16 + 4 * s->d.maxv;
     if ((rc = dalloc(ctx, &s->msg, s->ml.words())) || (rc = dalloc(ctx, &s->all_msgs, s->ml.words() * nranks)) ||
         (rc = dalloc(ctx, &s->pack_ids, s->ml.rec_cap)) || (rc = dalloc(ctx, &s->rec_base, 2 * nranks + 4)) || (rc = dalloc(ctx, &s->all_hdr, 4 * nranks)))
         return rc;
     if (!s->h_hdr) CUDA_TRY(cudaMallocHost((void**)&s->h_hdr, 4 * 64 * sizeof(int)));
     s->ml.stride = s->ml.words();
+    // NCCL sets its channels up on the first collective (hundreds of ms): pay that here, not inside the first wavefront step
+    CUDA_TRY(cudaMemsetAsync(s->msg, 0, 4 * sizeof(int), ctx->stream));
+    for (int warm = 0; warm < 2; ++warm) {
+        const ncclResult_t wr = api->AllGather(s->msg, s->all_hdr, 4, ncclInt32, comm, ctx->stream);
+        if (wr != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclAllGather (warm-up): ") + (api->GetErrorString ? api->GetErrorString(wr) : "error"));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     const size_t nrec = (size_t)nranks * s->ml.rec_cap;
     if ((rc = dalloc(ctx, &s->mg_keys, nrec)) || (rc = dalloc(ctx, &s->mg_keys2, nrec)) || (rc = dalloc(ctx, &s->mg_vals, nrec)) || (rc = dalloc(ctx, &s->mg_vals2, nrec)))
         return rc;
@@ -1550,6 +1575,179 @@ int pmk_probe_neighbor(pmk_ctx* ctx, int n, const float* lhs10, const float* rhs
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, dout, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+// ---- pass-throughs for the rest of PatchManager's public surface (mvskit_b200/host) --------------------------------------------------
+int pmk_contour2_to_projection(const float* intrinsics6, const float* extrinsics6, float* P12) {
+    if (!intrinsics6 || !extrinsics6 || !P12) return fail(PMK_ERR_ARG, "pmk_contour2_to_projection: null argument");
+    // Camera::setProjection, txtType 2 (camera.cpp:116-131) with Camera::quat2proj (:241-261); float arithmetic in the reference's
+    // order, 4 x 4 products summed left to right (the order the oracle's Matrix4f shim defines)
+    const float* in = intrinsics6; const float* q = extrinsics6;
+    const float K[4][4] = {{in[0], in[2], in[3], 0.0f}, {0.0f, in[1], in[4], 0.0f}, {0.0f, 0.0f, 1.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 1.0f}};
+    const float a = (float)(q[0] * M_PI / 180.0), b = (float)(q[1] * M_PI / 180.0), g = (float)(q[2] * M_PI / 180.0);
+    const float s1 = sinf(a), s2 = sinf(b), s3 = sinf(g), c1 = cosf(a), c2 = cosf(b), c3 = cosf(g);
+    float R[4][4];
+    R[0][0] = c2 * c3; R[0][1] = c3 * s2 * s1 - s3 * c1; R[0][2] = c3 * s2 * c1 + s3 * s1; R[0][3] = q[3];
+    R[1][0] = s3 * c2; R[1][1] = s3 * s2 * s1 + c3 * c1; R[1][2] = s3 * s2 * c1 - c3 * s1; R[1][3] = q[4];
+    R[2][0] = -s2;     R[2][1] = c2 * s1;                R[2][2] = c2 * c1;                R[2][3] = q[5];
+    R[3][0] = R[3][1] = R[3][2] = 0.0f; R[3][3] = 1.0f;
+    for (int y = 0; y < 3; ++y)
+        for (int x = 0; x < 4; ++x) {
+            float acc = K[y][0] * R[0][x];
+            acc = acc + K[y][1] * R[1][x];
+            acc = acc + K[y][2] * R[2][x];
+            acc = acc + K[y][3] * R[3][x];
+            P12[4 * y + x] = acc;
+        }
+    return PMK_OK;
+}
+
+int pmk_probe_visible(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const int* image, const int* cell_ixy, float strict, int* out, int* cell_ixy_out) {
+    if (!ctx || !coord4 || !normal4 || !image || !out) return fail(PMK_ERR_ARG, "pmk_probe_visible: null argument");
+    if (n <= 0) return PMK_OK;
+    for (int i = 0; i < n; ++i) if (image[i] < 0 || image[i] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_visible: image out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    const size_t N = (size_t)n;
+    void *dc, *dn, *di, *dcell = nullptr, *dout, *dco;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, image, N * 4, &di)) ||
+        (rc = stage_in(ctx, 3, nullptr, N * 4, &dout)) || (rc = stage_in(ctx, 4, nullptr, N * 8, &dco)))
+        return rc;
+    if (cell_ixy && (rc = stage_in(ctx, 5, cell_ixy, N * 8, &dcell))) return rc;
+    k_probe_visible<<<(n + 127) / 128, 128, 0, ctx->stream>>>(sp, n, (const float4*)dc, (const float4*)dn, (const int*)di, (const int*)dcell, strict, (int*)dout, (int*)dco);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cell_ixy_out) CUDA_TRY(cudaMemcpyAsync(cell_ixy_out, dco, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_probe_scales(pmk_ctx* ctx, int n, const float* coord4, const int* images, const int* nimages, int stride, float* dscale, float* ascale) {
+    if (!ctx || !coord4 || !images || !nimages || !dscale || !ascale) return fail(PMK_ERR_ARG, "pmk_probe_scales: null argument");
+    if (n <= 0) return PMK_OK;
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < std::min(nimages[i], stride); ++k)
+            if (images[(size_t)i * stride + k] < 0 || images[(size_t)i * stride + k] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_scales: image out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = upload_views(ctx);
+    if (rc) return rc;
+    CandParams cp;
+    if ((rc = cand_params(ctx, cp, 0))) return rc;
+    const size_t N = (size_t)n;
+    void *dc, *di, *dni, *dd, *da;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, images, N * stride * 4, &di)) || (rc = stage_in(ctx, 2, nimages, N * 4, &dni)) ||
+        (rc = stage_in(ctx, 3, nullptr, N * 4, &dd)) || (rc = stage_in(ctx, 4, nullptr, N * 4, &da)))
+        return rc;
+    k_probe_scales<<<std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS)), CAND_WARPS * 32, 0, ctx->stream>>>(cp, n, (const float4*)dc, (const int*)di, (const int*)dni, stride, (float*)dd, (float*)da);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dscale, dd, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ascale, da, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_probe_neighbors(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages, int stride,
+                        float scale, int margin, int cap, int* ids_out, int* count_out) {
+    if (!ctx || !coord4 || !normal4 || !scal4 || !images || !nimages || !ids_out || !count_out) return fail(PMK_ERR_ARG, "pmk_probe_neighbors: null argument");
+    if (n <= 0) return PMK_OK;
+    if (margin < 0 || margin > 2 || cap < 1) return fail(PMK_ERR_ARG, "pmk_probe_neighbors: margin must be 0..2 and cap >= 1");
+    for (int i = 0; i < n; ++i) {
+        if (nimages[i] < 1 || nimages[i] > stride) return fail(PMK_ERR_ARG, "pmk_probe_neighbors: bad image count");
+        for (int k = 0; k < nimages[i]; ++k) if (images[(size_t)i * stride + k] < 0 || images[(size_t)i * stride + k] >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_probe_neighbors: image out of range");
+    }
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    const size_t N = (size_t)n;
+    void *dc, *dn, *ds, *di, *dni, *dids, *dcnt;
+    if ((rc = stage_in(ctx, 0, coord4, N * 16, &dc)) || (rc = stage_in(ctx, 1, normal4, N * 16, &dn)) || (rc = stage_in(ctx, 2, scal4, N * 16, &ds)) ||
+        (rc = stage_in(ctx, 3, images, N * stride * 4, &di)) || (rc = stage_in(ctx, 4, nimages, N * 4, &dni)) || (rc = stage_in(ctx, 5, nullptr, N * cap * 4, &dids)) ||
+        (rc = stage_in(ctx, 6, nullptr, N * 4, &dcnt)))
+        return rc;
+    const int grid = std::max(1, std::min(ctx->cand_grid, (n + CAND_WARPS - 1) / CAND_WARPS));
+    k_probe_neighbors<<<grid, CAND_WARPS * 32, CAND_WARPS * 2 * CAND_MAXV * sizeof(int), ctx->stream>>>(sp, n, (const float4*)dc, (const float4*)dn, (const float4*)ds, (const int*)di,
+                                                                                                     (const int*)dni, stride, scale, margin, cap, (int*)dids, (int*)dcnt);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ids_out, dids, N * cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(count_out, dcnt, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return store_check_overflow(ctx);
+}
+
+int pmk_store_remove(pmk_ctx* ctx, int n, const int* ids) {
+    if (!ctx || (n > 0 && !ids)) return fail(PMK_ERR_ARG, "pmk_store_remove: null argument");
+    if (n <= 0) return PMK_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    if ((rc = store_check_overflow(ctx))) return rc;
+    for (int i = 0; i < n; ++i) if (ids[i] < 0 || ids[i] >= s->n) return fail(PMK_ERR_ARG, "pmk_store_remove: id out of range");
+    if (n > s->d.cap) return fail(PMK_ERR_ARG, "pmk_store_remove: too many ids");
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->rem_list, ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d.counters + SC_REM, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (n + 3) / 4)), 128, 0, ctx->stream>>>(sp, s->rem_list, s->d.cap);   // PatchManager::removePatch (patch_manager.cpp:303-325)
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    s->canonical = false;
+    return PMK_OK;
+}
+
+int pmk_store_update_depth_maps(pmk_ctx* ctx, int n, const int* ids) {
+    if (!ctx || (n > 0 && !ids)) return fail(PMK_ERR_ARG, "pmk_store_update_depth_maps: null argument");
+    if (n <= 0) return PMK_OK;
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    void* dids;
+    if ((rc = stage_in(ctx, 0, ids, (size_t)n * 4, &dids))) return rc;
+    k_store_update_depth<<<std::max(1, std::min(ctx->sm_count * 4, (n + 3) / 4)), 128, 0, ctx->stream>>>(sp, n, (const int*)dids);   // patch_manager.cpp:191-221
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMK_OK;
+}
+
+int pmk_store_cell_ids(pmk_ctx* ctx, int view, int which, int* offsets, int* ids, int ids_cap, int* total_out) {
+    if (!ctx || !offsets || !total_out) return fail(PMK_ERR_ARG, "pmk_store_cell_ids: null argument");
+    if (view < 0 || view >= ctx->cfg.nviews) return fail(PMK_ERR_ARG, "pmk_store_cell_ids: view out of range");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    pmk_store* s = ctx->store;
+    const int c0 = s->cell_base[view], nc = s->cell_base[view + 1] - c0;
+    if (nc + 1 > s->d.cap) return fail(PMK_ERR_CAPACITY, "pmk_store_cell_ids: scratch too small for this grid");
+    cudaStream_t st = ctx->stream;
+    k_store_cell_ids<<<(nc + 255) / 256, 256, 0, st>>>(s->d, c0, nc, which, 0, s->i_tmp, nullptr, nullptr);
+    CUDA_TRY(cudaMemsetAsync(s->i_tmp + nc, 0, sizeof(int), st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->cub_tmp, s->cub_bytes, s->i_tmp, s->i_tmp2, nc + 1, st));
+    CUDA_TRY(cudaMemcpyAsync(offsets, s->i_tmp2, (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int total = offsets[nc];
+    *total_out = total;
+    ctx->launches += 2;
+    if (!ids || total <= 0) return PMK_OK;
+    if (total > ids_cap) return fail(PMK_ERR_CAPACITY, "pmk_store_cell_ids: ids buffer too small (see total_out)");
+    if ((size_t)total * 4 > s->gather_bytes) return fail(PMK_ERR_CAPACITY, "pmk_store_cell_ids: scratch too small");
+    k_store_cell_ids<<<(nc + 255) / 256, 256, 0, st>>>(s->d, c0, nc, which, 1, nullptr, s->i_tmp2, (int*)s->gather_tmp);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ids, s->gather_tmp, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return PMK_OK;
 }
 

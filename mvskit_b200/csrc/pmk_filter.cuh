@@ -416,4 +416,97 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_probe_check(const StorePara
     }
 }
 
+// ---- probes behind the host mirror's PatchManager pass-throughs ------------------------------------------------------------------
+// PatchManager::isVisible0 / isVisible (patch_manager.cpp:327-376) for free-standing points against the store's depth maps;
+// cell_in == nullptr: isVisible0 (the cell is computed from the projection and returned in cell_out)
+__global__ void k_probe_visible(const StoreParams sp, int n, const float4* __restrict__ coord, const float4* __restrict__ normal, const int* __restrict__ image,
+                                const int* __restrict__ cell_in, float strict, int* __restrict__ out, int* __restrict__ cell_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V4 X = f4v(coord[i]), N = f4v(normal[i]);
+    int ix, iy, r;
+    if (cell_in) { ix = cell_in[2 * i]; iy = cell_in[2 * i + 1]; r = is_visible(sp, X, N, image[i], ix, iy, strict); }
+    else r = is_visible0(sp, X, N, image[i], ix, iy, strict);
+    out[i] = r;
+    if (cell_out) { cell_out[2 * i] = ix; cell_out[2 * i + 1] = iy; }
+}
+
+// PatchManager::setScales (patch_manager.cpp:378-399) for fresh patches (m_dscale starts at 0); one warp per patch
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_probe_scales(const CandParams cp, int n, const float4* __restrict__ coord, const int* __restrict__ images,
+                                                                  const int* __restrict__ nimg, int stride, float* __restrict__ dscale, float* __restrict__ ascale) {
+    __shared__ float tmp[CAND_WARPS][PMK_MAX_TAU + 1];
+    __shared__ int img[CAND_WARPS][PMK_MAX_TAU + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gwarp = blockIdx.x * CAND_WARPS + w;
+    for (int h = gwarp; h < n; h += gridDim.x * CAND_WARPS) {
+        const int nv = min(nimg[h], stride);
+        if (lane < min(nv, PMK_MAX_TAU)) img[w][lane] = images[(size_t)h * stride + lane];
+        __syncwarp();
+        float ds = 0.0f, as = 0.0f;
+        if (nv >= 1) warp_set_scales(cp.p, f4v(coord[h]), img[w], nv, ds, as, tmp[w], lane);
+        if (lane == 0) { dscale[h] = ds; ascale[h] = as; }
+        __syncwarp();
+    }
+}
+
+// PatchManager::findNeighbors (patch_manager.cpp:671-728) for free-standing patches {coord, normal, dscale, images}: ids of the
+// neighbours (store ids = m_ppatches indices after a rebuild), ascending, and their number
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_probe_neighbors(const StoreParams sp, int n, const float4* __restrict__ coord, const float4* __restrict__ normal,
+                                                                     const float4* __restrict__ scal, const int* __restrict__ images, const int* __restrict__ nimg, int stride,
+                                                                     float scale, int margin, int cap, int* __restrict__ ids_out, int* __restrict__ count_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* simg = reinterpret_cast<int*>(smem_raw) + (threadIdx.x >> 5) * 2 * CAND_MAXV;
+    int* cells = simg + CAND_MAXV;
+    const Params& p = sp.cp.p;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    const Overlay none{-1, nullptr, 0, nullptr, 0};
+    int* nb = sp.nb_scratch + (size_t)gwarp * NB_STRIDE;
+    for (int h = gwarp; h < n; h += gridDim.x * CAND_WARPS) {
+        const V4 X = f4v(coord[h]);
+        const int nv = min(min(nimg[h], stride), CAND_MAXV);
+        for (int i = lane; i < nv; i += 32) {
+            const int v = images[(size_t)h * stride + i];
+            simg[i] = v;
+            const V3 q = project(p.views[v].P, X);
+            cells[i] = pack_cell(cell_of(q.x, p.csize), cell_of(q.y, p.csize));
+        }
+        __syncwarp();
+        PGeo me; me.X = X; me.N = f4v(normal[h]); me.dscale = scal[h].y; me.ref = simg[0];
+        const PatchLists pl{simg, cells, nv, nullptr, nullptr, 0};
+        const int nn = warp_find_neighbors(sp, me, pl, scale, margin, none, nb, lane);
+        for (int k = lane; k < min(nn, cap); k += 32) ids_out[(size_t)h * cap + k] = nb[k];
+        if (lane == 0) count_out[h] = nn;
+        __syncwarp();
+    }
+}
+
+// PatchManager::updateDepthMaps (patch_manager.cpp:191-221) for stored patches; one warp per patch, lanes over the views
+__global__ void k_store_update_depth(const StoreParams sp, int n, const int* __restrict__ ids) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = gwarp; k < n; k += nwarps) {
+        const int id = ids[k];
+        if (id < 0 || id >= sp.st.cap || sp.st.state[id] != 1) continue;
+        const V4 X = f4v(sp.st.coord[id]);
+        for (int v = lane; v < sp.cp.p.nviews; v += 32) update_depth_map(sp, id, X, v);
+    }
+}
+
+// entries of the cells of one view, flattened: pass 0 counts per cell (which = 0: m_pgrids, 1: m_vpgrids), pass 1 writes ids at offs[cell]
+__global__ void k_store_cell_ids(const StoreDev st, int c0, int ncell, int which, int pass, int* __restrict__ count, const int* __restrict__ offs, int* __restrict__ ids) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int n = min(st.ccount[c0 + c], st.cell_cap);
+    int k = 0;
+    for (int s2 = 0; s2 < n; ++s2) {
+        const int e = st.cslots[(size_t)(c0 + c) * st.cell_cap + s2];
+        if ((e & 0x7fffffff) == SLOT_TOMB) continue;
+        if ((which != 0) != (e < 0)) continue;
+        if (pass) ids[offs[c] + k] = e & 0x7fffffff;
+        ++k;
+    }
+    if (!pass) count[c] = k;
+}
+
 }  // namespace pmk

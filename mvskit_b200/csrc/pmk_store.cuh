@@ -27,7 +27,7 @@ constexpr int NEW_MAX = 32;            // new patches one dest cell can stage in
 constexpr int SRC_MAX = 32;            // source patches feeding one dest cell (two cells of <= MAX_NUM_OF_PATCHES)
 constexpr int NB_CAP = 4096;           // findNeighbors scratch per warp (2 * NB_CAP ints: list + sort buffer)
 
-enum StoreCounter { SC_N = 0, SC_BIRTH = 1, SC_OVERFLOW = 2, SC_FULL = 3, SC_REM = 4, SC_NBOVER = 5, SC_NEXT = 6, SC_COUNT = 16 };   // SC_NEXT: work queue of a sweep step
+enum StoreCounter { SC_N = 0, SC_BIRTH = 1, SC_OVERFLOW = 2, SC_FULL = 3, SC_REM = 4, SC_NBOVER = 5, SC_NEXT = 6, SC_MSGOVER = 7, SC_COUNT = 16 };   // SC_NEXT: work queue of a sweep step
 
 struct StoreDev {
     int cap, stage_cap, maxv, cell_cap, total_cells;

@@ -39,6 +39,8 @@ struct pmk_store {
     void* nccl_comm = nullptr;
     pmk::MsgLayout ml = {0, 0, 0, 0};
     int* msg = nullptr; int* all_msgs = nullptr; int* pack_ids = nullptr; int* rec_base = nullptr;
+    unsigned long long* laps = nullptr;      // PMK_VERBOSE: [16] lap accumulators + [16] = last stamp
+    double host_wait_s = 0.0; long long host_waits = 0;
     int* all_hdr = nullptr; int* h_hdr = nullptr;      // the ranks' 4-word message headers: device copy, pinned host copy
     unsigned long long* mg_keys = nullptr; unsigned long long* mg_keys2 = nullptr; int* mg_vals = nullptr; int* mg_vals2 = nullptr;
     void* mg_cub = nullptr; size_t mg_cub_bytes = 0;
@@ -177,6 +179,7 @@ int store_check_overflow(pmk_ctx* ctx) {
     if (c[SC_OVERFLOW]) return fail(PMK_ERR_CAPACITY, "pmk: " + std::to_string(c[SC_OVERFLOW]) + " cell registrations dropped (raise pmk_config.cell_capacity)");
     if (c[SC_FULL]) return fail(PMK_ERR_CAPACITY, "pmk: patch store full, " + std::to_string(c[SC_FULL]) + " patches dropped (raise pmk_config.max_patches)");
     if (c[SC_NBOVER]) return fail(PMK_ERR_CAPACITY, "pmk: findNeighbors scratch overflow");
+    if (c[SC_MSGOVER]) return fail(PMK_ERR_CAPACITY, "pmk: a multi-GPU step produced more new patches / removals than one rank's message holds");
     return PMK_OK;
 }
 
@@ -431,6 +434,9 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     cudaStream_t st = ctx->stream;
     CUDA_TRY(cudaMemsetAsync(s->d.counters + SC_REM, 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(s->step_max, 0, sizeof(unsigned long long), st));
+    static const bool vlap = getenv("PMK_VERBOSE") != nullptr;
+#define PMK_LAP(slot) do { if (vlap && s->laps) k_lap<<<1, 1, 0, st>>>(s->laps, s->laps + 16, slot); } while (0)
+    PMK_LAP(-1);
     if (sa.ntasks > 0) {
         // longest-first order (k4_plan), then one CTA per dest cell, handed out through SC_NEXT (pmk_cell.cuh)
         k4_plan<<<1, 1024, 0, st>>>(sp, sa, s->order);
@@ -441,11 +447,13 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
         ctx->launches += 2;
     }
     k_fold_step<<<1, 1, 0, st>>>(s->stats, s->step_max);
+    PMK_LAP(0);                                   // plan + sweep kernel
     if (s->nranks <= 1) {
         k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
         k4_apply_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
         k4_apply_add<<<std::max(1, std::min(ctx->sm_count * 2, sa.ntasks)), 128, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
         ctx->launches += 3;
+        PMK_LAP(1);                               // apply (single GPU)
     } else {
         // pack this rank's mutations, all-gather over NVLink, apply every rank's in rank order
         NcclApi* api = nccl_api();
@@ -453,11 +461,13 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
         k4_pack_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->rem_list, s->ml, s->msg, s->pack_ids);
         k4_pack_copy<<<ctx->sm_count, 128, 0, st>>>(sp, sa, s->ml, s->msg, s->pack_ids);
         k_stamp<<<1, 1, 0, st>>>(s->step_max + 1);
+        PMK_LAP(2);                               // pack
         // headers first: every rank learns how much the others produced, the payload gather then moves max-over-ranks words
         ncclResult_t nr = api->AllGather(s->msg, s->all_hdr, 4, ncclInt32, (ncclComm_t)s->nccl_comm, st);
         if (nr != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nr) : "error"));
         CUDA_TRY(cudaMemcpyAsync(s->h_hdr, s->all_hdr, (size_t)s->nranks * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        PMK_LAP(3);                               // header all-gather (includes waiting for the slowest rank)
+        { const auto h0 = std::chrono::steady_clock::now(); CUDA_TRY(cudaStreamSynchronize(st)); s->host_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count(); s->host_waits++; }
         size_t need = 4;
         for (int r = 0; r < s->nranks; ++r) need = std::max(need, (size_t)4 + (size_t)s->h_hdr[4 * r + 1] + (size_t)s->h_hdr[4 * r] * s->ml.rec_words);
         need = std::min((need + 255) & ~(size_t)255, s->ml.words());
@@ -465,14 +475,24 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
         nr = api->AllGather(s->msg, s->all_msgs, need, ncclInt32, (ncclComm_t)s->nccl_comm, st);
         if (nr != ncclSuccess) return fail(PMK_ERR_CUDA, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nr) : "error"));
         k_fold_exchange<<<1, 1, 0, st>>>(s->stats, s->step_max + 1, (unsigned long long)(need + 4) * 4ull * s->nranks);
+        PMK_LAP(4);                               // host round trip + payload all-gather
         k4_unpack_remove<<<ctx->sm_count, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks);
-        const int nrec = s->nranks * s->ml.rec_cap;
-        k4_unpack_keys<<<(nrec + 255) / 256, 256, 0, st>>>(s->ml, s->all_msgs, s->nranks, s->mg_keys, s->mg_vals);
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->mg_cub, s->mg_cub_bytes, s->mg_keys, s->mg_keys2, s->mg_vals, s->mg_vals2, nrec, 0, 64, st));
+        PMK_LAP(5);                               // removals
+        RankOff ro;
+        ro.off[0] = 0;
+        for (int r = 0; r < s->nranks; ++r) ro.off[r + 1] = ro.off[r] + s->h_hdr[4 * r];
+        const int nrec = ro.off[s->nranks];
+        if (nrec > 0) {
+            k4_unpack_keys<<<(nrec + 255) / 256, 256, 0, st>>>(s->ml, s->all_msgs, s->nranks, ro, s->mg_keys, s->mg_vals);
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->mg_cub, s->mg_cub_bytes, s->mg_keys, s->mg_keys2, s->mg_vals, s->mg_vals2, nrec, 0, 40, st));
+        }
+        PMK_LAP(6);                               // keys + sort
         k4_unpack_scan<<<1, 32, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, s->rec_base);
-        k4_unpack_add<<<ctx->sm_count * 2, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, s->rec_base, s->mg_vals2);
+        if (nrec > 0) k4_unpack_add<<<ctx->sm_count * 2, 128, 0, st>>>(sp, s->ml, s->all_msgs, s->nranks, ro, s->rec_base, s->mg_vals2);
         ctx->launches += 7;
+        PMK_LAP(7);                               // scan + add
     }
+#undef PMK_LAP
     CUDA_TRY(cudaGetLastError());
     return PMK_OK;
 }

@@ -256,6 +256,13 @@ __global__ void k_fold_step(unsigned long long* stats, const unsigned long long*
 
 // multi-GPU: time stamps around a step's exchange (device clock, on the stream) and the bytes it gathered
 __global__ void k_stamp(unsigned long long* t) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*t)); }
+// profiling (PMK_VERBOSE): acc[slot] += now - *last; *last = now -- laps on the stream's own timeline
+__global__ void k_lap(unsigned long long* acc, unsigned long long* last, int slot) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (slot >= 0) acc[slot] += now - *last;
+    *last = now;
+}
 __global__ void k_fold_exchange(unsigned long long* stats, const unsigned long long* t0, unsigned long long bytes) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -523,18 +530,20 @@ __global__ void k4_unpack_remove(const StoreParams sp, MsgLayout ml, const int* 
     }
 }
 
-// sort keys of every rank's records: (global task, slot); unused tail = ~0.  One thread per record slot.
-__global__ void k4_unpack_keys(MsgLayout ml, const int* __restrict__ all, int nranks, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+struct RankOff { int off[65]; };        // off[r] = records of the ranks before r (host-side prefix of the gathered headers)
+__device__ __forceinline__ int rank_of_record(const RankOff& ro, int nranks, int i) {
+    int rk = 0;
+    while (rk + 1 < nranks && i >= ro.off[rk + 1]) ++rk;
+    return rk;
+}
+
+// sort keys of every rank's records: (global task, slot).  One thread per record.
+__global__ void k4_unpack_keys(MsgLayout ml, const int* __restrict__ all, int nranks, RankOff ro, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nranks * ml.rec_cap) return;
-    const int rk = i / ml.rec_cap, r = i % ml.rec_cap;
-    const int* msg = ml.msg_of(all, rk);
-    unsigned long long k = ~0ull;
-    if (r < msg[0]) {
-        const int* rec = MsgLayout::rec_of(msg, r, ml.rec_words);
-        k = (unsigned long long)(unsigned int)rec[14] * NEW_MAX + (unsigned int)rec[15];
-    }
-    keys[i] = k;
+    if (i >= ro.off[nranks]) return;
+    const int rk = rank_of_record(ro, nranks, i), r = i - ro.off[rk];
+    const int* rec = MsgLayout::rec_of(ml.msg_of(all, rk), r, ml.rec_words);
+    keys[i] = (unsigned long long)(unsigned int)rec[14] * NEW_MAX + (unsigned int)rec[15];
     vals[i] = i;
 }
 
@@ -545,7 +554,7 @@ __global__ void k4_unpack_scan(const StoreParams sp, MsgLayout ml, const int* __
     int total = 0;
     for (int rk = 0; rk < nranks; ++rk) {
         const int* msg = ml.msg_of(all, rk);
-        if (msg[2]) atomicAdd(st.counters + SC_OVERFLOW, 1);
+        if (msg[2]) atomicAdd(st.counters + SC_MSGOVER, 1);
         total += msg[0];
     }
     const int n = st.counters[SC_N], b = st.counters[SC_BIRTH];
@@ -557,7 +566,7 @@ __global__ void k4_unpack_scan(const StoreParams sp, MsgLayout ml, const int* __
 }
 
 // record at sorted position pos gets id n0 + pos and creation number b0 + pos (one warp per record)
-__global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks, const int* __restrict__ rec_base,
+__global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __restrict__ all, int nranks, RankOff ro, const int* __restrict__ rec_base,
                               const int* __restrict__ sorted_vals) {
     const StoreDev& st = sp.st;
     const int lane = threadIdx.x & 31;
@@ -566,7 +575,7 @@ __global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __r
     const int n0 = rec_base[0], b0 = rec_base[1], take = rec_base[2];
     for (int pos = gwarp; pos < take; pos += nwarps) {
         const int i = sorted_vals[pos];
-        const int rk = i / ml.rec_cap, r = i % ml.rec_cap;
+        const int rk = rank_of_record(ro, nranks, i), r = i - ro.off[rk];
         const int* rec = MsgLayout::rec_of(ml.msg_of(all, rk), r, ml.rec_words);
         const int fid = n0 + pos, mv = st.maxv;
         const int ni = rec[12], nv = rec[13];

@@ -201,8 +201,14 @@ void PhotoSet::init(PmMvps& pmmvps, const vector<int>& images, const string pref
         string header;
         float P[12];
         if (!(cam >> header)) die(string("Camera file not found: ") + cname);
-        if (header != "CONTOUR") die(string("Unrecognizable txt format: ") + cname);           // camera.cpp:39-53 (txtType 0 only)
-        for (int k = 0; k < 12; ++k) cam >> P[k];
+        if (header == "CONTOUR") {                                                             // camera.cpp:39-53, txtType 0: the raw 3 x 4
+            for (int k = 0; k < 12; ++k) cam >> P[k];
+        } else if (header == "CONTOUR2") {                                                     // txtType 2: K, Euler angles in degrees, translation
+            float intr[6], extr[6];
+            for (int k = 0; k < 6; ++k) cam >> intr[k];
+            for (int k = 0; k < 6; ++k) cam >> extr[k];
+            chk(pmk_contour2_to_projection(intr, extr, P), "pmk_contour2_to_projection");      // camera.cpp:116-131, quat2proj :241-261
+        } else die(string("Unrecognizable txt format: ") + cname);                             // CONTOUR3 is "to be written" in the reference too (:133-135)
         vector<unsigned char> rgb;
         int w = 0, h = 0;
         bool ok = false;
@@ -439,6 +445,151 @@ void PatchManager::writePly(const vector<Ppatch>& patches, const string filename
         const Patch& p = *patches[i];
         out << p.m_coord(0) << ' ' << p.m_coord(1) << ' ' << p.m_coord(2) << ' ' << p.m_normal(0) << ' ' << p.m_normal(1) << ' ' << p.m_normal(2) << ' '
             << colors[i](0) << ' ' << colors[i](1) << ' ' << colors[i](2) << '\n';
+    }
+}
+
+// ---- pass-throughs: the arithmetic and the grids are the device's, only the Patch objects are marshalled ---------------------------
+namespace {
+struct PatchRec {
+    float c[4], m[4], s[4];
+    vector<int> images;
+    int n;
+    explicit PatchRec(const Patch& p) : images(p.m_images), n((int)p.m_images.size()) {
+        for (int k = 0; k < 4; ++k) { c[k] = p.m_coord(k); m[k] = p.m_normal(k); }
+        s[0] = p.m_ncc; s[1] = p.m_dscale; s[2] = p.m_ascale; s[3] = p.m_tmp;
+    }
+};
+}  // namespace
+
+void PatchManager::removePatch(const Ppatch& ppatch) {
+    const int id = ppatch->m_id;                                        // collect-order index (collectPatches)
+    chk(pmk_store_remove(m_pmmvps.m_ctx, 1, &id), "removePatch");
+}
+
+void PatchManager::updateDepthMaps(Ppatch& ppatch) {
+    const int id = ppatch->m_id;
+    chk(pmk_store_update_depth_maps(m_pmmvps.m_ctx, 1, &id), "updateDepthMaps");
+}
+
+void PatchManager::setGridsImages(Patch& patch, vector<int>& images) const {
+    patch.m_images.clear();
+    patch.m_grids.clear();
+    const int n = (int)images.size();
+    if (n == 0) return;
+    vector<float> c((size_t)n * 4);
+    vector<int> cell((size_t)n * 2), ok(n);
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 4; ++k) c[4 * i + k] = patch.m_coord(k);
+    chk(pmk_probe(m_pmmvps.m_ctx, n, images.data(), c.data(), nullptr, nullptr, nullptr, nullptr, nullptr, cell.data(), ok.data()), "setGridsImages");
+    for (int i = 0; i < n; ++i)
+        if (ok[i]) { patch.m_images.push_back(images[i]); patch.m_grids.push_back(Vector2i(cell[2 * i], cell[2 * i + 1])); }
+}
+
+void PatchManager::setVGrids(Patch& patch) {
+    patch.m_vgrids.clear();
+    const int n = (int)patch.m_vimages.size();
+    if (n == 0) return;
+    vector<float> c((size_t)n * 4);
+    vector<int> cell((size_t)n * 2);
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 4; ++k) c[4 * i + k] = patch.m_coord(k);
+    chk(pmk_probe(m_pmmvps.m_ctx, n, patch.m_vimages.data(), c.data(), nullptr, nullptr, nullptr, nullptr, nullptr, cell.data(), nullptr), "setVGrids");
+    for (int i = 0; i < n; ++i) patch.m_vgrids.push_back(Vector2i(cell[2 * i], cell[2 * i + 1]));
+}
+
+void PatchManager::setVImagesVGrids(Ppatch& ppatch) { setVImagesVGrids(*ppatch); }
+
+void PatchManager::setVImagesVGrids(Patch& patch) {
+    m_pmmvps.syncDepth();
+    vector<char> seen(m_nimages, 0);
+    for (size_t i = 0; i < patch.m_images.size(); ++i) seen[patch.m_images[i]] = 1;
+    for (size_t i = 0; i < patch.m_vimages.size(); ++i) seen[patch.m_vimages[i]] = 1;
+    vector<int> cand;
+    for (int v = 0; v < m_nimages; ++v) if (!seen[v]) cand.push_back(v);
+    const int n = (int)cand.size();
+    if (n == 0) return;
+    vector<float> c((size_t)n * 4), m((size_t)n * 4);
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 4; ++k) { c[4 * i + k] = patch.m_coord(k); m[4 * i + k] = patch.m_normal(k); }
+    vector<int> vis(n), cell((size_t)n * 2);
+    chk(pmk_probe_visible(m_pmmvps.m_ctx, n, c.data(), m.data(), cand.data(), nullptr, m_pmmvps.m_neighborThreshold, vis.data(), cell.data()), "setVImagesVGrids");
+    for (int i = 0; i < n; ++i)
+        if (vis[i]) { patch.m_vimages.push_back(cand[i]); patch.m_vgrids.push_back(Vector2i(cell[2 * i], cell[2 * i + 1])); }
+}
+
+int PatchManager::isVisible0(const Patch& patch, const int image, int& ix, int& iy, const float strict) {
+    m_pmmvps.syncDepth();
+    const PatchRec r(patch);
+    int vis = 0, cell[2] = {0, 0};
+    chk(pmk_probe_visible(m_pmmvps.m_ctx, 1, r.c, r.m, &image, nullptr, strict, &vis, cell), "isVisible0");
+    ix = cell[0]; iy = cell[1];
+    return vis;
+}
+
+int PatchManager::isVisible(const Patch& patch, const int image, const int& ix, const int& iy, const float strict) {
+    m_pmmvps.syncDepth();
+    const PatchRec r(patch);
+    const int cell[2] = {ix, iy};
+    int vis = 0;
+    chk(pmk_probe_visible(m_pmmvps.m_ctx, 1, r.c, r.m, &image, cell, strict, &vis, nullptr), "isVisible");
+    return vis;
+}
+
+void PatchManager::setScales(Patch& patch) const {
+    const PatchRec r(patch);
+    if (r.n < 1) return;
+    float ds = 0.0f, as = 0.0f;
+    chk(pmk_probe_scales(m_pmmvps.m_ctx, 1, r.c, r.images.data(), &r.n, r.n, &ds, &as), "setScales");
+    patch.m_dscale = ds; patch.m_ascale = as;
+}
+
+void PatchManager::sortPatches(vector<Ppatch>& ppatches, const int ascend) const {
+    const int npatches = (int)ppatches.size();
+    if (npatches == 0) return;
+    for (int n = 0; n < npatches; ++n) if (ppatches[n]->m_ncc < 0.0f) computeNcc(*ppatches[n]);          // :411-415
+    if (npatches == 1) return;
+    for (int i = 0; i < npatches; ++i)                                                                    // the reference's swap sort, :419-432
+        for (int j = i + 1; j < npatches; ++j) {
+            const bool swap = ascend ? (ppatches[i]->m_ncc > ppatches[j]->m_ncc) : (ppatches[i]->m_ncc < ppatches[j]->m_ncc);
+            if (swap) ppatches[i].swap(ppatches[j]);
+        }
+}
+
+void PatchManager::findNeighbors(const Patch& patch, vector<Ppatch>& neighbors, const float scale, const int margin, const int skipvis) {
+    (void)skipvis;                                                       // unused in the reference as well (:671)
+    m_pmmvps.syncDepth();
+    const PatchRec r(patch);
+    if (r.n < 1) return;
+    int cap = 1024, count = 0;
+    vector<int> ids(cap);
+    chk(pmk_probe_neighbors(m_pmmvps.m_ctx, 1, r.c, r.m, r.s, r.images.data(), &r.n, r.n, scale, margin, cap, ids.data(), &count), "findNeighbors");
+    if (count > cap) {
+        cap = count; ids.resize(cap);
+        chk(pmk_probe_neighbors(m_pmmvps.m_ctx, 1, r.c, r.m, r.s, r.images.data(), &r.n, r.n, scale, margin, cap, ids.data(), &count), "findNeighbors");
+    }
+    for (int k = 0; k < std::min(count, cap); ++k)
+        if (ids[k] >= 0 && ids[k] < (int)m_ppatches.size()) neighbors.push_back(m_ppatches[ids[k]]);      // ids = m_ppatches indices (collectPatches)
+}
+
+void PatchManager::syncGrids() {
+    collectPatches(0);
+    m_pgrids.assign(m_nimages, vector<vector<Ppatch> >());
+    m_vpgrids.assign(m_nimages, vector<vector<Ppatch> >());
+    m_dpgrids.assign(m_nimages, vector<Ppatch>());
+    for (int v = 0; v < m_nimages; ++v) {
+        const int nc = m_gwidths[v] * m_gheights[v];
+        for (int which = 0; which < 2; ++which) {
+            vector<int> offs(nc + 1);
+            int total = 0;
+            chk(pmk_store_cell_ids(m_pmmvps.m_ctx, v, which, offs.data(), nullptr, 0, &total), "syncGrids");
+            vector<int> ids(std::max(total, 1));
+            if (total > 0) chk(pmk_store_cell_ids(m_pmmvps.m_ctx, v, which, offs.data(), ids.data(), total, &total), "syncGrids");
+            vector<vector<Ppatch> >& g = which ? m_vpgrids[v] : m_pgrids[v];
+            g.assign(nc, vector<Ppatch>());
+            for (int c = 0; c < nc; ++c)
+                for (int k = offs[c]; k < offs[c + 1]; ++k)
+                    if (ids[k] >= 0 && ids[k] < (int)m_ppatches.size()) g[c].push_back(m_ppatches[ids[k]]);
+        }
+        const vector<int> dm = depthMap(v);
+        m_dpgrids[v].assign(nc, Ppatch());
+        for (int c = 0; c < nc; ++c) if (dm[c] >= 0 && dm[c] < (int)m_ppatches.size()) m_dpgrids[v][c] = m_ppatches[dm[c]];
     }
 }
 

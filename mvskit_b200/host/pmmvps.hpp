@@ -138,12 +138,29 @@ public:
     void writePatches(const string prefix, bool bExportPLY, bool bExportPatch, bool bExportPSet);
     void writePly(const vector<Ppatch>& ppatches, const string filename);
     void writePly(const vector<Ppatch>& ppatches, const string filename, const vector<Vector3i>& colors);
+    // ---- the rest of the reference's public surface (patch_manager.hpp:31-107), each a pass-through to the device store ----
+    void removePatch(const Ppatch& ppatch);                               // :303-325 (by Patch::m_id, the collect-order index)
+    void updateDepthMaps(Ppatch& ppatch);                                 // :191-221
+    void setGridsImages(Patch& patch, vector<int>& images) const;         // :223-239
+    void setVGrids(Patch& patch);                                         // :251-261
+    void setVImagesVGrids(Ppatch& ppatch);                                // :263-265
+    void setVImagesVGrids(Patch& patch);                                  // :267-301
+    int isVisible0(const Patch& patch, const int image, int& ix, int& iy, const float strict);   // :327-333
+    int isVisible(const Patch& patch, const int image, const int& ix, const int& iy, const float strict);   // :335-376
+    void setScales(Patch& patch) const;                                   // :378-399
+    void sortPatches(vector<Ppatch>& ppatches, const int ascend = 1) const;    // :406-433
+    void findNeighbors(const Patch& patch, vector<Ppatch>& neighbors, const float scale = 1.0f, const int margin = 1, const int skipvis = 0);   // :671-728
+    // m_pgrids / m_vpgrids / m_dpgrids live in HBM; syncGrids() brings a host copy in the reference's shape (cell -> patches of
+    // m_ppatches, which it refreshes first), so that callers that walk the public grids keep working.  m_dpgrids holds null for m_MAXDEPTH.
+    void syncGrids();
     // sizes of m_pgrids / m_vpgrids cells and m_dpgrids ids of one view (the grids themselves stay in HBM)
     vector<int> cellCounts(const int image, const int vgrid = 0) const;
     vector<int> depthMap(const int image) const;
 
     vector<int> m_gheights, m_gwidths;
     vector<Ppatch> m_ppatches;
+    vector<vector<vector<Ppatch> > > m_pgrids, m_vpgrids;                // [image][cell] (patch_manager.hpp:89-96), filled by syncGrids()
+    vector<vector<Ppatch> > m_dpgrids;                                    // [image][cell] (patch_manager.hpp:100-104)
 
 protected:
     void readPatchFile(const string& name);

@@ -434,6 +434,49 @@ class Context:
         _chk(lib().pmk_probe_check(self.h, n, _p(coord), _p(normal), _p(scal), _p(images), _p(nimages), stride, _p(ret), _p(gain), _p(nn), _p(vimg), _p(nvimg)))
         return ret, gain, nn, vimg, nvimg
 
+    # -- PatchManager pass-throughs ----------------------------------------------------------------------------
+    def probe_visible(self, coord, normal, image, cells=None, strict: float = 0.5):
+        """PatchManager::isVisible0 (cells None) / isVisible (patch_manager.cpp:327-376) -> (flags, cells)."""
+        coord, normal = np.ascontiguousarray(coord, np.float32), np.ascontiguousarray(normal, np.float32)
+        image = np.ascontiguousarray(image, np.int32)
+        cells = np.ascontiguousarray(cells, np.int32) if cells is not None else None
+        out, cout = np.zeros(len(image), np.int32), np.zeros((len(image), 2), np.int32)
+        _chk(lib().pmk_probe_visible(self.h, len(image), _p(coord), _p(normal), _p(image), _p(cells), C.c_float(strict), _p(out), _p(cout)))
+        return out, cout
+
+    def probe_scales(self, coord, images, nimages):
+        """PatchManager::setScales (patch_manager.cpp:378-399) -> m_dscale, m_ascale."""
+        coord, images, nimages = np.ascontiguousarray(coord, np.float32), np.ascontiguousarray(images, np.int32), np.ascontiguousarray(nimages, np.int32)
+        ds, asc = np.zeros(len(coord), np.float32), np.zeros(len(coord), np.float32)
+        _chk(lib().pmk_probe_scales(self.h, len(coord), _p(coord), _p(images), _p(nimages), images.shape[1], _p(ds), _p(asc)))
+        return ds, asc
+
+    def probe_neighbors(self, coord, normal, scal, images, nimages, scale: float = 4.0, margin: int = 2, cap: int = 512):
+        """PatchManager::findNeighbors (patch_manager.cpp:671-728) -> list of ascending id arrays."""
+        coord, normal, scal = (np.ascontiguousarray(a, np.float32) for a in (coord, normal, scal))
+        images, nimages = np.ascontiguousarray(images, np.int32), np.ascontiguousarray(nimages, np.int32)
+        n = len(coord)
+        ids, cnt = np.zeros((n, cap), np.int32), np.zeros(n, np.int32)
+        _chk(lib().pmk_probe_neighbors(self.h, n, _p(coord), _p(normal), _p(scal), _p(images), _p(nimages), images.shape[1], C.c_float(scale), margin, cap, _p(ids), _p(cnt)))
+        return [ids[i, :min(cnt[i], cap)].copy() for i in range(n)], cnt
+
+    def store_remove(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        _chk(lib().pmk_store_remove(self.h, len(ids), _p(ids)))
+
+    def store_update_depth_maps(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        _chk(lib().pmk_store_update_depth_maps(self.h, len(ids), _p(ids)))
+
+    def store_cell_ids(self, view: int, which: int = 0):
+        """m_pgrids (which 0) / m_vpgrids (1) of one view: (offsets[cells + 1], ids)."""
+        gw, gh = self.grid_dims(view)
+        offs, tot = np.zeros(gw * gh + 1, np.int32), C.c_int()
+        _chk(lib().pmk_store_cell_ids(self.h, view, which, _p(offs), None, 0, C.byref(tot)))
+        ids = np.zeros(max(tot.value, 1), np.int32)
+        _chk(lib().pmk_store_cell_ids(self.h, view, which, _p(offs), _p(ids), len(ids), C.byref(tot)))
+        return offs, ids[:tot.value]
+
     # -- multi-GPU --------------------------------------------------------------------------------------------
     def comm_init(self, rank: int, nranks: int, unique_id: Optional[bytes]):
         _chk(lib().pmk_comm_init(self.h, rank, nranks, unique_id))
@@ -465,6 +508,14 @@ class Context:
 
     def flush_l2(self):
         _chk(lib().pmk_flush_l2(self.h))
+
+
+def contour2_to_projection(intrinsics6, extrinsics6) -> np.ndarray:
+    """Camera::setProjection for CONTOUR2 camera files (camera.cpp:116-131, 241-261) -> level-0 P (3, 4)."""
+    a, b = np.ascontiguousarray(intrinsics6, np.float32), np.ascontiguousarray(extrinsics6, np.float32)
+    P = np.zeros((3, 4), np.float32)
+    _chk(lib().pmk_contour2_to_projection(_p(a), _p(b), _p(P)))
+    return P
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:

@@ -394,6 +394,38 @@ class RefLib:
         r = int(self.L.pmref_check(_p(coord), _p(normal), _p(scal), _p(views), len(views), C.byref(gain), C.byref(io)))
         return r, float(gain.value), out
 
+    def write_ply(self, path: str) -> int:
+        """PatchManager::writePly of the current store."""
+        return int(self.L.pmref_write_ply(path.encode()))
+
+    # -- PatchManager's public surface --------------------------------------------------------------
+    def is_visible(self, coord, normal, image, cells=None, strict: float = 0.5):
+        coord, normal, image = _f32(coord), _f32(normal), _i32(image)
+        cells = _i32(cells) if cells is not None else None
+        out, cout = np.zeros(len(image), np.int32), np.zeros((len(image), 2), np.int32)
+        self.L.pmref_is_visible(len(image), _p(coord), _p(normal), _p(image), _p(cells) if cells is not None else None, C.c_float(strict), _p(out), _p(cout))
+        return out, cout
+
+    def set_scales(self, coord, views, nviews):
+        coord, views, nviews = _f32(coord), _i32(views), _i32(nviews)
+        ds, asc = np.zeros(len(coord), np.float32), np.zeros(len(coord), np.float32)
+        self.L.pmref_set_scales(len(coord), _p(coord), _p(views), _p(nviews), views.shape[1], _p(ds), _p(asc))
+        return ds, asc
+
+    def find_neighbors(self, coord, normal, scal, views, scale: float = 4.0, margin: int = 2, cap: int = 4096):
+        views = _i32(views)
+        ids = np.zeros(cap, np.int32)
+        n = int(self.L.pmref_find_neighbors(_p(_f32(coord)), _p(_f32(normal)), _p(_f32(scal)), _p(views), len(views), C.c_float(scale), margin, _p(ids), cap))
+        return ids[:min(n, cap)].copy(), n
+
+    def remove_patches(self, ids):
+        ids = _i32(ids)
+        self.L.pmref_remove_patches(len(ids), _p(ids))
+
+    def update_depth_maps(self, ids):
+        ids = _i32(ids)
+        self.L.pmref_update_depth_maps(len(ids), _p(ids))
+
     def run(self):
         alive = C.c_int()
         secs = float(self.L.pmref_run(C.byref(alive)))

@@ -8,6 +8,7 @@
 //
 // Used by: tests/ (parity), tests/golden/make_golden.py (fixture generation),
 //          bench.py --impl reference and bench.py's cpu_baseline leg.
+#include <algorithm>
 #include <cmath>
 #include <climits>
 #include <cstdio>
@@ -666,6 +667,58 @@ void pmref_stage_neighbors(int* count, int* quad) {
         count[i] = (int)nb.size();
         quad[i] = nb.size() >= 6 ? g_pm->m_filter.filterQuad(*g_prev[i], nb) : -1;
     }
+}
+
+// PatchManager::writePly (patch_manager.cpp:542-633) of the current store to `path` (ASCII PLY with the per-patch colours); returns the count
+int pmref_write_ply(const char* path) {
+    g_pm->m_patchManager.collectPatches(0);
+    g_pm->m_patchManager.writePly(g_pm->m_patchManager.m_ppatches, std::string(path));
+    return (int)g_pm->m_patchManager.m_ppatches.size();
+}
+
+// ---- PatchManager's public surface, for the pass-through tests ---------------------------------------------------------------
+// isVisible0 (cells == NULL; the cells come back) / isVisible (patch_manager.cpp:327-376)
+void pmref_is_visible(int n, const float* coord4, const float* normal4, const int* image, const int* cells, float strict, int* out, int* cells_out) {
+    for (int i = 0; i < n; ++i) {
+        Patch patch;
+        patch.m_coord = v4(coord4 + 4 * i); patch.m_normal = v4(normal4 + 4 * i);
+        int ix = 0, iy = 0;
+        if (cells) { ix = cells[2 * i]; iy = cells[2 * i + 1]; out[i] = g_pm->m_patchManager.isVisible(patch, image[i], ix, iy, strict); }
+        else out[i] = g_pm->m_patchManager.isVisible0(patch, image[i], ix, iy, strict);
+        if (cells_out) { cells_out[2 * i] = ix; cells_out[2 * i + 1] = iy; }
+    }
+}
+// setScales (patch_manager.cpp:378-399) on fresh patches
+void pmref_set_scales(int n, const float* coord4, const int* views, const int* nviews, int stride, float* dscale, float* ascale) {
+    for (int i = 0; i < n; ++i) {
+        Patch patch;
+        fill_patch(patch, coord4 + 4 * i, coord4 + 4 * i, views + (size_t)i * stride, nviews[i]);
+        g_pm->m_patchManager.setScales(patch);
+        dscale[i] = patch.m_dscale; ascale[i] = patch.m_ascale;
+    }
+}
+// findNeighbors (patch_manager.cpp:671-728) of a free-standing patch: the neighbours' m_ppatches indices (after pmref_collect), ascending
+int pmref_find_neighbors(const float* coord4, const float* normal4, const float* scal4, const int* views, int nviews, float scale, int margin, int* ids, int cap) {
+    Patch patch;
+    fill_patch(patch, coord4, normal4, views, nviews);
+    patch.m_ncc = scal4[0]; patch.m_dscale = scal4[1]; patch.m_ascale = scal4[2];
+    g_pm->m_patchManager.setGrids(patch);
+    std::vector<Ppatch> nb;
+    g_pm->m_patchManager.findNeighbors(patch, nb, scale, margin, 0);
+    std::vector<int> out;
+    for (size_t i = 0; i < nb.size(); ++i) out.push_back(nb[i]->m_id);
+    std::sort(out.begin(), out.end());
+    for (size_t i = 0; i < out.size() && (int)i < cap; ++i) ids[i] = out[i];
+    return (int)out.size();
+}
+// removePatch / updateDepthMaps (patch_manager.cpp:303-325, 191-221) for patches of the last pmref_collect, by index
+void pmref_remove_patches(int n, const int* ids) {
+    std::vector<Ppatch> pp = g_pm->m_patchManager.m_ppatches;
+    for (int i = 0; i < n; ++i) g_pm->m_patchManager.removePatch(pp[ids[i]]);
+}
+void pmref_update_depth_maps(int n, const int* ids) {
+    std::vector<Ppatch> pp = g_pm->m_patchManager.m_ppatches;
+    for (int i = 0; i < n; ++i) g_pm->m_patchManager.updateDepthMaps(pp[ids[i]]);
 }
 
 // PatchManager::setVImagesVGrids / Optim::check on a free-standing patch record (optim.cpp:290-323)

@@ -533,3 +533,91 @@ def test_thresholds_follow_the_reference(ctx, reflib):
         assert t.depth == step + 1
     reflib.set_ncc_thresholds(0.7, 0.4)
     c.close()
+
+
+def test_patch_manager_pass_throughs(ctx, reflib, populated, small_scene):
+    """The rest of PatchManager's public surface that the host mirror forwards to the device (mvskit_b200/host/pmmvps.hpp): isVisible0 /
+    isVisible, setScales, findNeighbors (the id lists, not only their sizes), removePatch, updateDepthMaps and the grids as the
+    reference's vectors -- each against the reference's own member function on the same store."""
+    g = populated
+    _load_both(ctx, reflib, g, 1)
+    reflib.filter_rebuild(0)
+    assert ctx.filter_rebuild(0) == g.n
+    rb, gb = reflib.get_patches(), ctx.store_get()
+    assert_bits_equal(gb.coord, rb.coord, "collect order")
+    rng = np.random.RandomState(9)
+    # ---- isVisible0 / isVisible: stored patches nudged along their normal (both outcomes), every view ----
+    pick = rng.choice(rb.n, 400, replace=False)
+    coord = rb.coord[pick].copy()
+    coord[:, :3] += rb.normal[pick, :3] * rng.uniform(-0.02, 0.02, (len(pick), 1)).astype(np.float32)
+    image = rng.randint(0, reflib.nviews, len(pick)).astype(np.int32)
+    for strict in (0.5, 1.0):
+        want, wcell = reflib.is_visible(coord, rb.normal[pick], image, None, strict)
+        got, gcell = ctx.probe_visible(coord, rb.normal[pick], image, None, strict)
+        assert np.array_equal(got, want) and np.array_equal(gcell, wcell), (strict, int((got != want).sum()))
+        shifted = wcell + rng.randint(-1, 2, wcell.shape).astype(np.int32)
+        want2, _ = reflib.is_visible(coord, rb.normal[pick], image, shifted, strict)
+        got2, _ = ctx.probe_visible(coord, rb.normal[pick], image, shifted, strict)
+        assert np.array_equal(got2, want2), strict
+    assert 0 < want.sum() < len(want)
+    # ---- setScales on the stored patches' coordinates and view lists ----
+    ds, asc = ctx.probe_scales(rb.coord[pick], rb.images[pick], rb.nimages[pick])
+    wds, wasc = reflib.set_scales(rb.coord[pick], rb.images[pick], rb.nimages[pick])
+    assert_bits_equal(ds, wds, "m_dscale")
+    assert np.abs(asc - wasc).max() <= 1e-6 * np.abs(wasc).max()          # atan() in double on both sides (libm vs CUDA: last-ulp freedom)
+    # ---- findNeighbors: the same patches, by id ----
+    sub = pick[:60]
+    lists, cnt = ctx.probe_neighbors(rb.coord[sub], rb.normal[sub], rb.scal[sub], rb.images[sub], rb.nimages[sub], 4.0, 2, 2048)
+    nonempty = 0
+    for k, i in enumerate(sub):
+        want_ids, n = reflib.find_neighbors(rb.coord[i], rb.normal[i], rb.scal[i], rb.images[i, :rb.nimages[i]], 4.0, 2)
+        assert cnt[k] == n and np.array_equal(lists[k], want_ids), (i, cnt[k], n)
+        nonempty += int(n > 0)
+    assert nonempty > 30
+    # ---- the grids as the reference's vectors: every cell's m_pgrids / m_vpgrids ids, every depth-map entry ----
+    for v in range(reflib.nviews):
+        gw, gh = ctx.grid_dims(v)
+        for which in (0, 1):
+            offs, ids = ctx.store_cell_ids(v, which)
+            assert np.array_equal(np.diff(offs).reshape(gh, gw), reflib.cell_counts(v, which))
+            for cidx in rng.choice(gw * gh, 40, replace=False):
+                assert sorted(ids[offs[cidx]:offs[cidx + 1]].tolist()) == sorted(reflib.cell_ids(v, int(cidx), which).tolist()), (v, which, cidx)
+    # ---- removePatch + updateDepthMaps ----
+    kill = np.sort(rng.choice(rb.n, 150, replace=False)).astype(np.int32)
+    reflib.remove_patches(kill)
+    ctx.store_remove(kill)
+    for v in range(reflib.nviews):
+        assert np.array_equal(ctx.store_cell_counts(v, 0), reflib.cell_counts(v, 0)), v
+        assert np.array_equal(ctx.store_cell_counts(v, 1), reflib.cell_counts(v, 1)), v
+    keep = np.setdiff1d(np.arange(rb.n), kill)[:200].astype(np.int32)
+    reflib.update_depth_maps(keep)
+    ctx.store_update_depth_maps(keep)
+    for v in range(reflib.nviews):
+        assert np.array_equal(ctx.store_depth_map(v), reflib.depth_map(v)), v
+
+
+def test_ply_colours_match_write_ply(ctx, reflib, populated, tmp_path):
+    """PatchManager::writePly's per-patch colour (patch_manager.cpp:566-581: mean over m_images of Image::getColor at the projection,
+    rounded) -- the device's pmk_store_colors against the PLY file the reference itself writes from the same store."""
+    g = populated
+    _load_both(ctx, reflib, g, 1)
+    path = str(tmp_path / "ref.ply")
+    n = reflib.write_ply(path)
+    assert n == g.n
+    rows = []
+    with open(path) as fh:
+        for line in fh:
+            if line.strip() == "end_header":
+                break
+        for line in fh:
+            t = line.split()
+            if len(t) >= 9:
+                rows.append([float(x) for x in t[:9]])
+    ply = np.array(rows)
+    assert len(ply) == n
+    gb = ctx.store_get()
+    assert np.abs(ply[:, :3] - gb.coord[:, :3]).max() < 1e-4              # same patches, same order (text precision)
+    rgb = ctx.store_colors(n)
+    d = np.abs(rgb.astype(int) - ply[:, 6:9].astype(int))
+    assert d.max() <= 1, d.max()                                             # the mean is rounded: an ulp in the float sum may flip one grey level
+    assert (d == 0).mean() >= 0.995, (d == 0).mean()
