@@ -449,7 +449,7 @@ static int set_view_impl(pmk_ctx* ctx, int view, const float* P, const uint8_t* 
         ctx->owned.push_back(d);
         vc.img[l] = (const Texel*)d;
     }
-    k0_u8_to_rgbx<<<(unsigned)((npix0 + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->s_misc[0].p, (Texel*)vc.img[0], (int)npix0);
+    k0_u8_to_rgbx<<<(unsigned)(((npix0 + 3) / 4 + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->s_misc[0].p, (Texel*)vc.img[0], (int)npix0);
     ctx->launches++;
     for (int l = 1; l < nlevels; ++l) {
         dim3 blk(32, 8), grd((vc.w[l] + 31) / 32, (vc.h[l] + 7) / 8);

@@ -12,10 +12,20 @@ namespace pmk {
 // result is re-rounded to an integer (floorf(c + 0.5f)) and stored as a half-float RGBX texel (exact for 0..255).
 // =====================================================================================================
 __global__ void k0_u8_to_rgbx(const uint8_t* __restrict__ src, Texel* __restrict__ dst, int npix) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // four pixels = three aligned 32-bit words in, four texels out: coalesced both ways (the staging buffer is 256-byte aligned)
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = 4 * q;
     if (i >= npix) return;
-    const uint8_t* p = src + (size_t)i * 3;
-    dst[i] = make_texel((float)p[0], (float)p[1], (float)p[2]);
+    if (i + 3 < npix) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(src) + 3 * (size_t)q;
+        const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
+        dst[i] = make_texel((float)(a & 255u), (float)((a >> 8) & 255u), (float)((a >> 16) & 255u));
+        dst[i + 1] = make_texel((float)(a >> 24), (float)(b & 255u), (float)((b >> 8) & 255u));
+        dst[i + 2] = make_texel((float)((b >> 16) & 255u), (float)(b >> 24), (float)(c & 255u));
+        dst[i + 3] = make_texel((float)((c >> 8) & 255u), (float)((c >> 16) & 255u), (float)(c >> 24));
+    } else {
+        for (int k = i; k < npix; ++k) { const uint8_t* p = src + (size_t)k * 3; dst[k] = make_texel((float)p[0], (float)p[1], (float)p[2]); }
+    }
 }
 
 __global__ void k0_downsample(const Texel* __restrict__ src, int Wp, int Hp, Texel* __restrict__ dst, int W, int H) {

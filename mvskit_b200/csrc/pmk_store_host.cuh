@@ -22,7 +22,7 @@ struct pmk_store {
     int* cell_base_d = nullptr;
     std::vector<int> cell_base;         // host copy
     // scratch
-    int* rem_list = nullptr; int* task_new = nullptr; int* final_id = nullptr; int* order = nullptr;
+    int* rem_list = nullptr; int* task_new = nullptr; int* final_id = nullptr; int* order = nullptr; int* alive_list = nullptr;
     unsigned long long* stats = nullptr; unsigned long long* step_max = nullptr;
     float* cell_ns = nullptr;            // per-cell sweep time of the last pass (allocated on first pmk_debug_cell_times call)
     unsigned long long* phase_ns = nullptr;   // warp time by try phase (allocated on first pmk_debug_phase_times call)
@@ -134,7 +134,7 @@ int store_init(pmk_ctx* ctx) {
         return rc;
     d.cell_base = s->cell_base_d;
     CUDA_TRY(cudaMemcpyAsync(s->cell_base_d, s->cell_base.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = dalloc(ctx, &s->rem_list, d.cap)) || (rc = dalloc(ctx, &s->task_new, s->max_tasks)) || (rc = dalloc(ctx, &s->order, s->max_tasks + 1)) || (rc = dalloc(ctx, &s->final_id, d.stage_cap)) ||
+    if ((rc = dalloc(ctx, &s->rem_list, d.cap)) || (rc = dalloc(ctx, &s->task_new, s->max_tasks)) || (rc = dalloc(ctx, &s->order, s->max_tasks + 1)) || (rc = dalloc(ctx, &s->final_id, d.stage_cap)) || (rc = dalloc(ctx, &s->alive_list, d.stage_cap)) ||
         (rc = dalloc(ctx, &s->stats, SS_COUNT)) || (rc = dalloc(ctx, &s->step_max, 4)) || (rc = dalloc(ctx, &s->keys, d.cap)) || (rc = dalloc(ctx, &s->keys2, d.cap)) ||
         (rc = dalloc(ctx, &s->vals, d.cap)) || (rc = dalloc(ctx, &s->vals2, d.cap)) || (rc = dalloc(ctx, &s->f_tmp, d.cap)) ||
         (rc = dalloc(ctx, &s->i_tmp, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp2, d.cap + 1)) || (rc = dalloc(ctx, &s->i_tmp3, d.cap + 1)) || (rc = dalloc(ctx, &s->small, 16)))
@@ -450,8 +450,8 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     PMK_LAP(0);                                   // plan + sweep kernel
     if (s->nranks <= 1) {
         k4_apply_remove<<<std::max(1, std::min(ctx->sm_count, (sa.ntasks + 3) / 4)), 128, 0, st>>>(sp, s->rem_list, s->d.cap);
-        k4_apply_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
-        k4_apply_add<<<std::max(1, std::min(ctx->sm_count * 2, sa.ntasks)), 128, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id);
+        k4_apply_scan<<<1, 1024, 0, st>>>(sp, s->task_new, sa.ntasks, s->final_id, s->alive_list, s->small + 8);
+        k4_apply_add<<<std::max(1, std::min(ctx->sm_count * 2, sa.ntasks)), 128, 0, st>>>(sp, s->final_id, s->alive_list, s->small + 8);
         ctx->launches += 3;
         PMK_LAP(1);                               // apply (single GPU)
     } else {

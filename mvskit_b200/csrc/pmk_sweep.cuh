@@ -352,7 +352,8 @@ __device__ __forceinline__ void warp_register_patch(const StoreParams& sp, int i
 
 // one block: exclusive scan of the staged-and-alive counts -> final ids (task order); bumps SC_N / SC_BIRTH.
 // final_id[task * NEW_MAX + j] = id or -1.  Launched with 1024 threads; thread t owns tasks t, t + 1024, ...
-__global__ void __launch_bounds__(1024) k4_apply_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, int* __restrict__ final_id) {
+__global__ void __launch_bounds__(1024) k4_apply_scan(const StoreParams sp, const int* __restrict__ task_new, int ntasks, int* __restrict__ final_id,
+                                                      int* __restrict__ alive_list, int* __restrict__ alive_count) {
     const StoreDev& st = sp.st;
     __shared__ int s_warp[32];
     __shared__ int s_carry;
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(1024) k4_apply_scan(const StoreParams sp, cons
                 if (st.state[sid] == 1) {
                     if (n0 + excl < st.cap) { fid = n0 + excl; st.birth[sid] = (unsigned int)(b0 + excl); }
                     else atomicAdd(st.counters + SC_FULL, 1);
+                    alive_list[excl] = t * NEW_MAX + j;             // compact list of the surviving staged entries, in (task, slot) order
                     ++excl;
                 }
                 final_id[t * NEW_MAX + j] = fid;
@@ -403,17 +405,18 @@ __global__ void __launch_bounds__(1024) k4_apply_scan(const StoreParams sp, cons
         const int total = s_carry;
         st.counters[SC_N] = min(st.cap, n0 + total);
         st.counters[SC_BIRTH] = b0 + total;
+        *alive_count = total;
     }
 }
 
-// copy every staged, surviving patch to its final slot and register it (one warp per staged entry)
-__global__ void k4_apply_add(const StoreParams sp, const int* __restrict__ task_new, int ntasks, const int* __restrict__ final_id) {
+// copy every staged, surviving patch to its final slot and register it (one warp per entry of the scan's compact list)
+__global__ void k4_apply_add(const StoreParams sp, const int* __restrict__ final_id, const int* __restrict__ alive_list, const int* __restrict__ alive_count) {
     const StoreDev& st = sp.st;
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int w = gwarp; w < ntasks * NEW_MAX; w += nwarps) {
-        const int t = w / NEW_MAX, j = w % NEW_MAX;
-        if (j >= task_new[t]) continue;
+    const int total = *alive_count;
+    for (int pos = gwarp; pos < total; pos += nwarps) {
+        const int w = alive_list[pos];
         const int fid = final_id[w];
         if (fid < 0) continue;
         const int sid = st.cap + w;
