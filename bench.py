@@ -540,7 +540,7 @@ def main():
             entry.update(res)
             entry["config"] = (f"config{cfg_i} scale {scale_i:g}: {scene_i.nviews} views {scene_i.width}x{scene_i.height}, seeds every {st_i}th cell, "
                                f"ITER {it_i}, sweep_group {args.sweep_group or scene_i.nviews}, {world} GPU(s)"
-                               + (": balanced row bands, replicated store, NCCL all-gather of each step's mutations" if world > 1 else ""))
+                               + (": every step's dest cells dealt out to the ranks in turn, replicated store, NCCL all-gather of each step's mutations" if world > 1 else ""))
             if cfg_i != args.config:
                 # K1 on this config's pyramid (not L2-resident): device-resident steps, L2 flushed, same kernel
                 nh = 1 << 19                                  # enough batches for every resident warp (a 2^17 launch is all tail)

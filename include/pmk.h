@@ -227,10 +227,12 @@ int pmk_filter_stage(pmk_ctx* ctx, int stage, int nmax, float* f_out, int* i_out
 int pmk_filter(pmk_ctx* ctx, int* counts6);
 
 /* ---- multi-GPU: one process and one pmk_ctx per GPU; images and the patch store are replicated, the dest cells of every
- * wavefront step are partitioned by row band (rank r of n takes rows [ylo, yhi) of every view's cell grid), and after each step
- * the ranks exchange the step's new and removed patches (ncclAllGather over NVLink/NVSwitch) and all apply all of them in rank
- * order, so every replica holds the same store.  The reference is single-threaded: there is no counterpart to cite. */
-int pmk_band_rows(int gheight, int rank, int nranks, int* ylo, int* yhi);     /* the partition function (host only) */
+ * wavefront step are dealt out to the ranks in turn (the step's cells are numbered view by view along the anti-diagonals; rank r of n
+ * takes the cells whose number G has G % n == r, so neighbouring cells -- and with them the heavy regions -- spread evenly), and after
+ * each step the ranks exchange the step's new and removed patches (ncclAllGather over NVLink/NVSwitch, headers first, then exactly the
+ * payload the step produced) and all apply all of them in global cell order, so every replica holds the single-GPU store.  The
+ * reference is single-threaded: there is no counterpart to cite. */
+int pmk_step_share(int step_tasks, int rank, int nranks, int* count);        /* how many of a step's cells rank r takes (host only) */
 int pmk_comm_unique_id(char* id128);                        /* rank 0: ncclGetUniqueId; ship the 128 bytes to every rank */
 int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128);     /* ncclCommInitRank; nranks == 1 needs no id */
 int pmk_comm_destroy(pmk_ctx* ctx);

@@ -325,6 +325,7 @@ int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
     CUDA_TRY(cudaSetDevice(cfg->device));
     pmk_ctx* ctx = new pmk_ctx();
     ctx->cfg = *cfg;
+    struct Guard { pmk_ctx* c; ~Guard() { if (c) pmk_destroy(c); } } guard{ctx};      // a failed step below releases what the earlier ones made
     CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
@@ -350,6 +351,7 @@ int pmk_create(const pmk_config* cfg, pmk_ctx** out) {
     ctx->ncc_threshold_before = cfg->ncc_threshold - 0.3f;
     ctx->depth = 0;
     refresh_params(ctx);
+    guard.c = nullptr;
     *out = ctx;
     return PMK_OK;
 }
@@ -358,7 +360,7 @@ void pmk_destroy(pmk_ctx* ctx) {
     if (!ctx) return;
     pmk_comm_destroy(ctx);
     cudaSetDevice(ctx->cfg.device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->owned) cudaFree(p);
     Scratch* all[] = {&ctx->s_coord, &ctx->s_normal, &ctx->s_views, &ctx->s_nviews, &ctx->s_incc, &ctx->s_ncc, &ctx->s_levels, &ctx->s_ready};
     if (ctx->h_epoch) cudaFreeHost(ctx->h_epoch);
@@ -366,13 +368,12 @@ void pmk_destroy(pmk_ctx* ctx) {
     for (Scratch& s : ctx->s_misc) if (s.p) cudaFree(s.p);
     for (Scratch& s : ctx->pool) if (s.p) cudaFree(s.p);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
-    cudaFree(ctx->d_views);
-    cudaFree(ctx->d_counters);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    if (ctx->d_views) cudaFree(ctx->d_views);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_k) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
-    cudaStreamDestroy(ctx->stream);
+    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->stream}) if (q) cudaStreamDestroy(q);
     if (ctx->store && ctx->store->adj) cudaFree(ctx->store->adj);
     if (ctx->store && ctx->store->h_hdr) cudaFreeHost(ctx->store->h_hdr);
     delete ctx->store;
@@ -726,6 +727,11 @@ static int ncc_eval_host(pmk_ctx* ctx, int n, const float* coord4, const float* 
     static const int nstreams = getenv("PMK_E2E_STREAMS") ? std::min(2, std::max(1, atoi(getenv("PMK_E2E_STREAMS")))) : 2;
     const size_t chunk = (size_t)1 << chunk_log2;
     const int nchunks = (int)((N + chunk - 1) / chunk);
+    // an error return after the first enqueue must not leave copies in flight that read the caller's buffers / h_epoch
+    struct Drain {
+        pmk_ctx* c; bool ok;
+        ~Drain() { if (!ok) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->s_out); cudaStreamSynchronize(c->stream); } }
+    } drain{ctx, false};
     CUDA_TRY(cudaEventRecord(ctx->ev1, st));                      // the copies must not overtake earlier work on the context stream
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev1, 0));
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev1, 0));
@@ -781,6 +787,7 @@ static int ncc_eval_host(pmk_ctx* ctx, int n, const float* coord4, const float* 
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
         CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+        drain.ok = true;
         return PMK_OK;
     }
     // PMK_E2E_MODE=chunks (kept for A/B measurements): three-stage pipeline over chunks of the batch, H2D on s_in, one K1 launch per
@@ -811,6 +818,7 @@ static int ncc_eval_host(pmk_ctx* ctx, int n, const float* coord4, const float* 
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     CUDA_TRY(cudaStreamSynchronize(st));
+    drain.ok = true;
     return PMK_OK;
 }
 
@@ -1371,10 +1379,6 @@ int pmk_propagate(pmk_ctx* ctx, int iter, uint64_t seed, uint64_t* stats16) {
     ctx->store->host_wait_s = 0.0; ctx->store->host_waits = 0;
     const auto t_prop0 = std::chrono::steady_clock::now();
     const int group = ctx->store->group;
-    {   // multi-GPU: re-cut the row bands from where the patches are now (no-op on one GPU)
-        StoreParams sp;
-        if ((rc = store_check_overflow(ctx)) || (rc = store_params(ctx, sp, seed)) || (rc = balance_bands(ctx, sp))) return rc;
-    }
     for (int image = 0; image < ctx->cfg.nviews; image += group) {                        // propagate.cpp:73, `group` views at a time
         if ((rc = sweep_views(ctx, iter, image, std::min(group, ctx->cfg.nviews - image), 0, 1 << 30, seed))) return rc;
         if ((rc = store_check_overflow(ctx))) return rc;
@@ -1454,10 +1458,9 @@ int pmk_filter(pmk_ctx* ctx, int* counts6) {
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------------------------------------
-int pmk_band_rows(int gheight, int rank, int nranks, int* ylo, int* yhi) {
-    if (!ylo || !yhi || gheight < 0 || nranks < 1 || rank < 0 || rank >= nranks) return fail(PMK_ERR_ARG, "pmk_band_rows: bad argument");
-    *ylo = (int)((long long)gheight * rank / nranks);
-    *yhi = (int)((long long)gheight * (rank + 1) / nranks);
+int pmk_step_share(int step_tasks, int rank, int nranks, int* count) {
+    if (!count || step_tasks < 0 || nranks < 1 || rank < 0 || rank >= nranks) return fail(PMK_ERR_ARG, "pmk_step_share: bad argument");
+    *count = step_tasks > rank ? (step_tasks - rank + nranks - 1) / nranks : 0;      // global tasks G of the step with G % nranks == rank
     return PMK_OK;
 }
 
@@ -1481,7 +1484,6 @@ int pmk_comm_init(pmk_ctx* ctx, int rank, int nranks, const char* id128) {
     pmk_store* s = ctx->store;
     if (s->nccl_comm) return fail(PMK_ERR_STATE, "pmk_comm_init: communicator already set");
     s->rank = rank; s->nranks = nranks;
-    s->band.clear();
     if (nranks == 1) return PMK_OK;
     if (!id128) return fail(PMK_ERR_ARG, "pmk_comm_init: null id");
     NcclApi* api = nccl_api();
@@ -1529,7 +1531,6 @@ int pmk_comm_destroy(pmk_ctx* ctx) {
         s->nccl_comm = nullptr;
     }
     s->rank = 0; s->nranks = 1;
-    s->band.clear();
     return PMK_OK;
 }
 

@@ -696,12 +696,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_cells(const __grid_constant_
         const int tslot = cs.task;
         if (tslot >= sa.ntasks) break;
         const int task = sa.order[tslot];
-        int g = 0;
-        while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+        const int G = sweep_global_task(sa, task), g = sweep_group_of(sa, G);
         const int img = sa.g_img[g];
         const ViewConst& vimgc = p.views[img];
         const int gw = vimgc.gw, gh = vimgc.gh;
-        const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
+        const int x = sa.g_xlo[g] + (G - sa.g_off[g]), y = sa.g_diag[g] - x;
         const int cD = st.cell_base[img] + y * gw + x;
         if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cs.t_begin));
         // ================= preamble: sortPatches' recomputation of negative m_ncc (patch_manager.cpp:411-415), by the CTA =================

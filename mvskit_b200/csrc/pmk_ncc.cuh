@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
                 nv = __ldcg(nviews + h);
             }
         }
-        const int sz = min(p.tau, nv);
+        const int sz = min(p.tau, min(nv, stride));       // a count beyond the row length must not read the next hypothesis' views
         const bool usable = live && nv >= 2;              // optim.cpp:631,643: fewer than 2 images -> 2.0
         int valid_mask = 0;
         float* myrow = frames + (size_t)lane * fstride;

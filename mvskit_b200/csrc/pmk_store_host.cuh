@@ -17,7 +17,7 @@ struct pmk_store {
     pmk::StoreDev d;                    // device pointers
     int n = 0;                          // patches allocated (host mirror of SC_N)
     int max_tasks = 0;
-    int rank = 0, nranks = 1;             // multi-GPU: this context sweeps band `rank` of `nranks` of every view's rows
+    int rank = 0, nranks = 1;             // multi-GPU: this context sweeps every nranks-th dest cell of a step, starting at `rank`
     int group = 1;                        // views swept concurrently (pmk_config.sweep_group)
     int* cell_base_d = nullptr;
     std::vector<int> cell_base;         // host copy
@@ -45,9 +45,6 @@ struct pmk_store {
     unsigned long long* mg_keys = nullptr; unsigned long long* mg_keys2 = nullptr; int* mg_vals = nullptr; int* mg_vals2 = nullptr;
     void* mg_cub = nullptr; size_t mg_cub_bytes = 0;
     bool canonical = false;             // patch ids are the reference's m_ppatches indices (collect order, no holes)
-    std::vector<int> band;              // multi-GPU: band[v * (nranks + 1) + r] = first cell row of rank r in view v (balance_bands)
-    std::vector<int> row_base;          // first entry of view v in the per-row work histogram
-    int* row_base_d = nullptr; int* rows_d = nullptr;
 };
 
 namespace {
@@ -94,6 +91,7 @@ int store_init(pmk_ctx* ctx) {
     for (int v = 0; v < nv; ++v) {
         const ViewConst& vc = ctx->h_views[v];
         if (vc.gw >= 65535 || vc.gh >= 32767) return fail(PMK_ERR_ARG, "pmk: cell grid too large for packed cell indices");
+        if ((long long)vc.gw * vc.gh >= (1ll << 24)) return fail(PMK_ERR_ARG, "pmk: more than 2^24 cells per view (the collect key keeps 24 bits of cell index)");
         s->cell_base[v + 1] = s->cell_base[v] + vc.gw * vc.gh;
         max_diag = std::max(max_diag, std::min(vc.gw, vc.gh));
     }
@@ -497,63 +495,15 @@ int launch_sweep(pmk_ctx* ctx, const StoreParams& sp, const SweepArgs& sa) {
     return PMK_OK;
 }
 
-// Multi-GPU partition of a sweep: every rank owns a band of cell rows of every view.  Equal bands leave most ranks idle when the
-// surface covers part of the image (round 1: 0.8 % of the calls on rank 0 of 8), so the bands are cut where the cumulative number
-// of live patches per (reference view, row) -- the sources of the propagatePatch calls -- reaches r / nranks of the view's total;
-// half of the weight stays uniform so that empty regions are still spread out.  Every rank holds the same store, hence computes the
-// same cuts; the result of a sweep does not depend on the cuts at all (ids follow the global task order).
-int balance_bands(pmk_ctx* ctx, const StoreParams& sp) {
-    pmk_store* s = ctx->store;
-    const int nv = ctx->cfg.nviews, nr = s->nranks;
-    s->band.assign((size_t)nv * (nr + 1), 0);
-    for (int v = 0; v < nv; ++v)
-        for (int r = 0; r <= nr; ++r) s->band[(size_t)v * (nr + 1) + r] = (int)((long long)ctx->h_views[v].gh * r / nr);
-    static const int balanced = getenv("PMK_EQUAL_BANDS") ? 0 : 1;
-    if (nr <= 1 || !balanced || s->n <= 0) return PMK_OK;
-    if (s->row_base.empty()) {
-        s->row_base.assign(nv + 1, 0);
-        for (int v = 0; v < nv; ++v) s->row_base[v + 1] = s->row_base[v] + ctx->h_views[v].gh;
-        int rc;
-        if ((rc = dalloc(ctx, &s->row_base_d, nv + 1)) || (rc = dalloc(ctx, &s->rows_d, s->row_base[nv]))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(s->row_base_d, s->row_base.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    const int total_rows = s->row_base[nv];
-    CUDA_TRY(cudaMemsetAsync(s->rows_d, 0, (size_t)total_rows * sizeof(int), ctx->stream));
-    k_row_work<<<(s->n + 255) / 256, 256, 0, ctx->stream>>>(sp, s->n, s->row_base_d, s->rows_d);
-    ctx->launches++;
-    std::vector<int> rows(total_rows);
-    CUDA_TRY(cudaMemcpyAsync(rows.data(), s->rows_d, (size_t)total_rows * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    for (int v = 0; v < nv; ++v) {
-        const int gh = ctx->h_views[v].gh;
-        const int* w = rows.data() + s->row_base[v];
-        long long tot = 0;
-        for (int y = 0; y < gh; ++y) tot += w[y];
-        if (tot <= 0) continue;
-        // weight of row y = w[y] / tot / 2 + 1 / gh / 2, in integer arithmetic: 2 * tot * gh units in all
-        const long long unit_u = tot, unit_w = gh;                  // row y carries w[y] * gh + tot units
-        long long acc = 0;
-        int r = 1;
-        for (int y = 0; y < gh && r < nr; ++y) {
-            acc += (long long)w[y] * unit_w + unit_u;
-            while (r < nr && acc * nr >= 2 * tot * gh * (long long)r) { s->band[(size_t)v * (nr + 1) + r] = y + 1; ++r; }
-        }
-        for (; r < nr; ++r) s->band[(size_t)v * (nr + 1) + r] = gh;
-        s->band[(size_t)v * (nr + 1) + nr] = gh;
-    }
-    return PMK_OK;
-}
-
 // Wavefront steps [step_first, step_first + step_count) of Propagate::propagatePmImage for views [img_first, img_first + nimg):
 // step k carries anti-diagonal k (from the far corner on odd iterations, propagate.cpp:80-86) of every view of the group.
-// (rank, nranks): this GPU only takes the dest cells whose row lies in its band of each view's grid (multi-GPU partition).
+// (rank, nranks): this GPU takes the dest cells of a step whose global number G has G % nranks == rank (multi-GPU partition).
 int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first, int step_count, uint64_t seed, int only_x = -1, const ForceIO* force = nullptr) {
     pmk_store* s = ctx->store;
     StoreParams sp;
     int rc = store_params(ctx, sp, seed);
     if (rc) return rc;
     if (nimg > GROUP_MAX) return fail(PMK_ERR_ARG, "pmk: sweep group too large");
-    if (s->band.size() != (size_t)ctx->cfg.nviews * (s->nranks + 1) && (rc = balance_bands(ctx, sp))) return rc;
     const int inc = (iter % 2 == 1) ? -1 : 1;
     SweepArgs sa;
     std::memset(&sa, 0, sizeof(sa));
@@ -565,28 +515,24 @@ int sweep_views(pmk_ctx* ctx, int iter, int img_first, int nimg, int step_first,
     sa.rem_list = s->rem_list; sa.task_new = s->task_new; sa.stats = s->stats; sa.order = s->order; sa.step_max = s->step_max; sa.cell_ns = s->cell_ns; sa.phase_ns = s->phase_ns;
     int max_steps = 0;
     for (int g = 0; g < nimg; ++g) { const ViewConst& vc = ctx->h_views[img_first + g]; max_steps = std::max(max_steps, vc.gw + vc.gh - 1); }
+    sa.rank = s->rank; sa.nranks = s->nranks;
     for (int k = step_first; k < step_first + step_count && k < max_steps; ++k) {
-        sa.ngroup = 0; sa.ntasks = 0;
-        int gtasks = 0;
+        sa.ngroup = 0;
+        int gtasks = 0;                                              // tasks of the whole step, all ranks
         for (int g = 0; g < nimg; ++g) {
             const ViewConst& vc = ctx->h_views[img_first + g];
             const int gw = vc.gw, gh = vc.gh, ndiag = gw + gh - 1;
             if (k >= ndiag) continue;
             const int d = inc > 0 ? k : ndiag - 1 - k;
-            // rows of this rank's band
-            const int ylo = s->band[(size_t)(img_first + g) * (s->nranks + 1) + s->rank], yhi = s->band[(size_t)(img_first + g) * (s->nranks + 1) + s->rank + 1];
-            const int gxlo = std::max(0, d - gh + 1), gxhi = std::min(gw - 1, d);             // the whole anti-diagonal
-            int xlo = std::max(gxlo, d - yhi + 1), xhi = std::min(gxhi, d - ylo);             // this rank's band of it
+            int xlo = std::max(0, d - gh + 1), xhi = std::min(gw - 1, d);                    // the whole anti-diagonal
             if (only_x >= 0) { xlo = std::max(xlo, only_x); xhi = std::min(xhi, only_x); }   // a single dest cell (pmk_propagate_forced)
-            const int goff = gtasks;
-            gtasks += gxhi - gxlo + 1;
             if (xhi < xlo) continue;
             const int m = sa.ngroup++;
-            sa.g_img[m] = img_first + g; sa.g_diag[m] = d; sa.g_xlo[m] = xlo; sa.g_off[m] = sa.ntasks;
-            sa.g_gxlo[m] = gxlo; sa.g_goff[m] = goff;
-            sa.ntasks += xhi - xlo + 1;
+            sa.g_img[m] = img_first + g; sa.g_diag[m] = d; sa.g_xlo[m] = xlo; sa.g_off[m] = gtasks;
+            gtasks += xhi - xlo + 1;
         }
-        sa.g_off[sa.ngroup] = sa.ntasks;
+        sa.g_off[sa.ngroup] = gtasks;
+        sa.ntasks = gtasks > s->rank ? (gtasks - s->rank + s->nranks - 1) / s->nranks : 0;   // global tasks G with G % nranks == rank
         if (sa.ntasks <= 0 && s->nranks <= 1) continue;
         if (sa.ntasks > s->max_tasks) return fail(PMK_ERR_CAPACITY, "pmk: sweep step exceeds the staging capacity");
         {

@@ -37,12 +37,13 @@ struct ForceIO {
 };
 
 struct SweepArgs {
-    // dest cells of this step: for group member g, view g_img[g], cells (g_xlo[g] + t, g_diag[g] - g_xlo[g] - t),
-    // t in [0, g_off[g + 1] - g_off[g]); task index = g_off[g] + t
-    int ngroup, ntasks, inc;
+    // dest cells of this step, enumerated over the whole step (every view of the group, every cell of its anti-diagonal): for group
+    // member g, view g_img[g], cells (g_xlo[g] + t, g_diag[g] - g_xlo[g] - t), t in [0, g_off[g + 1] - g_off[g]); global task = g_off[g] + t.
+    // Multi-GPU: rank r of n takes the global tasks G with G % n == r (interleaved: neighbouring cells of a diagonal go to different GPUs,
+    // so heavy regions spread evenly); its local task L stands for G = L * n + r.  ids and creation numbers follow the global order.
+    int ngroup, ntasks, inc;               // ntasks = LOCAL tasks of this rank
+    int rank, nranks;
     int g_img[GROUP_MAX], g_diag[GROUP_MAX], g_xlo[GROUP_MAX], g_off[GROUP_MAX + 1];
-    // the same enumeration without the row-band restriction (multi-GPU: ids and creation numbers follow THIS order on every rank)
-    int g_gxlo[GROUP_MAX], g_goff[GROUP_MAX];
     int iter;                              // Propagate::run(iter)
     int jitter_mode;                       // 0: the reference's four constant draws (propagate.cpp:139-141), 1: Philox per try
     float jitter[4];
@@ -58,6 +59,14 @@ struct SweepArgs {
     unsigned long long* phase_ns;          // optional [8]: warp time by phase of a try (profiling, pmk_debug_phase_times): generatePatch + computeNcc,
                                            // preProcess, refinePatch, postProcess, its store-reading tail, waiting for the turn / commit, tries, refined tries
 };
+
+__device__ __forceinline__ int sweep_global_task(const SweepArgs& sa, int task) { return task * sa.nranks + sa.rank; }
+// group member of global task G (linear scan: the group is the number of views swept together, at most GROUP_MAX)
+__device__ __forceinline__ int sweep_group_of(const SweepArgs& sa, int G) {
+    int g = 0;
+    while (g + 1 < sa.ngroup && G >= sa.g_off[g + 1]) ++g;
+    return g;
+}
 
 struct SweepScratch {                  // per warp
     int l_snap[LKEEP];                 // snapshot of the dest cell's list the try was evaluated against
@@ -184,11 +193,10 @@ __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const Swee
         const int task = base + threadIdx.x;
         int est = 0;
         if (task < sa.ntasks) {
-            int g = 0;
-            while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+            const int G = sweep_global_task(sa, task), g = sweep_group_of(sa, G);
             const int img = sa.g_img[g];
             const int gw = p.views[img].gw, gh = p.views[img].gh;
-            const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
+            const int x = sa.g_xlo[g] + (G - sa.g_off[g]), y = sa.g_diag[g] - x;
             int nsrc = 0;
             for (int side = 0; side < 2; ++side) {
                 const int sx = side == 0 ? x : x - sa.inc, sy = side == 0 ? y - sa.inc : y;
@@ -221,11 +229,10 @@ __global__ void __launch_bounds__(1024) k4_plan(const StoreParams sp, const Swee
         const int task = base + threadIdx.x;
         if (task >= sa.ntasks) continue;
         // recompute the estimate (cheaper than keeping it: tasks can exceed the block size)
-        int g = 0;
-        while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
+        const int G = sweep_global_task(sa, task), g = sweep_group_of(sa, G);
         const int img = sa.g_img[g];
         const int gw = p.views[img].gw, gh = p.views[img].gh;
-        const int x = sa.g_xlo[g] + (task - sa.g_off[g]), y = sa.g_diag[g] - x;
+        const int x = sa.g_xlo[g] + (G - sa.g_off[g]), y = sa.g_diag[g] - x;
         int nsrc = 0;
         for (int side = 0; side < 2; ++side) {
             const int sx = side == 0 ? x : x - sa.inc, sy = side == 0 ? y - sa.inc : y;
@@ -497,9 +504,7 @@ __global__ void k4_pack_copy(const StoreParams sp, const SweepArgs sa, MsgLayout
             rec[8] = __float_as_int(s.x); rec[9] = __float_as_int(s.y); rec[10] = __float_as_int(s.z); rec[11] = __float_as_int(s.w);
             rec[12] = st.nimg[sid]; rec[13] = st.nvimg[sid];
             const int task = (sid - st.cap) / NEW_MAX;
-            int g = 0;
-            while (g + 1 < sa.ngroup && task >= sa.g_off[g + 1]) ++g;
-            rec[14] = sa.g_goff[g] + (sa.g_xlo[g] + (task - sa.g_off[g]) - sa.g_gxlo[g]);
+            rec[14] = sweep_global_task(sa, task);
             rec[15] = (sid - st.cap) % NEW_MAX;
         }
         const int ni = st.nimg[sid], nv = st.nvimg[sid], mv = st.maxv;
@@ -594,17 +599,6 @@ __global__ void k4_unpack_add(const StoreParams sp, MsgLayout ml, const int* __r
         warp_register_patch(sp, fid, deep, deep, lane);
         __syncwarp();
     }
-}
-
-// Multi-GPU load balance: propagatePatch calls come from patches whose reference view is the swept view, so the live patches per
-// (reference view, cell row) estimate the work of that row.  rows[row_base[v] + y] += 1 per live patch.
-__global__ void k_row_work(const StoreParams sp, int n, const int* __restrict__ row_base, int* __restrict__ rows) {
-    const StoreDev& st = sp.st;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n || st.state[q] != 1 || st.nimg[q] < 1) return;
-    const int v = st.images[(size_t)q * st.maxv];
-    const int y = cell_y(st.cells[(size_t)q * st.maxv]);
-    if (y >= 0 && y < sp.cp.p.views[v].gh) atomicAdd(rows + row_base[v] + y, 1);
 }
 
 // order-independent digest of the live store (replica consistency checks): sum over patches of a hash of coord, ncc and lists

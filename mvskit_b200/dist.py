@@ -30,13 +30,10 @@ def init_comm(ctx: "pmk.Context", dist=None, device=None):
     return rank, world
 
 
-def band_partition(gheight: int, nranks: int):
-    """[(ylo, yhi)] per rank: contiguous row bands that tile [0, gheight) (pmk_band_rows)."""
-    return [pmk.band_rows(gheight, r, nranks) for r in range(nranks)]
-
-
-def step_tasks(gw: int, gh: int, diag: int, ylo: int, yhi: int):
-    """dest cells (x range) of anti-diagonal `diag` whose row lies in [ylo, yhi): the same arithmetic as the sweep driver."""
-    xlo = max(max(0, diag - gh + 1), diag - yhi + 1)
-    xhi = min(min(gw - 1, diag), diag - ylo)
-    return (xlo, xhi) if xhi >= xlo else None
+def step_tasks(gw: int, gh: int, diag: int, rank: int, nranks: int):
+    """dest cells (x, y) of anti-diagonal `diag` of one view that rank `rank` sweeps: the cells of the diagonal are numbered from its
+    smallest x, rank r takes the numbers G with G % nranks == r -- the same arithmetic as the sweep driver (one view per step)."""
+    xlo, xhi = max(0, diag - gh + 1), min(gw - 1, diag)
+    cells = [(x, diag - x) for x in range(xlo, xhi + 1) if (x - xlo) % nranks == rank]
+    assert len(cells) == pmk.step_share(max(0, xhi - xlo + 1), rank, nranks)
+    return cells

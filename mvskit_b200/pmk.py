@@ -229,7 +229,8 @@ class Context:
     def pack_hypotheses(coord, normal, views, nviews):
         """float4 / float4 / int32 records -> the byte-lean layout of pmk_ncc_eval_packed (w = 1 / w = 0 implied, byte view ids)."""
         views, nviews = np.asarray(views), np.asarray(nviews)
-        assert nviews.min() >= 0 and nviews.max() < 256
+        if nviews.min() < 0 or nviews.max() > min(255, views.shape[1]):
+            raise PmkError("pack_hypotheses: view counts must lie in [0, min(255, row length)]")
         v8 = np.where((views < 0) | (views > 254), 255, views).astype(np.uint8)      # 255 = "no such view" (the call needs nviews <= 255)
         return (np.ascontiguousarray(np.asarray(coord, np.float32)[:, :3]), np.ascontiguousarray(np.asarray(normal, np.float32)[:, :3]),
                 np.ascontiguousarray(v8), np.ascontiguousarray(nviews, np.uint8))
@@ -541,7 +542,8 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
-def band_rows(gheight: int, rank: int, nranks: int):
-    lo, hi = C.c_int(), C.c_int()
-    _chk(lib().pmk_band_rows(gheight, rank, nranks, C.byref(lo), C.byref(hi)))
-    return lo.value, hi.value
+def step_share(step_tasks: int, rank: int, nranks: int) -> int:
+    """How many of a wavefront step's dest cells rank `rank` of `nranks` sweeps (pmk_step_share)."""
+    n = C.c_int()
+    _chk(lib().pmk_step_share(step_tasks, rank, nranks, C.byref(n)))
+    return n.value

@@ -1,4 +1,4 @@
-"""Host-side logic of the N > 1 path on CPU: two gloo processes agree on the NCCL-id broadcast and on a band partition that
+"""Host-side logic of the N > 1 path on CPU: two gloo processes agree on the NCCL-id broadcast and on the interleaved partition that
 tiles every wavefront step exactly once (no GPU, no compute calls)."""
 import os
 import socket
@@ -19,20 +19,15 @@ WORKER = textwrap.dedent("""
     got = pdist.broadcast_bytes(dist, payload, 128)
     assert got == bytes(range(128)), got[:8]
     gw, gh = 80, 60
-    bands = pdist.band_partition(gh, world)
-    ylo, yhi = bands[rank]
     mine = []
     for d in range(gw + gh - 1):
-        t = pdist.step_tasks(gw, gh, d, ylo, yhi)
-        if t:
-            mine += [(x, d - x) for x in range(t[0], t[1] + 1)]
-    assert all(ylo <= y < yhi for _, y in mine)
+        mine += pdist.step_tasks(gw, gh, d, rank, world)
     out = [None] * world
     dist.all_gather_object(out, mine)
     if rank == 0:
         cells = [c for part in out for c in part]
-        assert len(cells) == len(set(cells)) == gw * gh, (len(cells), len(set(cells)))
-        assert bands[0][0] == 0 and bands[-1][1] == gh and all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+        assert len(cells) == len(set(cells)) == gw * gh, (len(cells), len(set(cells)))      # every dest cell exactly once
+        assert abs(len(out[0]) - len(out[1])) <= gw + gh                                    # and evenly
         print("OK", world, len(cells))
     dist.barrier()
     dist.destroy_process_group()

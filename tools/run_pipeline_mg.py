@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Multi-GPU end-to-end run (one process per GPU under torchrun): replicated store, dest cells split into row bands, the step
+"""Multi-GPU end-to-end run (one process per GPU under torchrun): replicated store, the dest cells of every step dealt out to the ranks in turn, the step
 mutations all-gathered over NCCL.  Checks that every replica ends with the same store and (rank 0) that the result equals a
 single-GPU run of the same scene.
    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/run_pipeline_mg.py --config 1 --scale 0.5"""
