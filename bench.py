@@ -483,7 +483,7 @@ def main():
 
     # ---------------- BASELINE metric (2): end-to-end patches/sec, on the configs the north-star names ----------------
     # config 2 (the K1 scene, already resident), then config 3 (DTU-shaped, 49 x 1600x1200, ITER 4) and config 5 (128 x 1920x1080,
-    # ITER 1), each at its stated shape; N > 1: dest-cell rows of every view cut into balanced bands, step mutations gathered (NCCL).
+    # ITER 1), each at its stated shape; N > 1: every step's dest cells dealt out to the ranks in turn, step mutations gathered (NCCL).
     t_bench0 = time.time()
     pipelines, k1_other = [], []
     plan = []

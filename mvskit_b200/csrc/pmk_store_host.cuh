@@ -306,7 +306,7 @@ int small_groups(pmk_ctx* ctx, const StoreParams& sp, int* flags_dev, int* remov
     if ((size_t)nedges > s->adj_cap) {                       // adjacency buffer, grown on demand and kept
         if (s->adj) CUDA_TRY(cudaFree(s->adj));
         s->adj = nullptr; s->adj_cap = 0;
-        const size_t cap = (size_t)nedges + (size_t)nedges / 4 + 1024;
+        const size_t cap = 2 * (size_t)nedges + 1024;        // the store grows ~1.3x per iteration: one allocation serves a whole run
         CUDA_TRY(cudaMalloc((void**)&s->adj, cap * sizeof(int)));
         s->adj_cap = cap;
     }
