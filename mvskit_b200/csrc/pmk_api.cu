@@ -107,7 +107,7 @@ struct pmk_ctx {
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     uint64_t launches = 0;
-    bool k1_attr_done = false;
+    unsigned k1_attr_done = 0;
     std::vector<Scratch> pool;               // staging buffers of the host-pointer entry points
     float* tex_scratch = nullptr;
     float* mat_scratch = nullptr;
@@ -168,10 +168,10 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
               void* incc, void* ncc, void* levels, const unsigned int* ready, unsigned int epoch, int chunk_shift, int packed) {
     const int fstride = ctx->params.tau * K1_FRAME_WORDS + 4;
     const size_t smem = (size_t)K1_WARPS * 32 * fstride * sizeof(float);
-    if (!ctx->k1_attr_done) {
+    if (!(ctx->k1_attr_done & (1u << MINB))) {                     // once per compiled variant
         CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(k1_ncc<WS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        ctx->k1_attr_done = true;
+        ctx->k1_attr_done |= 1u << MINB;
     }
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_ncc<WS, MINB>, K1_WARPS * 32, smem));
@@ -190,7 +190,7 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
 
 int dispatch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const void* views, const void* nviews, int stride,
                 void* incc, void* ncc, void* levels, const unsigned int* ready = nullptr, unsigned int epoch = 0, int chunk_shift = 0, int packed = 0) {
-    static const int minb = getenv("PMK_K1_MINB") ? atoi(getenv("PMK_K1_MINB")) : 4;   // tuning knob: CTAs/SM the kernel is compiled for
+    static const int minb = getenv("PMK_K1_MINB") ? atoi(getenv("PMK_K1_MINB")) : 4;   // tuning knob: CTAs/SM the kernel is compiled for (the 53 KB frame store caps it at 4)
 #ifdef PMK_WS_ONLY
     if (ctx->cfg.wsize == PMK_WS_ONLY) return launch_k1<PMK_WS_ONLY, 4>(ctx, n, coord, normal, views, nviews, stride, incc, ncc, levels, ready, epoch, chunk_shift, packed);
     (void)minb;
