@@ -1,4 +1,4 @@
-"""N > 1 on real GPUs (skipped on a single-GPU box): two ranks, row-band partition, NCCL all-gather of the step mutations.
+"""N > 1 on real GPUs (skipped on a single-GPU box): two ranks, every step's dest cells dealt out to the ranks in turn, NCCL all-gather of the step mutations.
 Every replica must end with the same store, and that store must be the single-GPU store bit for bit."""
 import json
 import os
