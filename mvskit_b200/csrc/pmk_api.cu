@@ -108,6 +108,7 @@ struct pmk_ctx {
     size_t flush_bytes = 0;
     uint64_t launches = 0;
     unsigned k1_attr_done = 0;
+    bool k1_prefetch = false;    // set by upload_views
     std::vector<Scratch> pool;               // staging buffers of the host-pointer entry points
     float* tex_scratch = nullptr;
     float* mat_scratch = nullptr;
@@ -136,6 +137,14 @@ int upload_views(pmk_ctx* ctx) {
     for (int v = 0; v < ctx->cfg.nviews; ++v)
         if (!ctx->view_set[v]) return fail(PMK_ERR_STATE, "pmk: view " + std::to_string(v) + " has not been uploaded (pmk_set_view)");
     CUDA_TRY(cudaMemcpyAsync(ctx->d_views, ctx->h_views.data(), sizeof(ViewConst) * ctx->cfg.nviews, cudaMemcpyHostToDevice, ctx->stream));
+    // K1 prefetches its gathers through L2 when the levels it samples (the working level and coarser) cannot stay L2-resident
+    size_t hot = 0;
+    for (const ViewConst& vc : ctx->h_views)
+        for (int l = ctx->cfg.level; l < ctx->cfg.level + 3 && l < PMK_MAX_LEVELS; ++l) hot += (size_t)vc.w[l] * vc.h[l] * sizeof(Texel);
+    int l2_bytes = 0;
+    cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, ctx->cfg.device);
+    const char* pf = getenv("PMK_K1_PREFETCH");
+    ctx->k1_prefetch = pf ? atoi(pf) != 0 : hot > (size_t)l2_bytes * 3 / 4;
     ctx->views_dirty = false;
     return PMK_OK;
 }
@@ -182,7 +191,7 @@ int launch_k1(pmk_ctx* ctx, int n, const void* coord, const void* normal, const 
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), ctx->stream));
     k1_ncc<WS, MINB><<<grid, K1_WARPS * 32, smem, ctx->stream>>>(ctx->params, n, (const float4*)coord, (const float4*)normal, (const int*)views,
                                                           (const int*)nviews, stride, (float*)incc, (float*)ncc, (int*)levels, ctx->d_counters,
-                                                          ready, epoch, chunk_shift, packed);
+                                                          ready, epoch, chunk_shift, (packed ? 1 : 0) | (ctx->k1_prefetch ? 2 : 0));
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return PMK_OK;

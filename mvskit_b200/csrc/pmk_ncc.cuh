@@ -117,6 +117,31 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask = 0xffffffffu)
 template <int GW>
 __device__ __forceinline__ unsigned group_mask(int lane) { return GW >= 32 ? 0xffffffffu : (((1u << GW) - 1u) << ((lane / GW) * GW)); }
 
+// L2 prefetch of the texels one sampling frame will gather (pyramids that do not fit L2: every gather of phase C would
+// otherwise pay a DRAM round trip inside a dependent chain).  The GW lanes of a group share the frame's bounding box:
+// rows [y0, y1] x texels [x0, x1], one prefetch per 32-byte sector, sectors dealt out over the lanes.  No effect on results.
+template <int WS, int GW>
+__device__ __forceinline__ void prefetch_frame(const Params& p, const float* __restrict__ fr, int col) {
+    const float4 fa = *reinterpret_cast<const float4*>(fr);            // tlx tly dxx dxy
+    const float4 fb = *reinterpret_cast<const float4*>(fr + 4);        // dyx dyy (level | view << 4) weight
+    const int pk = __float_as_int(fb.z);
+    const ViewConst& vc = p.views[pk >> 4];
+    const int lv = pk & 15, W = vc.w[lv], H = vc.h[lv];
+    constexpr float E = (float)(WS - 1);
+    const float ax = E * fa.z, bx = E * fb.x, ay = E * fa.w, by = E * fb.y;
+    const int x0 = max(0, (int)(fa.x + fminf(ax, 0.f) + fminf(bx, 0.f))), x1 = min(W - 1, (int)(fa.x + fmaxf(ax, 0.f) + fmaxf(bx, 0.f)) + 1);
+    const int y0 = max(0, (int)(fa.y + fminf(ay, 0.f) + fminf(by, 0.f))), y1 = min(H - 1, (int)(fa.y + fmaxf(ay, 0.f) + fmaxf(by, 0.f)) + 1);
+    if (x1 < x0 || y1 < y0) return;
+    const char* base = reinterpret_cast<const char*>(vc.img[lv]);
+    const int nr = min(y1 - y0 + 1, 16);
+    for (int t = col; t < nr * 4; t += GW) {
+        const size_t rowb = (size_t)(y0 + (t >> 2)) * W;
+        const size_t b0 = (rowb + x0) * sizeof(Texel), b1 = (rowb + x1 + 1) * sizeof(Texel);
+        const size_t a = (b0 & ~(size_t)31) + 32 * (t & 3);
+        if (a < b1) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + a));
+    }
+}
+
 template <int WS, int MINB>
 __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, int n, const float4* __restrict__ coord,
                                                               const float4* __restrict__ normal, const int* __restrict__ views,
@@ -124,7 +149,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
                                                               float* __restrict__ incc_out, float* __restrict__ ncc_out,
                                                               int* __restrict__ levels_out, unsigned int* __restrict__ next_batch,
                                                               const unsigned int* __restrict__ ready, unsigned int epoch, int chunk_shift,
-                                                              int packed) {
+                                                              int flags) {
+    const int packed = flags & 1;                         // pmk_ncc_eval_packed's wire format
+    const bool prefetch = (flags & 2) != 0;               // pyramid larger than L2: prefetch the next view's footprint while sampling this one
     // packed != 0 (pmk_ncc_eval_packed): coord / normal are rows of 3 floats (w = 1 / w = 0 implied), views rows of `stride` bytes,
     // nviews bytes -- 31 B per hypothesis over PCIe instead of 60; everything downstream is unchanged
     constexpr int NSAMP = WS * WS;
@@ -247,6 +274,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32, MINB) k1_ncc(const Params p, in
             float inv_msd0 = 1.0f;
 #pragma unroll 1
             for (int k = 0; k < p.tau; ++k) {
+                if (prefetch) {                                 // warp-uniform: the frame sampled after this one (next view, or the next pass' first)
+                    if (k + 1 < p.tau) prefetch_frame<WS, GW>(p, row + (k + 1) * K1_FRAME_WORDS, col);
+                    else if (i + 1 < 32 / G) prefetch_frame<WS, GW>(p, row + (size_t)G * fstride, col);
+                }
                 if (!((any_vm >> k) & 1u)) continue;           // warp-uniform
                 const float* fr = row + k * K1_FRAME_WORDS;
                 const float4 fa = *reinterpret_cast<const float4*>(fr);
