@@ -558,7 +558,7 @@ def main():
                     ms_i.append(ctx_i.timer_end())
                 pyr = sum(int(scene_i.width >> l) * int(scene_i.height >> l) * 8 for l in range(4)) * scene_i.nviews
                 k1_other.append({"config_id": cfg_i, "views": scene_i.nviews, "image": f"{scene_i.width}x{scene_i.height}", "pyramid_bytes": pyr,
-                                 "hypotheses_per_step": len(ci), "steps": 10, "ms_per_step": float(np.mean(ms_i)),
+                                 "hypotheses_per_step": len(ci), "steps": 10, "ms_per_step": float(np.mean(ms_i)), "l2_prefetch": os.environ.get("PMK_K1_PREFETCH", "auto (on: sampled levels exceed 3/4 of L2)"),
                                  "value_per_gpu": len(ci) / (float(np.mean(ms_i)) * 1e-3), "unit": UNIT})
                 ctx_i.close()
         except Exception as exc:                      # the headline line must not be lost to the second metric
@@ -590,7 +590,7 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes * N,
                          "kernel": "k1_ncc<7,4>", "algorithmic_bytes_per_eval": algo_bytes, "valid_views_per_eval": valid_views,
                          "layout_bytes_per_eval": layout_bytes, "achieved_layout": per_gpu * layout_bytes / 1e9, "frac_layout": per_gpu * layout_bytes / 1e9 / peak,
-                         "note": "the binding unit is the L1TEX data pipe (85 % of its peak, issue slots 78 %: profiles/r01_k1_ncc_v4_streamed.txt), not HBM: the config-2 pyramid (154 MB) stays L2-resident and measured DRAM traffic is 1.5 % of the algorithmic bytes; achieved / peak / frac keep the SURVEY 8(d) convention (algorithmic bytes against the measured HBM copy peak); k1_other_configs holds the same kernel on the 1-3 GB pyramids of configs 3 and 5", "l1tex_pct_of_peak": 85.0, "issue_slots_pct": 78.0, "peak_source": peak_src,
+                         "note": "the binding unit is the L1TEX data pipe (85 % of its peak, issue slots 78 %: profiles/r01_k1_ncc_v4_streamed.txt), not HBM: the config-2 pyramid (154 MB) stays L2-resident and measured DRAM traffic is 1.5 % of the algorithmic bytes; achieved / peak / frac keep the SURVEY 8(d) convention (algorithmic bytes against the measured HBM copy peak); k1_other_configs holds the same kernel on the 1-3 GB pyramids of configs 3 and 5 (latency-bound on DRAM there; the kernel prefetches the next view's footprint into L2: profiles/r02_k1_ncc_config3_pyramid.txt, r02_k1_prefetch_ab.txt)", "l1tex_pct_of_peak": 85.0, "issue_slots_pct": 78.0, "peak_source": peak_src,
                          "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0)},
         }
         if pipelines:
