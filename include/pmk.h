@@ -275,7 +275,12 @@ int pmk_probe_scales(pmk_ctx* ctx, int n, const float* coord4, const int* images
  * dscale, ascale, -}): the neighbours' store ids in ascending order (ids_out[n][cap], first min(count, cap)) and their number. */
 int pmk_probe_neighbors(pmk_ctx* ctx, int n, const float* coord4, const float* normal4, const float* scal4, const int* images, const int* nimages,
                         int stride, float scale, int margin, int cap, int* ids_out, int* count_out);
-/* PatchManager::removePatch (patch_manager.cpp:303-325) for stored patches (ids in collect order, as pmk_store_get returns them). */
+/* Store ids of the live patches in collect order: ids_out[i] is the store id of the i-th record pmk_store_get returns (= the reference's
+ * m_ppatches[i], patch_manager.cpp:75-104).  Right after pmk_filter_rebuild / pmk_filter the store is compact and ids_out[i] == i; after
+ * pmk_store_add / pmk_propagate / pmk_store_remove it is not.  pmk_store_remove, pmk_store_update_depth_maps, pmk_probe_neighbors,
+ * pmk_store_cell_ids and pmk_store_depth_map all speak store ids. */
+int pmk_store_ids(pmk_ctx* ctx, int nmax, int* ids_out, int* n_out);
+/* PatchManager::removePatch (patch_manager.cpp:303-325) for stored patches, by store id (pmk_store_ids). */
 int pmk_store_remove(pmk_ctx* ctx, int n, const int* ids);
 /* PatchManager::updateDepthMaps (patch_manager.cpp:191-221) for stored patches. */
 int pmk_store_update_depth_maps(pmk_ctx* ctx, int n, const int* ids);

@@ -1693,6 +1693,25 @@ int pmk_probe_neighbors(pmk_ctx* ctx, int n, const float* coord4, const float* n
     return store_check_overflow(ctx);
 }
 
+int pmk_store_ids(pmk_ctx* ctx, int nmax, int* ids_out, int* n_out) {
+    if (!ctx || !n_out || (nmax > 0 && !ids_out)) return fail(PMK_ERR_ARG, "pmk_store_ids: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    int rc = store_init(ctx);
+    if (rc) return rc;
+    if ((rc = store_check_overflow(ctx))) return rc;
+    StoreParams sp;
+    if ((rc = store_params(ctx, sp, 0))) return rc;
+    int nalive = 0;
+    if ((rc = store_order(ctx, sp, &nalive))) return rc;         // live patches first, in collect order: vals2 = their store ids
+    *n_out = nalive;
+    const int n = std::min(nalive, nmax);
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(ids_out, ctx->store->vals2, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return PMK_OK;
+}
+
 int pmk_store_remove(pmk_ctx* ctx, int n, const int* ids) {
     if (!ctx || (n > 0 && !ids)) return fail(PMK_ERR_ARG, "pmk_store_remove: null argument");
     if (n <= 0) return PMK_OK;

@@ -444,9 +444,9 @@ __global__ void k4_apply_add(const StoreParams sp, const int* __restrict__ final
 }  // namespace pmk
 
 // =====================================================================================================================
-// Multi-GPU: the store is replicated, the dest cells of a step are partitioned by row band, and the step's mutations
+// Multi-GPU: the store is replicated, the dest cells of a step are dealt out to the ranks in turn (global task G -> rank G % nranks), and the step's mutations
 // (new patches, removals) travel between the ranks as one fixed-layout message per rank (ncclAllGather over NVLink).
-// Every rank then applies ALL messages in rank order, so ids, creation numbers and grids stay identical everywhere.
+// Every rank then applies ALL messages, so ids, creation numbers and grids stay identical everywhere.
 //   message = int hdr[4] {n_new, n_rem, overflow, 0} | int rem[n_rem] | rec[n_new][16 + 4 * maxv]      (compact: only what the step produced)
 //   record  = coord4, normal4, scal4 (as int bits), nimg, nvimg, global task index, slot in the task,
 //             images[maxv], cells[maxv], vimages[maxv], vcells[maxv]

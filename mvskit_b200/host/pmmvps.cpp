@@ -324,6 +324,20 @@ void PatchManager::collectPatches(const int target) {
         }
         m_ppatches.push_back(pp);
     }
+    m_storeIds.assign(m_ppatches.size(), -1);
+    m_indexOfStoreId.clear();
+    int nid = 0;
+    if (!m_ppatches.empty()) chk(pmk_store_ids(m_pmmvps.m_ctx, (int)m_storeIds.size(), m_storeIds.data(), &nid), "pmk_store_ids");
+    for (int i = 0; i < (int)m_storeIds.size(); ++i) m_indexOfStoreId[m_storeIds[i]] = i;
+}
+
+int PatchManager::storeId(const Patch& patch) const {
+    return (patch.m_id >= 0 && patch.m_id < (int)m_storeIds.size()) ? m_storeIds[patch.m_id] : -1;
+}
+
+Ppatch PatchManager::byStoreId(const int id) const {
+    const auto it = m_indexOfStoreId.find(id);
+    return it == m_indexOfStoreId.end() ? Ppatch() : m_ppatches[it->second];
 }
 
 namespace {
@@ -369,6 +383,44 @@ void PatchManager::computeNcc(Patch& patch) const {                 // patch_man
     float incc = 2.0f, ncc = 0.0f;
     if (n > 0) chk(pmk_ncc_eval(m_pmmvps.m_ctx, 1, c, m, patch.m_images.data(), &n, n, &incc, &ncc, nullptr), "computeNcc");
     patch.m_ncc = ncc;
+}
+
+void PatchManager::computeNcc(vector<Ppatch>& ppatches) const {      // patch_manager.cpp:401-404 over a batch, one K1 launch
+    const int n = (int)ppatches.size();
+    if (n == 0) return;
+    int stride = 1;
+    bool lean = m_nimages <= 255;                                     // byte view ids, 255 = no view
+    for (const Ppatch& pp : ppatches) {
+        stride = std::max(stride, (int)pp->m_images.size());
+        lean = lean && pp->m_coord(3) == 1.0f && pp->m_normal(3) == 0.0f && pp->m_images.size() <= 255;
+        for (int v : pp->m_images) lean = lean && v >= 0 && v < 255;
+    }
+    stride = std::min(stride, 255);
+    vector<float> incc(n, 2.0f), ncc(n, 0.0f);
+    if (lean) {
+        vector<float> c((size_t)n * 3), m((size_t)n * 3);
+        vector<uint8_t> views((size_t)n * stride, 255), counts(n);
+        for (int i = 0; i < n; ++i) {
+            const Patch& p = *ppatches[i];
+            for (int k = 0; k < 3; ++k) { c[3 * (size_t)i + k] = p.m_coord(k); m[3 * (size_t)i + k] = p.m_normal(k); }
+            const int ni = std::min((int)p.m_images.size(), stride);
+            counts[i] = (uint8_t)ni;
+            for (int k = 0; k < ni; ++k) views[(size_t)i * stride + k] = (uint8_t)p.m_images[k];
+        }
+        chk(pmk_ncc_eval_packed(m_pmmvps.m_ctx, n, c.data(), m.data(), views.data(), counts.data(), stride, incc.data(), ncc.data(), nullptr), "computeNcc");
+    } else {
+        vector<float> c((size_t)n * 4), m((size_t)n * 4);
+        vector<int> views((size_t)n * stride, -1), counts(n);
+        for (int i = 0; i < n; ++i) {
+            const Patch& p = *ppatches[i];
+            for (int k = 0; k < 4; ++k) { c[4 * (size_t)i + k] = p.m_coord(k); m[4 * (size_t)i + k] = p.m_normal(k); }
+            const int ni = std::min((int)p.m_images.size(), stride);
+            counts[i] = ni;
+            for (int k = 0; k < ni; ++k) views[(size_t)i * stride + k] = p.m_images[k];
+        }
+        chk(pmk_ncc_eval(m_pmmvps.m_ctx, n, c.data(), m.data(), views.data(), counts.data(), stride, incc.data(), ncc.data(), nullptr), "computeNcc");
+    }
+    for (int i = 0; i < n; ++i) ppatches[i]->m_ncc = ppatches[i]->m_images.empty() ? 0.0f : ncc[i];
 }
 
 void PatchManager::readPatchFile(const string& name) {              // patch_manager.cpp:435-497
@@ -462,12 +514,14 @@ struct PatchRec {
 }  // namespace
 
 void PatchManager::removePatch(const Ppatch& ppatch) {
-    const int id = ppatch->m_id;                                        // collect-order index (collectPatches)
+    const int id = storeId(*ppatch);                                    // m_id is the collect-order index (collectPatches)
+    if (id < 0) { cerr << "removePatch: not a stored patch (collectPatches first)" << endl; return; }
     chk(pmk_store_remove(m_pmmvps.m_ctx, 1, &id), "removePatch");
 }
 
 void PatchManager::updateDepthMaps(Ppatch& ppatch) {
-    const int id = ppatch->m_id;
+    const int id = storeId(*ppatch);
+    if (id < 0) { cerr << "updateDepthMaps: not a stored patch (collectPatches first)" << endl; return; }
     chk(pmk_store_update_depth_maps(m_pmmvps.m_ctx, 1, &id), "updateDepthMaps");
 }
 
@@ -543,7 +597,9 @@ void PatchManager::setScales(Patch& patch) const {
 void PatchManager::sortPatches(vector<Ppatch>& ppatches, const int ascend) const {
     const int npatches = (int)ppatches.size();
     if (npatches == 0) return;
-    for (int n = 0; n < npatches; ++n) if (ppatches[n]->m_ncc < 0.0f) computeNcc(*ppatches[n]);          // :411-415
+    vector<Ppatch> unscored;                                                                              // :411-415, scored in one K1 launch
+    for (int n = 0; n < npatches; ++n) if (ppatches[n]->m_ncc < 0.0f) unscored.push_back(ppatches[n]);
+    computeNcc(unscored);
     if (npatches == 1) return;
     for (int i = 0; i < npatches; ++i)                                                                    // the reference's swap sort, :419-432
         for (int j = i + 1; j < npatches; ++j) {
@@ -564,8 +620,10 @@ void PatchManager::findNeighbors(const Patch& patch, vector<Ppatch>& neighbors, 
         cap = count; ids.resize(cap);
         chk(pmk_probe_neighbors(m_pmmvps.m_ctx, 1, r.c, r.m, r.s, r.images.data(), &r.n, r.n, scale, margin, cap, ids.data(), &count), "findNeighbors");
     }
-    for (int k = 0; k < std::min(count, cap); ++k)
-        if (ids[k] >= 0 && ids[k] < (int)m_ppatches.size()) neighbors.push_back(m_ppatches[ids[k]]);      // ids = m_ppatches indices (collectPatches)
+    for (int k = 0; k < std::min(count, cap); ++k) {                      // store ids -> m_ppatches (collectPatches)
+        const Ppatch pp = byStoreId(ids[k]);
+        if (pp) neighbors.push_back(pp);
+    }
 }
 
 void PatchManager::syncGrids() {
@@ -584,12 +642,14 @@ void PatchManager::syncGrids() {
             vector<vector<Ppatch> >& g = which ? m_vpgrids[v] : m_pgrids[v];
             g.assign(nc, vector<Ppatch>());
             for (int c = 0; c < nc; ++c)
-                for (int k = offs[c]; k < offs[c + 1]; ++k)
-                    if (ids[k] >= 0 && ids[k] < (int)m_ppatches.size()) g[c].push_back(m_ppatches[ids[k]]);
+                for (int k = offs[c]; k < offs[c + 1]; ++k) {
+                    const Ppatch pp = byStoreId(ids[k]);
+                    if (pp) g[c].push_back(pp);
+                }
         }
         const vector<int> dm = depthMap(v);
         m_dpgrids[v].assign(nc, Ppatch());
-        for (int c = 0; c < nc; ++c) if (dm[c] >= 0 && dm[c] < (int)m_ppatches.size()) m_dpgrids[v][c] = m_ppatches[dm[c]];
+        for (int c = 0; c < nc; ++c) if (dm[c] >= 0) m_dpgrids[v][c] = byStoreId(dm[c]);
     }
 }
 

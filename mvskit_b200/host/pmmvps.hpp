@@ -12,6 +12,7 @@
 
 #include <iostream>
 #include <map>
+#include <unordered_map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -133,6 +134,9 @@ public:
     void addPatch(Ppatch& ppatch);                      // setGrids result + registration in the device grids
     void setGrids(Patch& patch);
     void computeNcc(Patch& patch) const;                // K1 on one patch
+    // K1 on a batch in one call: Patch objects are marshalled into the byte-lean wire format of pmk_ncc_eval_packed (3-float coord / normal,
+    // byte view ids, 31 B per patch at 6 views instead of 60) when every patch qualifies, else into the wide one; same scores bit for bit
+    void computeNcc(vector<Ppatch>& ppatches) const;
     void readPatches();
     void readPatches(const int iter);
     void writePatches(const string prefix, bool bExportPLY, bool bExportPatch, bool bExportPSet);
@@ -159,6 +163,10 @@ public:
 
     vector<int> m_gheights, m_gwidths;
     vector<Ppatch> m_ppatches;
+    // Patch::m_id = index in m_ppatches (collect order); the device speaks store ids, which equal the index only right after a rebuild
+    vector<int> m_storeIds;                                               // m_ppatches index -> store id (collectPatches)
+    int storeId(const Patch& patch) const;                                // -1 when the patch is not one collectPatches delivered
+    Ppatch byStoreId(const int id) const;                                 // null when the id is not in m_ppatches
     vector<vector<vector<Ppatch> > > m_pgrids, m_vpgrids;                // [image][cell] (patch_manager.hpp:89-96), filled by syncGrids()
     vector<vector<Ppatch> > m_dpgrids;                                    // [image][cell] (patch_manager.hpp:100-104)
 
@@ -166,6 +174,7 @@ protected:
     void readPatchFile(const string& name);
     PmMvps& m_pmmvps;
     int m_nimages;
+    std::unordered_map<int, int> m_indexOfStoreId;                        // store id -> m_ppatches index
 };
 
 class DepthNormInit {

@@ -461,6 +461,15 @@ class Context:
         _chk(lib().pmk_probe_neighbors(self.h, n, _p(coord), _p(normal), _p(scal), _p(images), _p(nimages), images.shape[1], C.c_float(scale), margin, cap, _p(ids), _p(cnt)))
         return [ids[i, :min(cnt[i], cap)].copy() for i in range(n)], cnt
 
+    def store_ids(self):
+        """Store ids of the live patches in collect order (row i of store_get() is store id ids[i]); arange(n) right after a rebuild."""
+        n = self.store_count()
+        ids = np.zeros(max(n, 1), np.int32)
+        got = C.c_int()
+        _chk(lib().pmk_store_ids(self.h, n, _p(ids), C.byref(got)))
+        assert got.value == n
+        return ids[:n]
+
     def store_remove(self, ids):
         ids = np.ascontiguousarray(ids, np.int32)
         _chk(lib().pmk_store_remove(self.h, len(ids), _p(ids)))

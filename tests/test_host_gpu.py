@@ -81,6 +81,15 @@ def test_pmmvps_run_end_to_end(scene_dir, small_scene):
     assert np.quantile(z, 0.9) <= 2.0e-3, np.quantile(z, [0.5, 0.9, 0.99])
 
 
+@pytest.mark.gpu
+def test_patch_manager_pass_throughs_of_the_host_mirror(scene_dir):
+    """`pmmvps_b200 <prefix> --selftest`: the C++ mirror's PatchManager methods on the loaded seeds -- one-patch computeNcc (wide call) against the
+    batched computeNcc (Patch objects marshalled into the byte-lean wire format) bit for bit, sortPatches, setScales, isVisible0, findNeighbors,
+    removePatch / updateDepthMaps by collect index on a store that is not in collect order, syncGrids."""
+    r = subprocess.run([_exe(), scene_dir, "--selftest"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "selftest ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
 def test_patch_file_round_trip_matches_what_the_reference_reads(scene_dir, reflib, tmp_path):
     """The mirror's Patch stream operators (patch.cpp:31-88 format) on CPU: parse the seed file, write it back, and compare the
     records with what the reference's own readPatches got from the same file."""

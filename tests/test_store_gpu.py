@@ -596,6 +596,29 @@ def test_patch_manager_pass_throughs(ctx, reflib, populated, small_scene):
         assert np.array_equal(ctx.store_depth_map(v), reflib.depth_map(v)), v
 
 
+def test_store_ids_translate_collect_order_to_store_ids(ctx, populated):
+    """pmk_store_ids: row i of pmk_store_get is store id ids[i].  Records added in a shuffled order sit in the store in that order, so the
+    ids are a non-trivial permutation until a rebuild compacts the store; removal by store id takes out exactly the rows asked for."""
+    g = populated
+    rng = np.random.RandomState(4)
+    perm = rng.permutation(g.n)
+    ctx.set_depth(0)
+    ctx.store_clear()
+    ctx.store_add(g.coord[perm], g.normal[perm], g.scal[perm], g.images[perm], g.nimages[perm])
+    ctx.set_depth(1)
+    got, ids = ctx.store_get(), ctx.store_ids()
+    assert got.n == g.n and sorted(ids.tolist()) == list(range(g.n)) and not np.array_equal(ids, np.arange(g.n))
+    assert_bits_equal(got.coord, g.coord[perm][ids], "row i of store_get is the record added as number ids[i]")
+    kill_rows = np.sort(rng.choice(g.n, 50, replace=False))
+    ctx.store_remove(ids[kill_rows])
+    left = ctx.store_get()
+    keep = np.setdiff1d(np.arange(g.n), kill_rows)
+    assert left.n == g.n - 50
+    assert_bits_equal(left.coord, got.coord[keep], "exactly the chosen rows are gone, the order of the others is unchanged")
+    assert ctx.filter_rebuild(0) == left.n
+    assert np.array_equal(ctx.store_ids(), np.arange(left.n))
+
+
 def test_ply_colours_match_write_ply(ctx, reflib, populated, tmp_path):
     """PatchManager::writePly's per-patch colour (patch_manager.cpp:566-581: mean over m_images of Image::getColor at the projection,
     rounded) -- the device's pmk_store_colors against the PLY file the reference itself writes from the same store."""
