@@ -13,8 +13,8 @@
 //   * Optim::check (optim.cpp:300-323) -> computeGain one warp per registration, findNeighbors one warp per view with a
 //     CTA-wide hash table, filterQuad on the first warp.
 // The list logic (addImages, constraintImages, sortImages, ...) stays on warp 0 and is tiny.  The kernel needs <= 80 registers
-// (the monolith needed 254), runs 3 CTAs x 8 warps per SM, and a dest cell's chain of tries is ~6x shorter, which is what
-// bounds a wavefront step.
+// (the monolith needed 254), runs 3 CTAs x 8 warps per SM, and a dest cell's chain of tries -- which is what bounds a wavefront
+// step -- is about half as long (measured on config 2: Propagate::run 6.5 s -> 3.2-3.5 s; DESIGN.md section 4 has the phase times).
 #pragma once
 
 #include "pmk_sweep.cuh"
